@@ -1,0 +1,154 @@
+/*
+ * ppodash_b200 -- C ABI of the B200 (sm_100a) kernels behind the PPO-Dash training hot path.
+ *
+ * The reference (Sohojoe/ppo-dash) is pure Python/PyTorch and has no FFI of its own; the
+ * drop-in boundary is its Python class API.  Each entry point below replaces
+ * the torch-op sequence of one reference function; the Python classes in ppodash_b200/ call
+ * them through ctypes (INTEGRATION.md shows the binding).  Paths are relative to
+ *   PKG = ppo-dash-training/pytorch-a2c-ppo-acktr-gail/a2c_ppo_acktr
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (torch's current stream); calls only enqueue
+ *     work: they never allocate, never synchronise, never touch the host copy of the data;
+ *   - return value: 0 on success, a positive cudaError_t value if CUDA reported an error,
+ *     a negative PPD_E* value for bad arguments; ppd_last_error() returns a message;
+ *   - all arithmetic is fp32 unless stated; int64 is used for actions and permutations
+ *     (PKG/storage.py:26, torch.randperm).
+ */
+#ifndef PPODASH_B200_H
+#define PPODASH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPD_ABI_VERSION 1
+#define PPD_EINVAL (-1)    /* bad argument (null pointer, negative size, unsupported shape) */
+#define PPD_EWORKSPACE (-2) /* workspace too small */
+
+int ppd_abi_version(void);
+const char* ppd_last_error(void);
+/* Number of this library's kernels launched by the calling thread since the last reset. */
+int64_t ppd_launch_count(void);
+void ppd_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Returns / GAE                          replaces RolloutStorage.compute_returns, PKG/storage.py:82-121
+ * rewards [T,N]; value_preds, masks, bad_masks, returns [T+1,N]; next_value [N].
+ * One env per lane, time split into per-warp chunks that are combined as an affine scan
+ * X_t = a_t X_{t+1} + c_t; inside a chunk the reference's operation order is replayed.
+ * Side effects as in the reference: use_gae -> value_preds[T] = next_value (storage.py:90,108),
+ * returns[T] untouched; otherwise returns[T] = next_value (storage.py:101,118).
+ * gamma*gae_lambda is formed in double and rounded once, as Python does in the reference.
+ */
+int ppd_compute_returns(const float* rewards, float* value_preds, const float* masks,
+                        const float* bad_masks, float* returns, const float* next_value,
+                        int T, int N, double gamma, double gae_lambda,
+                        int use_gae, int use_proper_time_limits, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Advantage statistics                    replaces PKG/algo/ppo.py:35-37
+ * moments[3] (double, device) = { sum(adv), sum(adv^2), count } with adv = returns - value_preds
+ * over the first n = T*N elements.  Split in two so that a data-parallel caller can
+ * all-reduce the three doubles between the calls.
+ * stats[2] (float, device) = { mean, unbiased_std + 1e-5 }.
+ */
+size_t ppd_advantage_moments_workspace(int64_t n);
+int ppd_advantage_moments(const float* returns, const float* value_preds, int64_t n,
+                          double* moments, void* workspace, size_t workspace_bytes, void* stream);
+int ppd_advantage_finalize(const double* moments, float* stats, void* stream);
+/* adv_out[i] = (returns[i] - value_preds[i] - mean) / (std + 1e-5) */
+int ppd_advantage_normalize(const float* returns, const float* value_preds, int64_t n,
+                            const float* stats, float* adv_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Minibatch gathers        replace RolloutStorage.feed_forward_generator (PKG/storage.py:123-160)
+ *                          and RolloutStorage.recurrent_generator   (PKG/storage.py:162-223)
+ * Source fields are the time-major storage buffers ([T(+1), N, ...], row r = t*N + n).
+ *  feed-forward: output row i  <- source row perm[mb_start + i],        i in [0, rows)
+ *  recurrent   : output row t*E + j <- source row t*N + perm[env_start + j]; hidden state only
+ *                at t = 0 -> hxs_out [E, hxs_row]
+ * Any (src,dst) pair may be NULL to skip that field.  Advantages: if `adv` is non-NULL it is
+ * gathered like the other fields; otherwise, if `adv_stats` is non-NULL, the normalised
+ * advantage (returns - value_preds - stats[0]) / stats[1] is computed on the fly.
+ * `*_out_ld` is the output row stride in elements (0 = dense), so a caller can gather the
+ * vector obs straight into a padded feature matrix.
+ */
+typedef struct ppd_gather_desc {
+    const float* obs;          float* obs_out;          int64_t obs_row;   /* elems per row: C*H*W */
+    const float* vobs;         float* vobs_out;         int64_t vobs_row;  int64_t vobs_out_ld;
+    const float* hxs;          float* hxs_out;          int64_t hxs_row;
+    const int64_t* actions;    int64_t* actions_out;    int64_t actions_row;
+    const float* value_preds;  float* value_preds_out;
+    const float* returns;      float* returns_out;
+    const float* masks;        float* masks_out;
+    const float* logp;         float* logp_out;
+    const float* adv;          float* adv_out;
+    const float* adv_stats;
+} ppd_gather_desc;
+
+int ppd_gather_feed_forward(const ppd_gather_desc* d, const int64_t* perm, int64_t mb_start,
+                            int64_t rows, int T, int N, void* stream);
+int ppd_gather_recurrent(const ppd_gather_desc* d, const int64_t* env_perm, int64_t env_start,
+                         int E, int T, int N, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused PPO loss, forward + backward      replaces PKG/algo/ppo.py:61-81 and the Categorical
+ *                                         log-prob / entropy of PKG/distributions.py:23-25,66-68
+ * z [B, ldz]: columns 0..A-1 = action logits, column A = value prediction (the heads GEMM
+ * writes both).  Per row: log-softmax, log-prob of the taken action, entropy, ratio, clipped
+ * surrogate, clipped value loss; and the closed-form gradient dz [B, ldz] of
+ *   loss = value_loss*value_coef + action_loss - entropy*entropy_coef
+ * with every mean taken over `global_rows` rows (= B on one GPU; sum of B over ranks when the
+ * minibatch is sharded, so that summing dz-derived gradients over ranks gives the global mean).
+ * loss_out[3] (device) = { value_loss, action_loss, dist_entropy } contributions of these B rows
+ * (already divided by global_rows).  logp_out / entropy_out may be NULL.
+ */
+size_t ppd_ppo_loss_workspace(int64_t B);
+int ppd_ppo_loss_fwd_bwd(const float* z, int ldz, int A, const int64_t* actions,
+                         const float* old_logp, const float* adv, const float* old_values,
+                         const float* returns, int64_t B, int64_t global_rows,
+                         float clip_param, float value_coef, float entropy_coef,
+                         int use_clipped_value_loss,
+                         float* dz, float* logp_out, float* entropy_out, float* loss_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* Forward only: log-prob of `actions`, per-row entropy and (if mode_out) the arg-max action.
+ * Used by Policy.act / evaluate_actions (PKG/model.py:54-79). */
+int ppd_categorical_eval(const float* z, int ldz, int A, const int64_t* actions, int64_t B,
+                         float* logp_out, float* entropy_out, int64_t* mode_out, float* probs_out,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Gradient-norm clip + Adam over one flat buffer     replaces PKG/algo/ppo.py:82-84
+ *   total_norm = ||grads||_2 ; coef = min(1, max_norm / (total_norm + 1e-6)) (skipped if max_norm <= 0)
+ *   torch.optim.Adam (no amsgrad / weight decay): m = lerp(m, g, 1-b1); v = v*b2 + (1-b2) g^2;
+ *   p -= (lr / (1-b1^step)) * m / (sqrt(v)/sqrt(1-b2^step) + eps)
+ * `step` is the 1-based optimiser step.  grad_norm_out (device float, may be NULL) receives total_norm.
+ * If loss_in/loss_acc are non-NULL, loss_acc[0..2] += loss_in[0..2] (running sums over minibatches,
+ * read once per update instead of three .item() syncs per minibatch, ppo.py:86-88).
+ */
+size_t ppd_clip_adam_workspace(int64_t n);
+int ppd_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                       int64_t n, int64_t step, double lr, double beta1, double beta2, double eps,
+                       double max_norm, float* grad_norm_out, const float* loss_in, float* loss_acc,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Running observation normalisation     replaces VecNormalize._obfilt (PKG/envs.py:208-217) +
+ *                                       baselines RunningMeanStd.update (third party, unpinned)
+ * obs [N, F] fp32; mean, var [F] float64 (device, updated in place when update != 0);
+ * count_host = running count BEFORE this batch (the caller adds N afterwards).
+ * out [N, F] = clip((obs - mean) / sqrt(var + epsilon), -clipob, clipob) using the UPDATED moments.
+ */
+int ppd_obs_rms_update_normalize(const float* obs, int N, int64_t F, double* mean, double* var,
+                                 double count_host, int update, double epsilon, double clipob,
+                                 float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPODASH_B200_H */

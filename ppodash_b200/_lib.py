@@ -1,0 +1,124 @@
+"""ctypes binding of libppodash_b200.so (the C ABI declared in include/ppodash_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a kernel entry point is called
+with a tensor that is not on a CUDA device, this module raises.  Build the library with
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C ppodash_b200/csrc``.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libppodash_b200.so")
+
+
+class PpdError(RuntimeError):
+    pass
+
+
+class GatherDesc(Structure):
+    """Mirror of ``ppd_gather_desc``."""
+    _fields_ = [
+        ("obs", c_void_p), ("obs_out", c_void_p), ("obs_row", c_int64),
+        ("vobs", c_void_p), ("vobs_out", c_void_p), ("vobs_row", c_int64), ("vobs_out_ld", c_int64),
+        ("hxs", c_void_p), ("hxs_out", c_void_p), ("hxs_row", c_int64),
+        ("actions", c_void_p), ("actions_out", c_void_p), ("actions_row", c_int64),
+        ("value_preds", c_void_p), ("value_preds_out", c_void_p),
+        ("returns", c_void_p), ("returns_out", c_void_p),
+        ("masks", c_void_p), ("masks_out", c_void_p),
+        ("logp", c_void_p), ("logp_out", c_void_p),
+        ("adv", c_void_p), ("adv_out", c_void_p),
+        ("adv_stats", c_void_p),
+    ]
+
+
+_P = c_void_p
+_PROTOTYPES = {
+    "ppd_abi_version": (c_int, []),
+    "ppd_last_error": (c_char_p, []),
+    "ppd_launch_count": (c_int64, []),
+    "ppd_reset_launch_count": (None, []),
+    "ppd_compute_returns": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_double, c_double, c_int, c_int, _P]),
+    "ppd_advantage_moments_workspace": (c_size_t, [c_int64]),
+    "ppd_advantage_moments": (c_int, [_P, _P, c_int64, _P, _P, c_size_t, _P]),
+    "ppd_advantage_finalize": (c_int, [_P, _P, _P]),
+    "ppd_advantage_normalize": (c_int, [_P, _P, c_int64, _P, _P, _P]),
+    "ppd_gather_feed_forward": (c_int, [POINTER(GatherDesc), _P, c_int64, c_int64, c_int, c_int, _P]),
+    "ppd_gather_recurrent": (c_int, [POINTER(GatherDesc), _P, c_int64, c_int, c_int, c_int, _P]),
+    "ppd_ppo_loss_workspace": (c_size_t, [c_int64]),
+    "ppd_ppo_loss_fwd_bwd": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, c_int64, c_int64, c_float, c_float,
+                                     c_float, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "ppd_categorical_eval": (c_int, [_P, c_int, c_int, _P, c_int64, _P, _P, _P, _P, _P]),
+    "ppd_clip_adam_workspace": (c_size_t, [c_int64]),
+    "ppd_clip_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_double, c_double, c_double, c_double,
+                                   c_double, _P, _P, _P, _P, c_size_t, _P]),
+    "ppd_obs_rms_update_normalize": (c_int, [_P, c_int, c_int64, _P, _P, c_double, c_int, c_double, c_double,
+                                             _P, _P]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names declared in include/ppodash_b200.h that the library must export."""
+    return sorted(_PROTOTYPES)
+
+
+def register(name, restype, argtypes):
+    """Used by the other binding modules (network kernels) to add prototypes."""
+    _PROTOTYPES[name] = (restype, argtypes)
+    if _lib is not None:
+        fn = getattr(_lib, name)
+        fn.restype, fn.argtypes = restype, argtypes
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PpdError(
+                f"{LIB_PATH} not found: the CUDA extension is not built. ppodash_b200 has no CPU or "
+                "PyTorch fallback; run `make -C ppodash_b200/csrc` (needs nvcc, sm_100a).")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _PROTOTYPES.items():
+            fn = getattr(handle, name)          # AttributeError here == header/library mismatch
+            fn.restype, fn.argtypes = restype, argtypes
+        if handle.ppd_abi_version() != 1:
+            raise PpdError("libppodash_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().ppd_last_error().decode("utf-8", "replace")
+        raise PpdError(f"{what or 'ppodash_b200'} failed (code {rc}): {msg}")
+
+
+def ptr(t, dtype=None):
+    """Device pointer of a CUDA tensor (None -> NULL).  Refuses CPU tensors: no fallback."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("expected a torch.Tensor")
+    if not t.is_cuda:
+        raise PpdError("ppodash_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count():
+    return int(lib().ppd_launch_count())
+
+
+def reset_launch_count():
+    lib().ppd_reset_launch_count()

@@ -1,0 +1,197 @@
+"""RolloutStorage: drop-in for the reference class (PKG/storage.py:9-223).
+
+Same constructor, public tensor attributes, ``insert`` / ``after_update`` /
+``compute_returns`` / ``feed_forward_generator`` / ``recurrent_generator``.
+The buffers are ordinary time-major torch tensors ([T(+1), N, ...], fp32, int64
+actions) so callers can keep indexing and mutating them (run.py:140-141,172-175,237);
+the three heavy methods enqueue sm_100a kernels from libppodash_b200.so on the
+current CUDA stream and never synchronise:
+
+  compute_returns          -> ppd_compute_returns           (storage.py:82-121)
+  feed_forward_generator   -> ppd_gather_feed_forward       (storage.py:123-160)
+  recurrent_generator      -> ppd_gather_recurrent          (storage.py:162-223)
+
+The minibatch permutations are drawn on the host from torch's global CPU generator with the
+same call the reference makes (one ``torch.randperm`` per epoch), so with equal seeds the index
+sets are bit-identical to the reference's.  There is no CPU fallback for the kernels.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GatherDesc, check, lib, ptr, stream_ptr
+
+
+class FusedAdvantages:
+    """Handle that lets the generators compute the normalised advantage
+    (returns - value_preds - mean) / (std + 1e-5) on the fly (ppo.py:35-37) instead of
+    gathering it from a materialised [T, N, 1] tensor.  ``stats`` is a 2-float device tensor."""
+
+    def __init__(self, stats):
+        self.stats = stats
+
+
+def _flatten_helper(T, N, _tensor):
+    return _tensor.view(T * N, *_tensor.size()[2:])
+
+
+class RolloutStorage(object):
+    def __init__(self, num_steps, num_processes, obs_shape, vector_obs_shape, action_space,
+                 recurrent_hidden_state_size):
+        self.obs = torch.zeros(num_steps + 1, num_processes, *obs_shape)
+        self.vector_obs = torch.zeros(num_steps + 1, num_processes, *vector_obs_shape)
+        self.recurrent_hidden_states = torch.zeros(num_steps + 1, num_processes, recurrent_hidden_state_size)
+        self.rewards = torch.zeros(num_steps, num_processes, 1)
+        self.value_preds = torch.zeros(num_steps + 1, num_processes, 1)
+        self.returns = torch.zeros(num_steps + 1, num_processes, 1)
+        self.action_log_probs = torch.zeros(num_steps, num_processes, 1)
+        if action_space.__class__.__name__ == 'Discrete':
+            action_shape = 1
+        else:
+            action_shape = action_space.shape[0]
+        self.actions = torch.zeros(num_steps, num_processes, action_shape)
+        if action_space.__class__.__name__ == 'Discrete':
+            self.actions = self.actions.long()
+        self.masks = torch.ones(num_steps + 1, num_processes, 1)
+        # 0 where the episode ended because of a time limit rather than a true terminal state
+        self.bad_masks = torch.ones(num_steps + 1, num_processes, 1)
+        self.num_steps = num_steps
+        self.step = 0
+
+    _FIELDS = ("obs", "vector_obs", "recurrent_hidden_states", "rewards", "value_preds", "returns",
+               "action_log_probs", "actions", "masks", "bad_masks")
+
+    def to(self, device):
+        for name in self._FIELDS:
+            setattr(self, name, getattr(self, name).to(device, non_blocking=True))
+
+    def half(self):
+        # The reference's experimental --half_precision path (storage.py:48-58) also casts the int64
+        # actions to fp16, which breaks Categorical.log_prob; no published run used it.
+        raise NotImplementedError("half-precision rollout storage is out of scope (SURVEY.md section 5)")
+
+    def insert(self, obs, vector_obs, recurrent_hidden_states, actions, action_log_probs,
+               value_preds, rewards, masks, bad_masks):
+        s = self.step
+        self.obs[s + 1].copy_(obs, non_blocking=True)
+        self.vector_obs[s + 1].copy_(vector_obs, non_blocking=True)
+        self.recurrent_hidden_states[s + 1].copy_(recurrent_hidden_states, non_blocking=True)
+        self.actions[s].copy_(actions, non_blocking=True)
+        self.action_log_probs[s].copy_(action_log_probs, non_blocking=True)
+        self.value_preds[s].copy_(value_preds, non_blocking=True)
+        self.rewards[s].copy_(rewards, non_blocking=True)
+        self.masks[s + 1].copy_(masks, non_blocking=True)
+        self.bad_masks[s + 1].copy_(bad_masks, non_blocking=True)
+        self.step = (self.step + 1) % self.num_steps
+
+    def after_update(self):
+        self.obs[0].copy_(self.obs[-1])
+        self.vector_obs[0].copy_(self.vector_obs[-1])
+        self.recurrent_hidden_states[0].copy_(self.recurrent_hidden_states[-1])
+        self.masks[0].copy_(self.masks[-1])
+        self.bad_masks[0].copy_(self.bad_masks[-1])
+
+    # ------------------------------------------------------------------ returns / GAE
+    def compute_returns(self, next_value, use_gae, gamma, gae_lambda, use_proper_time_limits=True):
+        T, N = self.rewards.size(0), self.rewards.size(1)
+        dev = self.rewards.device
+        nv = next_value.detach().to(device=dev, dtype=torch.float32).reshape(N).contiguous()
+        check(lib().ppd_compute_returns(
+            ptr(self.rewards, torch.float32), ptr(self.value_preds, torch.float32),
+            ptr(self.masks, torch.float32), ptr(self.bad_masks, torch.float32),
+            ptr(self.returns, torch.float32), ptr(nv), T, N, float(gamma), float(gae_lambda),
+            int(bool(use_gae)), int(bool(use_proper_time_limits)), stream_ptr(dev)), "compute_returns")
+
+    # ------------------------------------------------------------------ generators
+    def _out(self, rows, like, dtype=None):
+        return torch.empty((rows,) + tuple(like.shape[2:]), dtype=dtype or like.dtype, device=like.device)
+
+    def _gather(self, mode, perm_dev, start, rows, E, advantages, out=None):
+        """Fill one minibatch; returns the 9-tuple in the reference's order (storage.py:159-160)."""
+        T, N = self.rewards.size(0), self.rewards.size(1)
+        dev = self.obs.device
+        o = out or {}
+        obs_b = o.get("obs") if "obs" in o else self._out(rows, self.obs)
+        vobs_b = o.get("vector_obs") if "vector_obs" in o else self._out(rows, self.vector_obs)
+        hrows = rows if mode == "ff" else E
+        hxs_b = o.get("hxs") if "hxs" in o else self._out(hrows, self.recurrent_hidden_states)
+        act_b = self._out(rows, self.actions)
+        val_b = self._out(rows, self.value_preds)
+        ret_b = self._out(rows, self.returns)
+        msk_b = self._out(rows, self.masks)
+        lp_b = self._out(rows, self.action_log_probs)
+        d = GatherDesc()
+        obs_row = self.obs[0, 0].numel()
+        d.obs, d.obs_out, d.obs_row = ptr(self.obs, torch.float32), ptr(obs_b), obs_row
+        vrow = self.vector_obs[0, 0].numel()
+        if vrow > 0:
+            d.vobs, d.vobs_out, d.vobs_row = ptr(self.vector_obs, torch.float32), vobs_b.data_ptr(), vrow
+            d.vobs_out_ld = int(o.get("vector_obs_ld", 0))
+        d.hxs, d.hxs_out = ptr(self.recurrent_hidden_states, torch.float32), ptr(hxs_b)
+        d.hxs_row = self.recurrent_hidden_states.size(-1)
+        d.actions, d.actions_out, d.actions_row = ptr(self.actions, torch.int64), ptr(act_b), self.actions.size(-1)
+        d.value_preds, d.value_preds_out = ptr(self.value_preds, torch.float32), ptr(val_b)
+        d.returns, d.returns_out = ptr(self.returns, torch.float32), ptr(ret_b)
+        d.masks, d.masks_out = ptr(self.masks, torch.float32), ptr(msk_b)
+        d.logp, d.logp_out = ptr(self.action_log_probs, torch.float32), ptr(lp_b)
+        adv_b = None
+        keep = None
+        if isinstance(advantages, FusedAdvantages):
+            adv_b = torch.empty(rows, 1, dtype=torch.float32, device=dev)
+            d.adv_stats, d.adv_out = ptr(advantages.stats, torch.float32), ptr(adv_b)
+        elif advantages is not None:
+            keep = advantages.detach()
+            if keep.dtype != torch.float32 or not keep.is_contiguous():
+                keep = keep.float().contiguous()
+            adv_b = torch.empty(rows, 1, dtype=torch.float32, device=dev)
+            d.adv, d.adv_out = ptr(keep), ptr(adv_b)
+        if mode == "ff":
+            rc = lib().ppd_gather_feed_forward(ctypes.byref(d), ptr(perm_dev, torch.int64), start, rows, T, N,
+                                               stream_ptr(dev))
+        else:
+            rc = lib().ppd_gather_recurrent(ctypes.byref(d), ptr(perm_dev, torch.int64), start, E, T, N,
+                                            stream_ptr(dev))
+        check(rc, "minibatch gather")
+        return obs_b, vobs_b, hxs_b, act_b, val_b, ret_b, msk_b, lp_b, adv_b
+
+    @staticmethod
+    def _perm_to_device(perm, device):
+        if not torch.device(device).type == "cuda":
+            raise _lib.PpdError("RolloutStorage generators need the storage on a CUDA device "
+                                "(call rollouts.to(device) first; there is no CPU fallback)")
+        return perm.pin_memory().to(device, non_blocking=True)
+
+    def feed_forward_generator(self, advantages, num_mini_batch=None, mini_batch_size=None):
+        num_steps, num_processes = self.rewards.size()[0:2]
+        batch_size = num_processes * num_steps
+        if mini_batch_size is None:
+            assert batch_size >= num_mini_batch, (
+                "PPO requires the number of processes ({}) "
+                "* number of steps ({}) = {} "
+                "to be greater than or equal to the number of PPO mini batches ({})."
+                "".format(num_processes, num_steps, num_processes * num_steps, num_mini_batch))
+            mini_batch_size = batch_size // num_mini_batch
+        # SubsetRandomSampler(range(batch_size)) draws exactly this (CPU global generator); BatchSampler
+        # with drop_last=True then cuts it into consecutive blocks (storage.py:138-142).
+        perm = torch.randperm(batch_size)
+        perm_dev = self._perm_to_device(perm, self.obs.device)
+        for k in range(batch_size // mini_batch_size):
+            yield self._gather("ff", perm_dev, k * mini_batch_size, mini_batch_size, 0, advantages)
+
+    def recurrent_generator(self, advantages, num_mini_batch):
+        num_processes = self.rewards.size(1)
+        assert num_processes >= num_mini_batch, (
+            "PPO requires the number of processes ({}) "
+            "to be greater than or equal to the number of "
+            "PPO mini batches ({}).".format(num_processes, num_mini_batch))
+        num_envs_per_batch = num_processes // num_mini_batch
+        perm = torch.randperm(num_processes)                       # storage.py:169
+        perm_dev = self._perm_to_device(perm, self.obs.device)
+        T = self.num_steps
+        for start_ind in range(0, num_processes, num_envs_per_batch):
+            if start_ind + num_envs_per_batch > num_processes:
+                # the reference runs off the end of `perm` here (storage.py:182)
+                raise IndexError("index {} is out of bounds for dimension 0 with size {}".format(
+                    num_processes, num_processes))
+            yield self._gather("rec", perm_dev, start_ind, T * num_envs_per_batch, num_envs_per_batch, advantages)

@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Kernel microbenchmarks (CUDA events on the launching stream, L2 flushed between iterations).
+Prints one JSON object per kernel: achieved algorithmic GB/s against MEASURED_PEAKS.json."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ppodash_b200 import _lib, synthetic  # noqa: E402
+from ppodash_b200.storage import FusedAdvantages, RolloutStorage  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    _flush.add_(1)
+
+
+def time_kernel(fn, iters=10, warmup=3, flush=True):
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            flush_l2()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = n
+        self.shape = ()
+
+
+def bench_gae(T, N, proper=False):
+    L = _lib.lib()
+    r = torch.rand(T, N, 1, device=DEV)
+    v = torch.randn(T + 1, N, 1, device=DEV)
+    m = (torch.rand(T + 1, N, 1, device=DEV) > 0.002).float()
+    b = torch.ones(T + 1, N, 1, device=DEV)
+    ret = torch.zeros(T + 1, N, 1, device=DEV)
+    nv = torch.randn(N, 1, device=DEV)
+    s = _lib.stream_ptr()
+
+    def fn():
+        _lib.check(L.ppd_compute_returns(r.data_ptr(), v.data_ptr(), m.data_ptr(), b.data_ptr(), ret.data_ptr(),
+                                         nv.data_ptr(), T, N, 0.99, 0.95, 1, int(proper), s))
+    med, best = time_kernel(fn)
+    bytes_ = (20 if proper else 16) * T * N + 4 * N
+    return dict(kernel="returns_scan", T=T, N=N, proper=proper, ms=med, ms_best=best,
+                steps_per_s=T * N / (med * 1e-3), gbs=bytes_ / (med * 1e-3) / 1e9)
+
+
+def bench_gather(T, N, C, V, recurrent, nmb):
+    H = 512 if recurrent else 1
+    st = RolloutStorage(T, N, (C, 84, 84), [V], Discrete(8), H)
+    st.to(DEV)
+    st.obs.normal_()
+    stats = torch.tensor([0.0, 1.0], device=DEV)
+    row = C * 84 * 84 * 4 + V * 4 + 8 + 5 * 4
+    out = {}
+
+    def fn():
+        gen = st.recurrent_generator(FusedAdvantages(stats), nmb) if recurrent else st.feed_forward_generator(FusedAdvantages(stats), nmb)
+        for mb in gen:
+            out["x"] = mb
+    med, best = time_kernel(fn, iters=5, warmup=2)
+    samples = (T * N // nmb) * nmb if not recurrent else T * (N // nmb) * nmb
+    bytes_ = 2 * row * samples + (N // nmb) * nmb * H * 8 * (1 if recurrent else 0)
+    return dict(kernel="gather_" + ("recurrent" if recurrent else "ff"), T=T, N=N, C=C, nmb=nmb, ms_epoch=med,
+                ms_best=best, samples_per_s=samples / (med * 1e-3), gbs=bytes_ / (med * 1e-3) / 1e9)
+
+
+def bench_adam(n):
+    L = _lib.lib()
+    p = torch.randn(n, device=DEV); g = torch.randn(n, device=DEV) * 1e-3
+    m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
+    ws = torch.empty(L.ppd_clip_adam_workspace(n), dtype=torch.uint8, device=DEV)
+    s = _lib.stream_ptr()
+
+    def fn():
+        _lib.check(L.ppd_clip_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 3, 1e-4, 0.9, 0.999,
+                                        1e-5, 0.5, None, None, None, ws.data_ptr(), ws.numel(), s))
+    med, best = time_kernel(fn)
+    return dict(kernel="clip_adam", n=n, ms=med, ms_best=best, gbs=32 * n / (med * 1e-3) / 1e9)
+
+
+def main():
+    peak, how = peak_hbm()
+    res = []
+    for T, N in ((512, 32), (512, 1024), (2048, 4096)):
+        res.append(bench_gae(T, N))
+    res.append(bench_gae(2048, 4096, proper=True))
+    res.append(bench_gather(512, 32, 3, 15, True, 8))
+    res.append(bench_gather(128, 32, 4, 0, False, 4))
+    res.append(bench_gather(512, 256, 3, 15, True, 8))
+    res.append(bench_gather(512, 256, 3, 15, False, 8))
+    res.append(bench_adam(2464393))
+    res.append(bench_adam(1 << 26))
+    for r in res:
+        r["frac_of_hbm_peak"] = r["gbs"] / peak
+        r["peak"] = how
+        print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()
