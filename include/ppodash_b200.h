@@ -39,16 +39,21 @@ void ppd_reset_launch_count(void);
 /* ---------------------------------------------------------------------------------------
  * Returns / GAE                          replaces RolloutStorage.compute_returns, PKG/storage.py:82-121
  * rewards [T,N]; value_preds, masks, bad_masks, returns [T+1,N]; next_value [N].
- * One env per lane, time split into per-warp chunks that are combined as an affine scan
- * X_t = a_t X_{t+1} + c_t; inside a chunk the reference's operation order is replayed.
+ * One env per lane, time split into per-warp chunks that are combined as a single-pass chained
+ * affine scan X_t = a_t X_{t+1} + c_t; inside a chunk the reference's operation order is replayed.
+ * `workspace` (>= ppd_compute_returns_workspace bytes, 16-byte aligned) holds the inter-CTA carries;
+ * it must be zero-filled once when allocated and may then be reused by every later call on the
+ * same stream (each launch re-arms it).
  * Side effects as in the reference: use_gae -> value_preds[T] = next_value (storage.py:90,108),
  * returns[T] untouched; otherwise returns[T] = next_value (storage.py:101,118).
  * gamma*gae_lambda is formed in double and rounded once, as Python does in the reference.
  */
+size_t ppd_compute_returns_workspace(int T, int N);
 int ppd_compute_returns(const float* rewards, float* value_preds, const float* masks,
                         const float* bad_masks, float* returns, const float* next_value,
                         int T, int N, double gamma, double gae_lambda,
-                        int use_gae, int use_proper_time_limits, void* stream);
+                        int use_gae, int use_proper_time_limits,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Advantage statistics                    replaces PKG/algo/ppo.py:35-37
@@ -147,6 +152,75 @@ int ppd_clip_adam_step(float* params, const float* grads, float* exp_avg, float*
 int ppd_obs_rms_update_normalize(const float* obs, int N, int64_t F, double* mean, double* var,
                                  double count_host, int update, double epsilon, double clipob,
                                  float* out, void* stream);
+
+/* =======================================================================================
+ * Policy network (PKG/model.py).  "fp32" mode: SIMT fp32 kernels, used for the 1e-5 parity gate.
+ * ======================================================================================= */
+
+/* ---------------------------------------------------------------------------------------
+ * GEMM family                 replaces nn.Conv2d / nn.Linear / GRU input projection forward and
+ *                             backward (PKG/model.py:176-180,186-188,90; PKG/distributions.py:64)
+ *   C[i,j] (+)= sum_kk OpA(i,kk) * OpB(j,kk)
+ *   OpA(i,kk) = a_kmajor ? A[i*lda + kk] : A[kk*lda + i];  OpB likewise with b_kmajor / ldb.
+ * Epilogue (in this order): + bias[j]; ReLU if relu; zero where mask[i*ldm + j] <= 0 (ReLU
+ * backward against the saved activation); C += result if accumulate, else C = result.
+ * Long contractions are split over CTAs and reduced in a fixed order (deterministic).
+ */
+typedef struct ppd_gemm_args {
+    const float* A; int64_t lda; int a_kmajor;
+    const float* B; int64_t ldb; int b_kmajor;
+    float* C; int64_t ldc;
+    int64_t I, J, KK;
+    const float* bias;
+    const float* mask; int64_t ldm;
+    int relu; int accumulate;
+} ppd_gemm_args;
+size_t ppd_sgemm_workspace(int64_t I, int64_t J, int64_t KK);
+int ppd_sgemm(const ppd_gemm_args* g, void* workspace, size_t workspace_bytes, void* stream);
+/* out[j] (+)= sum_i X[i*ld + j]  (bias gradients) */
+size_t ppd_colsum_workspace(int64_t I, int64_t J);
+int ppd_colsum(const float* X, int64_t ld, int64_t I, int64_t J, float* out, int accumulate,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Convolution lowering (conv = im2col + GEMM; activations NHWC between the convolutions).
+ *   im2col_nchw: x [B,C,H,W] -> cols [B*OH*OW, ld], patch index (c,ky,kx)   (conv1 reads the obs)
+ *   im2col_nhwc: x [B,H,W,C] -> cols [B*OH*OW, ld], patch index (ky,kx,c)
+ *   col2im_nhwc: transpose of im2col_nhwc (gather form, no atomics); if act_mask != NULL the
+ *                result is zeroed where act_mask[b,y,x,c] <= 0 (ReLU backward fused)
+ *   batched_transpose: y[b,c,r] = x[b,r,c]  (NHWC <-> NCHW of the last conv activation, so the
+ *                flatten order equals the reference's, PKG/model.py:10-12)
+ */
+int ppd_im2col_nchw(const float* x, int B, int C, int H, int W, int kh, int kw, int stride,
+                    float* cols, int64_t ld, void* stream);
+int ppd_im2col_nhwc(const float* x, int B, int H, int W, int C, int kh, int kw, int stride,
+                    float* cols, int64_t ld, void* stream);
+int ppd_col2im_nhwc(const float* dcols, int64_t ld, int B, int H, int W, int C, int kh, int kw, int stride,
+                    const float* act_mask, float* dx, void* stream);
+int ppd_batched_transpose(const float* x, int64_t B, int R, int Cc, float* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * GRU with mask reset            replaces NNBase._forward_gru, PKG/model.py:111-166
+ *   h_t = GRU(x_t, h_{t-1} * m_t), gate order r,z,n; gi = x W_ih^T + b_ih is computed by the caller
+ *   for all T steps (one GEMM).  Rows are time-major: row = t*E + e.
+ * forward : gi [T*E,3H], h0 [E,H], masks [T*E], w_hh [3H,H], b_hh [3H] -> hs [T*E,H] (all hidden
+ *           states = the GRU output), h_last [E,H] (may be NULL); save_* [T*E,H] (r, z, n and
+ *           W_hn h + b_hn) are needed by backward, pass NULL for inference.
+ * backward: dhs [T*E,H] = dL/d hs -> dgi [T*E,3H] (gradient wrt gi) and dghn [T*E,H] (gradient wrt
+ *           the hidden-side n pre-activation; the r,z hidden-side gradients equal dgi's); dh0
+ *           [E,H] may be NULL.  Weight gradients follow as GEMMs over all T*E rows.
+ * One persistent cooperative launch runs all T steps (one grid barrier per step).
+ * masked_prev: hm[t*E+e,:] = (t ? hs[(t-1)*E+e,:] : h0[e,:]) * masks[t*E+e]  (operand of dW_hh).
+ */
+int ppd_gru_forward(const float* gi, const float* h0, const float* masks, const float* w_hh,
+                    const float* b_hh, int T, int E, int H, float* hs, float* h_last,
+                    float* save_r, float* save_z, float* save_n, float* save_ghn, void* stream);
+int ppd_gru_backward(const float* dhs, const float* masks, const float* w_hh, const float* h0,
+                     const float* hs, const float* save_r, const float* save_z, const float* save_n,
+                     const float* save_ghn, int T, int E, int H, float* dgi, float* dghn, float* dh0,
+                     void* stream);
+int ppd_gru_masked_prev(const float* hs, const float* h0, const float* masks, int T, int E, int H,
+                        float* hm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -34,13 +34,28 @@ class GatherDesc(Structure):
     ]
 
 
+class GemmArgs(Structure):
+    """Mirror of ``ppd_gemm_args``."""
+    _fields_ = [
+        ("A", c_void_p), ("lda", c_int64), ("a_kmajor", c_int),
+        ("B", c_void_p), ("ldb", c_int64), ("b_kmajor", c_int),
+        ("C", c_void_p), ("ldc", c_int64),
+        ("I", c_int64), ("J", c_int64), ("KK", c_int64),
+        ("bias", c_void_p),
+        ("mask", c_void_p), ("ldm", c_int64),
+        ("relu", c_int), ("accumulate", c_int),
+    ]
+
+
 _P = c_void_p
 _PROTOTYPES = {
     "ppd_abi_version": (c_int, []),
     "ppd_last_error": (c_char_p, []),
     "ppd_launch_count": (c_int64, []),
     "ppd_reset_launch_count": (None, []),
-    "ppd_compute_returns": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_double, c_double, c_int, c_int, _P]),
+    "ppd_compute_returns_workspace": (c_size_t, [c_int, c_int]),
+    "ppd_compute_returns": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_double, c_double, c_int, c_int,
+                                    _P, c_size_t, _P]),
     "ppd_advantage_moments_workspace": (c_size_t, [c_int64]),
     "ppd_advantage_moments": (c_int, [_P, _P, c_int64, _P, _P, c_size_t, _P]),
     "ppd_advantage_finalize": (c_int, [_P, _P, _P]),
@@ -56,6 +71,17 @@ _PROTOTYPES = {
                                    c_double, _P, _P, _P, _P, c_size_t, _P]),
     "ppd_obs_rms_update_normalize": (c_int, [_P, c_int, c_int64, _P, _P, c_double, c_int, c_double, c_double,
                                              _P, _P]),
+    "ppd_sgemm_workspace": (c_size_t, [c_int64, c_int64, c_int64]),
+    "ppd_sgemm": (c_int, [POINTER(GemmArgs), _P, c_size_t, _P]),
+    "ppd_colsum_workspace": (c_size_t, [c_int64, c_int64]),
+    "ppd_colsum": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, _P, c_size_t, _P]),
+    "ppd_im2col_nchw": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P]),
+    "ppd_im2col_nhwc": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P]),
+    "ppd_col2im_nhwc": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "ppd_batched_transpose": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    "ppd_gru_forward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "ppd_gru_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "ppd_gru_masked_prev": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
 }
 
 _lib = None
@@ -114,6 +140,21 @@ def ptr(t, dtype=None):
 
 def stream_ptr(device=None):
     return torch.cuda.current_stream(device).cuda_stream
+
+
+_workspaces = {}
+
+
+def workspace(nbytes, device, tag="default", zero=False):
+    """Grow-only uint8 scratch buffer per (device, tag); kernels that need scratch get it from here
+    so that the C ABI itself never allocates.  ``zero=True``: zero-filled when (re)allocated."""
+    key = (str(device), tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        alloc = torch.zeros if zero else torch.empty
+        buf = alloc(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
 
 
 def launch_count():

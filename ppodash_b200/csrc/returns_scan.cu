@@ -1,19 +1,26 @@
-// Returns / GAE as a chunked affine scan, one env per lane.
+// Returns / GAE as a single-pass chained affine scan, one env per lane.
 // Replaces RolloutStorage.compute_returns (PKG/storage.py:82-121).  Compile with -fmad=false:
 // the in-chunk replay keeps the reference's operation order (separate mul / add roundings).
 //
 // Layout: every field is time-major [T(+1), N]; for fixed t the N envs are contiguous, so a
 // warp reading lane = env issues one 128-byte request per (field, t).
 //
-// Work split: CTA = 32 envs x kWarps warps.  Time is consumed from the end in super-chunks of
-// kWarps*kSteps steps; inside a super-chunk warp w owns kSteps consecutive steps.
+// Work split: CTA = 32 envs x one time segment of kWarps*kSteps steps; warp w owns kSteps
+// consecutive steps.  The recurrence X_t = a_t X_{t+1} + c_t is an affine map per step, so a
+// run of steps composes to X_out = P * X_in + Q:
 //   phase A  each lane loads its kSteps x {r, V, m, (b)} into registers (all loads issued up
-//            front -> kSteps*3 requests in flight per thread), evaluates its chunk with zero
-//            incoming carry and publishes the chunk's affine map (P, Q): X_out = P*X_in + Q
-//   phase B  every lane walks the <= kWarps maps of its env column in order to get the carry
-//            entering its own chunk (and the carry leaving the super-chunk)
-//   phase C  the chunk is replayed from the true carry with the reference's exact op order
-//            and returns[t] is written.
+//            front -> ~3*kSteps requests in flight per thread), evaluates its chunk with zero
+//            incoming carry, publishes its (P, Q) to shared memory; warp 0 folds the kWarps maps
+//            into the segment's (P, Q) and publishes that to global memory (value + epoch in
+//            one 8-byte store)
+//   look-back the carry entering the segment is the fold of the maps of all LATER segments of
+//            the same env block; each warp polls a contiguous range of them (they were
+//            scheduled earlier because segments are handed out latest-first through an atomic
+//            ticket, and their maps do not depend on any carry, so there is no serial chain
+//            between CTAs)
+//   phase B  fold the in-CTA maps to get the carry entering this warp's chunk
+//   phase C  replay the chunk from the true carry with the reference's exact op order and
+//            write returns[t].
 // Each input element is read from HBM exactly once and each output written once:
 // 16 B/step (GAE), 20 B/step with bad_masks.
 #include "ppd_common.cuh"
@@ -21,32 +28,72 @@
 namespace {
 
 constexpr int kSteps = 16;
-constexpr int kWarps = 16;
+constexpr int kWarps = 8;
+constexpr int kSeg = kSteps * kWarps;     // steps per CTA
+constexpr int kHeaderBytes = 128;
+
+// Workspace header.  The workspace must be zero-filled once when it is allocated; every launch
+// leaves it ready for the next one (the last CTA to finish resets the ticket and bumps the epoch),
+// so no memset is enqueued per call.
+struct Header {
+    unsigned ticket;   // next CTA ticket of the running launch
+    unsigned done;     // CTAs that finished
+    unsigned epoch;    // number of completed launches; flags of the running launch carry epoch + 1
+};
+
+// A segment's affine map is published per lane as two 8-byte words {P, epoch} and {Q, epoch}:
+// an aligned 8-byte store is single-copy atomic, so a reader that sees the epoch sees the value
+// (no separate flag, no fence, one round trip per look-back step).
+__device__ __forceinline__ void publish(uint2* slot, float P, float Q, unsigned epoch) {
+    uint4 v = make_uint4(__float_as_uint(P), epoch, __float_as_uint(Q), epoch);
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(slot), "r"(v.x), "r"(v.y) : "memory");
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(slot + 1), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void wait_map(const uint2* slot, unsigned epoch, float& P, float& Q) {
+    uint2 a, b;
+    do {
+        asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(slot) : "memory");
+        asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(b.x), "=r"(b.y) : "l"(slot + 1) : "memory");
+    } while (a.y != epoch || b.y != epoch);
+    P = __uint_as_float(a.x);
+    Q = __uint_as_float(b.x);
+}
 
 template <bool GAE, bool PROPER>
 __global__ void __launch_bounds__(kWarps * 32)
 returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ value_preds,
                     const float* __restrict__ masks, const float* __restrict__ bad_masks,
                     float* __restrict__ returns, const float* __restrict__ next_value,
-                    int T, int N, float g, float gl) {
+                    int T, int N, float g, float gl, int nblk, int nseg,
+                    Header* __restrict__ hdr, uint2* __restrict__ seg_pq) {
     __shared__ float sP[kWarps][32];
     __shared__ float sQ[kWarps][32];
+    __shared__ float lP[kWarps][32];
+    __shared__ float lQ[kWarps][32];
+    __shared__ unsigned s_ticket, s_epoch;
+    if (threadIdx.x == 0) {
+        s_epoch = *reinterpret_cast<volatile unsigned*>(&hdr->epoch) + 1u;
+        s_ticket = atomicAdd(&hdr->ticket, 1u);
+    }
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    const int ticket = (int)s_ticket;
+    const int seg = ticket / nblk;            // 0 = latest segment in time (handed out first)
+    const int blk = ticket - seg * nblk;
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
-    const int n = blockIdx.x * 32 + lane;
+    const int n = blk * 32 + lane;
     const bool live = n < N;
     const float nv = live ? next_value[n] : 0.f;
-    float carry = GAE ? 0.f : nv;   // X at t_hi: gae accumulator (storage.py:91,109) or returns[T]
-    if (w == 0 && live) {
+    const int t_hi = T - seg * kSeg;          // exclusive upper step of this segment
+    if (seg == 0 && w == 0 && live) {
         if (GAE) value_preds[(size_t)T * N + n] = nv;   // storage.py:90,108
         else     returns[(size_t)T * N + n] = nv;       // storage.py:101,118
     }
 
-    for (int t_hi = T; t_hi > 0; t_hi -= kWarps * kSteps) {
-        const int t0 = t_hi - (w + 1) * kSteps;   // first step of this warp's chunk (may be < 0)
-        // per-step registers kept from phase A to phase C
-        float f0[kSteps], f1[kSteps], f2[kSteps], f3[kSteps];
-        // ---- loads (all independent, issued before any use)
+    const int t0 = t_hi - (w + 1) * kSteps;   // first step of this warp's chunk (may be < 0)
+    float f0[kSteps], f1[kSteps], f2[kSteps], f3[kSteps];
+    {
         float r_[kSteps], v_[kSteps + 1], m_[kSteps], b_[kSteps];
 #pragma unroll
         for (int i = 0; i < kSteps; ++i) {
@@ -54,12 +101,12 @@ returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ value
             const bool ok = live && t >= 0;
             const size_t o = (size_t)(ok ? t : 0) * N + (live ? n : 0);
             r_[i] = ok ? __ldg(rewards + o) : 0.f;
-            m_[i] = ok ? __ldg(masks + o + N) : 1.f;            // m_{t+1}
-            if (PROPER) b_[i] = ok ? __ldg(bad_masks + o + N) : 1.f;   // b_{t+1}
+            m_[i] = ok ? __ldg(masks + o + N) : 1.f;                    // m_{t+1}
+            if (PROPER) b_[i] = ok ? __ldg(bad_masks + o + N) : 1.f;    // b_{t+1}
             if (GAE || PROPER) v_[i] = ok ? value_preds[o] : 0.f;
         }
         if (GAE) {
-            const int tt = t0 + kSteps;   // V_{t+1} of the chunk's last step
+            const int tt = t0 + kSteps;       // V_{t+1} of the chunk's last step
             v_[kSteps] = (tt >= T) ? nv : ((live && tt >= 0) ? value_preds[(size_t)tt * N + n] : 0.f);
         }
         // ---- phase A: chunk with zero carry
@@ -87,54 +134,112 @@ returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ value
                 }
             }
         }
-        __syncthreads();   // previous super-chunk's phase B readers are done with sP/sQ
         sP[w][lane] = P;
         sQ[w][lane] = Q;
-        __syncthreads();
-        // ---- phase B: carry entering this warp's chunk, and leaving the super-chunk
-        float x = carry, mine = carry;
+    }
+    __syncthreads();
+    // ---- publish this segment's map (warp 0): fold of the kWarps chunk maps, latest chunk first
+    if (w == 0 && seg + 1 < nseg) {
+        float Ps = 1.f, Qs = 0.f;
 #pragma unroll
         for (int ww = 0; ww < kWarps; ++ww) {
-            if (ww == w) mine = x;
-            x = sP[ww][lane] * x + sQ[ww][lane];
+            Qs = sP[ww][lane] * Qs + sQ[ww][lane];
+            Ps = sP[ww][lane] * Ps;
         }
-        carry = x;
-        // ---- phase C: replay with the reference's exact operation order
-        x = mine;
+        publish(seg_pq + (((size_t)blk * nseg + seg) * 32 + lane) * 2, Ps, Qs, epoch);
+    }
+    // ---- look-back: maps of the later segments 0..seg-1, split over the warps in contiguous
+    //      ranges (composition is associative, not commutative), then folded in order
+    {
+        const int per = (seg + kWarps - 1) / kWarps;
+        const int s_begin = min(seg, w * per), s_end = min(seg, s_begin + per);
+        float Pw = 1.f, Qw = 0.f;
+        for (int s = s_begin; s < s_end; ++s) {
+            float Pm, Qm;
+            wait_map(seg_pq + (((size_t)blk * nseg + s) * 32 + lane) * 2, epoch, Pm, Qm);
+            Qw = Pm * Qw + Qm;
+            Pw = Pm * Pw;
+        }
+        lP[w][lane] = Pw;
+        lQ[w][lane] = Qw;
+    }
+    __syncthreads();
+    float x = GAE ? 0.f : nv;   // X at T: gae accumulator (storage.py:91,109) or returns[T]
 #pragma unroll
-        for (int i = kSteps - 1; i >= 0; --i) {
-            const int t = t0 + i;
-            if (t < 0) continue;
-            float out;
-            if (GAE) {
-                x = f0[i] + f1[i] * x;                     // gae = delta + gamma*lambda*m*gae
-                if (PROPER) x = x * f3[i];                 // gae = gae * bad_mask   (storage.py:98)
-                out = x + f2[i];                           // returns = gae + V_t
-            } else {
-                x = (x * g) * f1[i] + f0[i];               // storage.py:120-121
-                if (PROPER) x = x * f3[i] + (1.f - f3[i]) * f2[i];   // storage.py:104-105
-                out = x;
-            }
-            if (live) __stcs(returns + (size_t)t * N + n, out);
+    for (int ww = 0; ww < kWarps; ++ww) x = lP[ww][lane] * x + lQ[ww][lane];
+    // ---- phase B: carry entering this warp's chunk
+    for (int ww = 0; ww < w; ++ww) x = sP[ww][lane] * x + sQ[ww][lane];
+    // ---- phase C: replay with the reference's exact operation order
+#pragma unroll
+    for (int i = kSteps - 1; i >= 0; --i) {
+        const int t = t0 + i;
+        if (t < 0) continue;
+        float out;
+        if (GAE) {
+            x = f0[i] + f1[i] * x;                     // gae = delta + gamma*lambda*m*gae
+            if (PROPER) x = x * f3[i];                 // gae = gae * bad_mask   (storage.py:98)
+            out = x + f2[i];                           // returns = gae + V_t
+        } else {
+            x = (x * g) * f1[i] + f0[i];               // storage.py:120-121
+            if (PROPER) x = x * f3[i] + (1.f - f3[i]) * f2[i];   // storage.py:104-105
+            out = x;
+        }
+        if (live) __stcs(returns + (size_t)t * N + n, out);
+    }
+    // ---- last CTA out re-arms the workspace for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(&hdr->done, 1u);
+        if (prev == gridDim.x - 1) {
+            hdr->ticket = 0;
+            hdr->done = 0;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned*>(&hdr->epoch) = epoch;
         }
     }
 }
 
+struct Plan { int nblk, nseg; size_t total; };
+Plan plan(int T, int N) {
+    Plan p;
+    p.nblk = (N + 31) / 32;
+    p.nseg = (T + kSeg - 1) / kSeg;
+    p.total = kHeaderBytes + (size_t)p.nblk * p.nseg * 32 * 2 * sizeof(uint2);
+    return p;
+}
+
 }  // namespace
+
+extern "C" size_t ppd_compute_returns_workspace(int T, int N) {
+    if (T <= 0 || N <= 0) return 0;
+    return plan(T, N).total;
+}
 
 extern "C" int ppd_compute_returns(const float* rewards, float* value_preds, const float* masks,
                                    const float* bad_masks, float* returns, const float* next_value,
                                    int T, int N, double gamma, double gae_lambda, int use_gae,
-                                   int use_proper_time_limits, void* stream) {
-    PPD_REQUIRE(rewards && value_preds && masks && returns && next_value, "null pointer");
+                                   int use_proper_time_limits, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+    PPD_REQUIRE(rewards && value_preds && masks && returns && next_value && workspace, "null pointer");
     PPD_REQUIRE(!use_proper_time_limits || bad_masks, "bad_masks required with use_proper_time_limits");
     PPD_REQUIRE(T > 0 && N > 0, "T and N must be positive");
+    const Plan p = plan(T, N);
+    if (workspace_bytes < p.total) {
+        ppd::set_error("ppd_compute_returns: workspace too small");
+        return PPD_EWORKSPACE;
+    }
+    PPD_REQUIRE((uintptr_t)workspace % 16 == 0, "workspace must be 16-byte aligned");
+    PPD_REQUIRE((int64_t)p.nblk * p.nseg <= 0x7fffffffLL, "grid too large");
     const float g = (float)gamma;
     const float gl = (float)(gamma * gae_lambda);
-    dim3 grid((N + 31) / 32), block(kWarps * 32);
     cudaStream_t s = ppd::as_stream(stream);
+    char* ws = reinterpret_cast<char*>(workspace);
+    Header* hdr = reinterpret_cast<Header*>(ws);
+    uint2* pq = reinterpret_cast<uint2*>(ws + kHeaderBytes);
+    dim3 grid((unsigned)(p.nblk * p.nseg)), block(kWarps * 32);
 #define PPD_LAUNCH(G, P) \
-    returns_scan_kernel<G, P><<<grid, block, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl)
+    returns_scan_kernel<G, P><<<grid, block, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, \
+                                                     T, N, g, gl, p.nblk, p.nseg, hdr, pq)
     if (use_gae) { if (use_proper_time_limits) PPD_LAUNCH(true, true); else PPD_LAUNCH(true, false); }
     else         { if (use_proper_time_limits) PPD_LAUNCH(false, true); else PPD_LAUNCH(false, false); }
 #undef PPD_LAUNCH

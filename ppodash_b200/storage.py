@@ -97,11 +97,15 @@ class RolloutStorage(object):
         T, N = self.rewards.size(0), self.rewards.size(1)
         dev = self.rewards.device
         nv = next_value.detach().to(device=dev, dtype=torch.float32).reshape(N).contiguous()
+        if dev.type != "cuda":
+            raise _lib.PpdError("compute_returns needs the storage on a CUDA device (no CPU fallback)")
+        ws = _lib.workspace(lib().ppd_compute_returns_workspace(T, N), dev, "returns", zero=True)
         check(lib().ppd_compute_returns(
             ptr(self.rewards, torch.float32), ptr(self.value_preds, torch.float32),
             ptr(self.masks, torch.float32), ptr(self.bad_masks, torch.float32),
             ptr(self.returns, torch.float32), ptr(nv), T, N, float(gamma), float(gae_lambda),
-            int(bool(use_gae)), int(bool(use_proper_time_limits)), stream_ptr(dev)), "compute_returns")
+            int(bool(use_gae)), int(bool(use_proper_time_limits)), ws.data_ptr(), ws.numel(),
+            stream_ptr(dev)), "compute_returns")
 
     # ------------------------------------------------------------------ generators
     def _out(self, rows, like, dtype=None):

@@ -47,7 +47,7 @@ def test_no_cpu_fallback():
 def test_bad_arguments_return_error_codes():
     from ppodash_b200 import _lib
     L = _lib.lib()
-    rc = L.ppd_compute_returns(None, None, None, None, None, None, 4, 4, 0.99, 0.95, 1, 0, None)
+    rc = L.ppd_compute_returns(None, None, None, None, None, None, 4, 4, 0.99, 0.95, 1, 0, None, 0, None)
     assert rc == -1 and b"null" in L.ppd_last_error()
     assert L.ppd_advantage_moments_workspace(1000) >= 16
     assert L.ppd_clip_adam_workspace(1 << 20) > 256

@@ -1,0 +1,185 @@
+"""GPU parity of the network building blocks (fp32 mode) through the C ABI: GEMM family, column
+sums, conv lowering, GRU forward/backward.  Comparison: torch-CPU fp32 (the reference's own ops)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import policy as o_pol  # noqa: E402
+from ppodash_b200 import _lib  # noqa: E402
+from ppodash_b200._lib import GemmArgs  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def sgemm(A, lda, a_k, Bm, ldb, b_k, C, ldc, I, J, KK, bias=None, mask=None, ldm=0, relu=0, acc=0):
+    L = _lib.lib()
+    g = GemmArgs()
+    g.A, g.lda, g.a_kmajor = A.data_ptr(), lda, a_k
+    g.B, g.ldb, g.b_kmajor = Bm.data_ptr(), ldb, b_k
+    g.C, g.ldc = C.data_ptr(), ldc
+    g.I, g.J, g.KK = I, J, KK
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.mask = mask.data_ptr() if mask is not None else None
+    g.ldm = ldm
+    g.relu, g.accumulate = relu, acc
+    ws = _lib.workspace(L.ppd_sgemm_workspace(I, J, KK), DEV, "gemm")
+    _lib.check(L.ppd_sgemm(ctypes.byref(g), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+
+
+@pytest.mark.parametrize("M,N,K", [(5, 3, 7), (64, 32, 192), (300, 64, 512), (2048, 512, 1568), (130, 1536, 527),
+                                   (1000, 9, 512), (4096, 32, 576)])
+def test_sgemm_forward_nt(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    ldx = K + (1 if K == 527 else 0)
+    X = torch.randn(M, ldx, generator=g)
+    W = torch.randn(N, K, generator=g) / np.sqrt(K)
+    b = torch.randn(N, generator=g)
+    want = F.relu(F.linear(X[:, :K], W, b))
+    Xd, Wd, bd = X.to(DEV), W.to(DEV), b.to(DEV)
+    C = torch.full((M, N + 3), -5.0, device=DEV)
+    sgemm(Xd, ldx, 1, Wd, K, 1, C, N + 3, M, N, K, bias=bd, relu=1)
+    np.testing.assert_allclose(C[:, :N].cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5)
+    assert torch.all(C[:, N:] == -5.0)          # never writes outside J
+
+
+@pytest.mark.parametrize("M,N,K", [(5, 3, 7), (300, 64, 512), (2048, 512, 1568), (130, 1536, 527), (1000, 9, 512)])
+def test_sgemm_dgrad_nn_with_relu_mask(M, N, K):
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    dY = torch.randn(M, N, generator=g)
+    W = torch.randn(N, K, generator=g) / np.sqrt(N)
+    act = torch.randn(M, K, generator=g)
+    want = (dY @ W) * (act > 0)
+    dX = torch.zeros(M, K, device=DEV)
+    sgemm(dY.to(DEV), N, 1, W.to(DEV), K, 0, dX, K, M, K, N, mask=act.to(DEV), ldm=K)
+    np.testing.assert_allclose(dX.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("M,N,K", [(5, 3, 7), (81 * 64, 64, 512), (2048, 512, 1568), (2048, 1536, 527), (40000, 32, 192),
+                                   (3000, 9, 512)])
+def test_sgemm_wgrad_tn_splitk_accumulate(M, N, K):
+    g = torch.Generator().manual_seed(M + 7 * N + K)
+    dY = torch.randn(M, N, generator=g) / np.sqrt(M)
+    X = torch.randn(M, K, generator=g)
+    dW0 = torch.randn(N, K, generator=g)
+    want = dW0 + (dY.double().t() @ X.double()).float()
+    dW = dW0.to(DEV).clone()
+    sgemm(dY.to(DEV), N, 0, X.to(DEV), K, 0, dW, K, N, K, M, acc=1)
+    np.testing.assert_allclose(dW.cpu().numpy(), want.numpy(), rtol=1e-5, atol=2e-5)
+
+
+def test_colsum():
+    L = _lib.lib()
+    for (I, J, ld) in [(1, 1, 1), (1000, 9, 12), (5000, 1536, 1536)]:
+        X = torch.randn(I, ld)
+        out0 = torch.randn(J)
+        Xd = X.to(DEV)
+        out = out0.to(DEV).clone()
+        ws = _lib.workspace(L.ppd_colsum_workspace(I, J), DEV, "colsum")
+        _lib.check(L.ppd_colsum(Xd.data_ptr(), ld, I, J, out.data_ptr(), 1, ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        np.testing.assert_allclose(out.cpu().numpy(), (out0 + X[:, :J].double().sum(0).float()).numpy(), rtol=1e-5, atol=1e-4)
+
+
+def _unfold_nchw(x, k, s):
+    # [B, C*k*k, L] with patch index (c,ky,kx) -> [B*L, C*k*k]
+    u = F.unfold(x, k, stride=s)
+    return u.transpose(1, 2).reshape(-1, u.shape[1])
+
+
+def test_im2col_nchw_matches_unfold():
+    L = _lib.lib()
+    for (B, C, H, k, s) in [(3, 3, 84, 8, 4), (2, 1, 84, 8, 4), (2, 12, 84, 8, 4), (2, 2, 21, 3, 2)]:
+        x = torch.randn(B, C, H, H)
+        want = _unfold_nchw(x, k, s)
+        K = C * k * k
+        if K % 4:
+            continue
+        cols = torch.zeros(want.shape[0], K, device=DEV)
+        xd = x.to(DEV)
+        _lib.check(L.ppd_im2col_nchw(xd.data_ptr(), B, C, H, H, k, k, s, cols.data_ptr(), K, _lib.stream_ptr()))
+        assert torch.equal(cols.cpu(), want)
+
+
+def test_im2col_col2im_nhwc():
+    L = _lib.lib()
+    for (B, H, C, k, s) in [(3, 20, 32, 4, 2), (2, 9, 64, 3, 1), (1, 11, 8, 3, 2)]:
+        x_nchw = torch.randn(B, C, H, H)
+        x = x_nchw.permute(0, 2, 3, 1).contiguous()            # NHWC
+        OH = (H - k) // s + 1
+        u = F.unfold(x_nchw, k, stride=s)                       # [B, C*k*k, L], index (c,ky,kx)
+        want = u.reshape(B, C, k, k, OH * OH).permute(0, 4, 2, 3, 1).reshape(B * OH * OH, k * k * C)   # (ky,kx,c)
+        K = k * k * C
+        cols = torch.zeros(B * OH * OH, K, device=DEV)
+        xd = x.to(DEV)
+        _lib.check(L.ppd_im2col_nhwc(xd.data_ptr(), B, H, H, C, k, k, s, cols.data_ptr(), K, _lib.stream_ptr()))
+        assert torch.equal(cols.cpu(), want)
+        # col2im = transpose of im2col (F.fold), fused with the ReLU mask
+        dcols = torch.randn(B * OH * OH, K)
+        act = torch.randn(B, H, H, C)
+        d_u = dcols.reshape(B, OH * OH, k, k, C).permute(0, 4, 2, 3, 1).reshape(B, C * k * k, OH * OH)
+        want_dx = F.fold(d_u, (H, H), k, stride=s).permute(0, 2, 3, 1) * (act > 0)
+        dx = torch.zeros(B, H, H, C, device=DEV)
+        dd, ad = dcols.to(DEV), act.to(DEV)
+        _lib.check(L.ppd_col2im_nhwc(dd.data_ptr(), K, B, H, H, C, k, k, s, ad.data_ptr(), dx.data_ptr(), _lib.stream_ptr()))
+        np.testing.assert_allclose(dx.cpu().numpy(), want_dx.numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_batched_transpose():
+    L = _lib.lib()
+    x = torch.randn(37, 49, 32)
+    xd = x.to(DEV)
+    y = torch.zeros(37, 32, 49, device=DEV)
+    _lib.check(L.ppd_batched_transpose(xd.data_ptr(), 37, 49, 32, y.data_ptr(), _lib.stream_ptr()))
+    assert torch.equal(y.cpu(), x.transpose(1, 2).contiguous())
+
+
+@pytest.mark.parametrize("T,E,H,I", [(5, 3, 32, 35), (16, 4, 512, 527), (1, 32, 512, 527), (4, 40, 64, 64), (64, 4, 512, 527)])
+def test_gru_forward_backward_vs_torch(T, E, H, I):
+    g = torch.Generator().manual_seed(T * 100 + E)
+    p = {"base.gru.weight_ih_l0": torch.randn(3 * H, I, generator=g) / np.sqrt(I),
+         "base.gru.weight_hh_l0": torch.randn(3 * H, H, generator=g) / np.sqrt(H),
+         "base.gru.bias_ih_l0": 0.1 * torch.randn(3 * H, generator=g),
+         "base.gru.bias_hh_l0": 0.1 * torch.randn(3 * H, generator=g)}
+    x = torch.randn(T * E, I, generator=g)
+    h0 = 0.5 * torch.randn(E, H, generator=g)
+    masks = (torch.rand(T * E, 1, generator=g) > 0.2).float()
+    dhs = torch.randn(T * E, H, generator=g)
+    # reference: segmented torch GRU + autograd
+    w_hh = p["base.gru.weight_hh_l0"].clone().requires_grad_(True)
+    pp = dict(p); pp["base.gru.weight_hh_l0"] = w_hh
+    xr = x.clone().requires_grad_(True)
+    h0r = h0.clone().requires_grad_(True)
+    if T == 1:
+        out, hl = o_pol.gru_cell_stepwise(pp, xr, h0r, masks)
+    else:
+        out, hl = o_pol.gru_with_resets(pp, xr, h0r, masks)
+    (out * dhs).sum().backward()
+    gi_ref = F.linear(x, p["base.gru.weight_ih_l0"], p["base.gru.bias_ih_l0"])
+
+    L = _lib.lib()
+    d = lambda t: t.to(DEV).contiguous()
+    gi, h0d, md, whh, bhh, dhsd = d(gi_ref), d(h0), d(masks), d(p["base.gru.weight_hh_l0"]), d(p["base.gru.bias_hh_l0"]), d(dhs)
+    hs = torch.zeros(T * E, H, device=DEV); hlast = torch.zeros(E, H, device=DEV)
+    sr, sz, sn, sg = (torch.zeros(T * E, H, device=DEV) for _ in range(4))
+    _lib.check(L.ppd_gru_forward(gi.data_ptr(), h0d.data_ptr(), md.data_ptr(), whh.data_ptr(), bhh.data_ptr(), T, E, H,
+                                 hs.data_ptr(), hlast.data_ptr(), sr.data_ptr(), sz.data_ptr(), sn.data_ptr(), sg.data_ptr(),
+                                 _lib.stream_ptr()))
+    np.testing.assert_allclose(hs.cpu().numpy(), out.detach().numpy(), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(hlast.cpu().numpy(), hl.detach().numpy(), rtol=1e-5, atol=2e-6)
+    dgi = torch.zeros(T * E, 3 * H, device=DEV); dghn = torch.zeros(T * E, H, device=DEV); dh0 = torch.zeros(E, H, device=DEV)
+    _lib.check(L.ppd_gru_backward(dhsd.data_ptr(), md.data_ptr(), whh.data_ptr(), h0d.data_ptr(), hs.data_ptr(),
+                                  sr.data_ptr(), sz.data_ptr(), sn.data_ptr(), sg.data_ptr(), T, E, H, dgi.data_ptr(),
+                                  dghn.data_ptr(), dh0.data_ptr(), _lib.stream_ptr()))
+    # dx = dgi @ W_ih ; dW_hh = dgh^T hm ; dh0
+    dx = dgi.cpu() @ p["base.gru.weight_ih_l0"]
+    np.testing.assert_allclose(dx.numpy(), xr.grad.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(dh0.cpu().numpy(), h0r.grad.numpy(), rtol=1e-4, atol=2e-5)
+    hm = torch.zeros(T * E, H, device=DEV)
+    _lib.check(L.ppd_gru_masked_prev(hs.data_ptr(), h0d.data_ptr(), md.data_ptr(), T, E, H, hm.data_ptr(), _lib.stream_ptr()))
+    dgh = torch.cat([dgi[:, :2 * H], dghn], 1).cpu()
+    dwhh = dgh.t() @ hm.cpu()
+    np.testing.assert_allclose(dwhh.numpy(), w_hh.grad.numpy(), rtol=1e-4, atol=5e-5)

@@ -39,6 +39,11 @@ def storage_from(roll, obs_shape, V, A, H, dev=DEV):
 
 
 # --------------------------------------------------------------------------- returns
+def _ws(T, N):
+    w = _lib.workspace(_lib.lib().ppd_compute_returns_workspace(T, N), DEV, "returns", zero=True)
+    return w.data_ptr(), w.numel()
+
+
 @pytest.mark.parametrize("use_gae", [True, False])
 @pytest.mark.parametrize("proper", [True, False])
 def test_returns_vs_golden(golden, use_gae, proper):
@@ -72,7 +77,7 @@ def test_returns_vs_oracle_shapes(T, N, use_gae, proper):
     ret = torch.zeros(T + 1, N, 1, device=DEV)
     _lib.check(L.ppd_compute_returns(d["rewards"].data_ptr(), d["value_preds"].data_ptr(), d["masks"].data_ptr(),
                                      d["bad_masks"].data_ptr(), ret.data_ptr(), d["next_value"].data_ptr(), T, N,
-                                     0.99, 0.95, int(use_gae), int(proper), _lib.stream_ptr()))
+                                     0.99, 0.95, int(use_gae), int(proper), *_ws(T, N), _lib.stream_ptr()))
     np.testing.assert_allclose(ret.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
     assert np.array_equal(d["value_preds"].cpu().numpy(), want_v)
     if T <= 16:   # a single chunk: no re-association at all -> bit exact
@@ -99,7 +104,7 @@ def test_returns_edge_masks():
         ret = torch.zeros(T + 1, N, 1, device=DEV)
         _lib.check(L.ppd_compute_returns(d["rewards"].data_ptr(), d["value_preds"].data_ptr(), md.data_ptr(),
                                          d["bad_masks"].data_ptr(), ret.data_ptr(), d["next_value"].data_ptr(), T, N,
-                                         0.99, 0.95, 1, 0, _lib.stream_ptr()))
+                                         0.99, 0.95, 1, 0, *_ws(T, N), _lib.stream_ptr()))
         np.testing.assert_allclose(ret.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
 
 
@@ -114,7 +119,7 @@ def test_returns_full_size_recurrence_property():
     nv = torch.randn(N, 1, device=DEV, generator=gen)
     ret = torch.zeros(T + 1, N, 1, device=DEV)
     _lib.check(_lib.lib().ppd_compute_returns(r.data_ptr(), v.data_ptr(), m.data_ptr(), None, ret.data_ptr(),
-                                              nv.data_ptr(), T, N, 0.99, 0.95, 1, 0, _lib.stream_ptr()))
+                                              nv.data_ptr(), T, N, 0.99, 0.95, 1, 0, *_ws(T, N), _lib.stream_ptr()))
     assert torch.equal(v[T], nv)
     A = (ret[:T] - v[:T]).double()
     delta = r.double() + 0.99 * v[1:].double() * m[1:].double() - v[:T].double()
@@ -369,9 +374,14 @@ def test_clip_adam_vs_torch(n, max_norm):
         _lib.check(L.ppd_clip_adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, step, 1e-4, 0.9,
                                         0.999, 1e-5, max_norm, gn.data_ptr(), loss_in.data_ptr(), loss_acc.data_ptr(),
                                         ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
-        assert abs(gn.item() - want_norm.item()) <= 1e-5 * max(1.0, want_norm.item())
-        # stated tolerance: |dp| per step <= lr = 1e-4; agree to 2e-9 absolute (1e-5 of a step) + 1e-6 relative
-        np.testing.assert_allclose(p.cpu().numpy(), ref_p.detach().numpy(), rtol=1e-6, atol=2e-9)
+        # torch's fp32 CPU norm is itself ~4e-5 off the float64 value at 2.4M elements; the kernel
+        # (fp32 per thread, fp64 across threads) is checked against float64, and loosely against torch
+        exact = grad.double().norm().item()
+        assert abs(gn.item() - exact) <= 1e-6 * max(1.0, exact)
+        assert abs(gn.item() - want_norm.item()) <= 2e-4 * max(1.0, want_norm.item())
+        # stated tolerance: |dp| per step <= lr = 1e-4; agree to 1e-8 absolute (1e-4 of a step) + 1e-6 relative
+        # (torch's clip coefficient inherits the ~4e-5 error of its fp32 norm)
+        np.testing.assert_allclose(p.cpu().numpy(), ref_p.detach().numpy(), rtol=1e-6, atol=1e-8)
     assert torch.allclose(loss_acc.cpu(), torch.tensor([5.0, 10.0, 15.0]))
     st = opt.state[ref_p]
     np.testing.assert_allclose(m.cpu().numpy(), st["exp_avg"].numpy(), rtol=1e-5, atol=1e-10)

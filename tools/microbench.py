@@ -65,10 +65,11 @@ def bench_gae(T, N, proper=False):
     ret = torch.zeros(T + 1, N, 1, device=DEV)
     nv = torch.randn(N, 1, device=DEV)
     s = _lib.stream_ptr()
+    ws = torch.zeros(L.ppd_compute_returns_workspace(T, N), dtype=torch.uint8, device=DEV)
 
     def fn():
         _lib.check(L.ppd_compute_returns(r.data_ptr(), v.data_ptr(), m.data_ptr(), b.data_ptr(), ret.data_ptr(),
-                                         nv.data_ptr(), T, N, 0.99, 0.95, 1, int(proper), s))
+                                         nv.data_ptr(), T, N, 0.99, 0.95, 1, int(proper), ws.data_ptr(), ws.numel(), s))
     med, best = time_kernel(fn)
     bytes_ = (20 if proper else 16) * T * N + 4 * N
     return dict(kernel="returns_scan", T=T, N=N, proper=proper, ms=med, ms_best=best,
