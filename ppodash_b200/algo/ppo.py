@@ -1,0 +1,140 @@
+"""PPO: drop-in for PKG/algo/ppo.py (same constructor, ``update(rollouts)`` returning
+``(value_loss, action_loss, dist_entropy)`` as Python floats, ``.optimizer.param_groups[i]['lr']``
+writable for the linear LR schedule, PKG/utils.py:46-50).
+
+What changes underneath (all on the current CUDA stream, no host sync until the final read):
+  * advantage mean / unbiased std over all T*N in one reduction kernel; the normalised advantage is
+    recomputed on the fly inside the minibatch gather (ppo.py:35-37);
+  * per minibatch: gather kernel -> network forward -> fused PPO loss forward+backward -> network
+    backward -> (NCCL all-reduce of the flat gradient buffer when data-parallel) -> fused global-norm
+    clip + Adam (ppo.py:57-84).  The reference's three ``.item()`` syncs per minibatch
+    (ppo.py:86-88) become one 3-float device-to-host read per ``update``.
+Data-parallel: every rank holds the envs of its shard in its own RolloutStorage;
+advantage moments (3 doubles) are all-reduced once per update and the flat gradient buffer (with
+the loss partial sums in its tail) once per minibatch; all ranks then apply the identical step.
+"""
+import torch
+
+from .. import _lib
+from .._lib import check, lib
+from ..storage import FusedAdvantages
+
+
+class FusedClipAdam(torch.optim.Optimizer):
+    """torch.optim.Adam-compatible facade (param_groups, state_dict) whose step is the fused
+    clip + Adam kernel over the policy's flat parameter buffer."""
+
+    def __init__(self, policy, lr=None, eps=None):
+        defaults = dict(lr=1e-3 if lr is None else lr, betas=(0.9, 0.999), eps=1e-8 if eps is None else eps)
+        super().__init__(list(policy.parameters()), defaults)
+        self._policy = policy
+        self.max_grad_norm = None
+
+    def zero_grad(self, set_to_none=False):
+        eng = self._policy.engine()
+        eng.bind()
+        eng.flat_grad.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None, loss_acc=None, grad_norm_out=None):
+        g = self.param_groups[0]
+        self._policy.engine().adam_step(g["lr"], g["betas"], g["eps"], self.max_grad_norm, loss_acc, grad_norm_out)
+
+    def state_dict(self):
+        eng = self._policy.engine()
+        eng.bind()
+        st = eng.adam_state
+        return dict(step=st["step"], exp_avg=st["exp_avg"].clone(), exp_avg_sq=st["exp_avg_sq"].clone(),
+                    param_groups=[{k: v for k, v in g.items() if k != "params"} for g in self.param_groups])
+
+    def load_state_dict(self, sd):
+        eng = self._policy.engine()
+        eng.bind()
+        eng.adam_state["step"] = int(sd["step"])
+        eng.adam_state["exp_avg"].copy_(sd["exp_avg"])
+        eng.adam_state["exp_avg_sq"].copy_(sd["exp_avg_sq"])
+        for g, s in zip(self.param_groups, sd["param_groups"]):
+            g.update(s)
+
+
+class PPO():
+    def __init__(self,
+                 actor_critic,
+                 clip_param,
+                 ppo_epoch,
+                 num_mini_batch,
+                 value_loss_coef,
+                 entropy_coef,
+                 lr=None,
+                 eps=None,
+                 max_grad_norm=None,
+                 use_clipped_value_loss=True,
+                 process_group=None):
+        self.actor_critic = actor_critic
+        self.clip_param = clip_param
+        self.ppo_epoch = ppo_epoch
+        self.num_mini_batch = num_mini_batch
+        self.value_loss_coef = value_loss_coef
+        self.entropy_coef = entropy_coef
+        self.max_grad_norm = max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self.optimizer = FusedClipAdam(actor_critic, lr=lr, eps=eps)
+        # data parallel: None -> use the default process group if one is initialised with >1 ranks
+        self.process_group = process_group
+        self.last_grad_norm = None
+
+    def _world(self):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1, None
+        pg = self.process_group
+        ws = dist.get_world_size(pg)
+        return ws, dist
+
+    def advantage_stats(self, rollouts):
+        """Device tensor [mean, std + 1e-5] of returns[:-1] - value_preds[:-1] over all ranks."""
+        L = lib()
+        T, N = rollouts.rewards.size(0), rollouts.rewards.size(1)
+        dev = rollouts.returns.device
+        n = T * N
+        ws = _lib.workspace(L.ppd_advantage_moments_workspace(n), dev, "advmom")
+        mom = torch.empty(3, dtype=torch.float64, device=dev)
+        stats = torch.empty(2, dtype=torch.float32, device=dev)
+        st = _lib.stream_ptr(dev)
+        check(L.ppd_advantage_moments(_lib.ptr(rollouts.returns, torch.float32), _lib.ptr(rollouts.value_preds, torch.float32),
+                                      n, mom.data_ptr(), ws.data_ptr(), ws.numel(), st), "advantage_moments")
+        world, dist = self._world()
+        if world > 1:
+            dist.all_reduce(mom, group=self.process_group)
+        check(L.ppd_advantage_finalize(mom.data_ptr(), stats.data_ptr(), st), "advantage_finalize")
+        return stats
+
+    def update(self, rollouts):
+        pol = self.actor_critic
+        eng = pol.engine()
+        eng.bind()
+        dev = eng.device
+        world, dist = self._world()
+        stats = self.advantage_stats(rollouts)
+        advantages = FusedAdvantages(stats)
+        loss_acc = torch.zeros(3, dtype=torch.float32, device=dev)
+        gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.optimizer.max_grad_norm = self.max_grad_norm
+
+        for e in range(self.ppo_epoch):
+            if pol.is_recurrent:
+                data_generator = rollouts.recurrent_generator(advantages, self.num_mini_batch)
+            else:
+                data_generator = rollouts.feed_forward_generator(advantages, self.num_mini_batch)
+            for sample in data_generator:
+                rows = sample[0].shape[0]
+                eng.train_minibatch(sample, self.clip_param, self.value_loss_coef, self.entropy_coef,
+                                    self.use_clipped_value_loss, global_rows=rows * world)
+                if world > 1:
+                    dist.all_reduce(eng.flat_grad, group=self.process_group)     # grads + loss partials
+                self.optimizer.step(loss_acc=loss_acc, grad_norm_out=gnorm)
+
+        num_updates = self.ppo_epoch * self.num_mini_batch
+        vals = (loss_acc / num_updates).tolist()          # the only device->host sync of update()
+        self.last_grad_norm = gnorm
+        return vals[0], vals[1], vals[2]

@@ -40,9 +40,9 @@ struct Args {
 // Load one BROWS x BK operand tile into registers.  KMAJ: contraction index contiguous in memory.
 template <int BROWS, bool KMAJ>
 struct TileLoader {
-    static constexpr int kElems = BROWS * BK / kThreads;   // floats per thread (4 or 8)
-    static constexpr int kVecs = kElems / 4;
-    float v[kElems];
+    static constexpr int kTileVecs = BROWS * BK / 4;                       // float4 per tile
+    static constexpr int kVecs = (kTileVecs + kThreads - 1) / kThreads;    // float4 per thread (1 or 2)
+    float v[4 * kVecs];
 
     __device__ __forceinline__ void load(const float* __restrict__ P, int64_t ld, int64_t row0, int64_t nrows,
                                          int64_t kk0, int64_t kk_end, bool vec) {
@@ -50,6 +50,7 @@ struct TileLoader {
 #pragma unroll
         for (int q = 0; q < kVecs; ++q) {
             const int e = tid + q * kThreads;          // vector index within the tile
+            if (kTileVecs % kThreads != 0 && e >= kTileVecs) break;
             if (KMAJ) {
                 const int r = e / (BK / 4), c = (e % (BK / 4)) * 4;
                 const int64_t row = row0 + r, kk = kk0 + c;
@@ -83,6 +84,7 @@ struct TileLoader {
 #pragma unroll
         for (int q = 0; q < kVecs; ++q) {
             const int e = tid + q * kThreads;
+            if (kTileVecs % kThreads != 0 && e >= kTileVecs) break;
             if (KMAJ) {
                 const int r = e / (BK / 4), c = (e % (BK / 4)) * 4;
 #pragma unroll

@@ -1,0 +1,437 @@
+"""PolicyEngine: runs the actor-critic (PKG/model.py:54-199) forward and backward on the
+libppodash_b200 kernels, over one flat fp32 parameter buffer.
+
+Data layout in HBM
+  * parameters / gradients / Adam moments: one flat fp32 buffer each, segments 256-byte aligned.
+    The ``nn.Module`` parameters are *views* into the flat buffer (so ``state_dict`` keys, shapes and
+    ``load_state_dict`` behave as in the reference) and ``p.grad`` are views into the flat gradient
+    buffer.  Three segments use a kernel-friendly layout behind a strided view:
+      - conv2 / conv3 weights are stored (o, ky, kx, c) -- the patch order of NHWC im2col;
+      - gru.weight_ih rows are padded from hidden+V to a multiple of 4 floats (16-byte rows);
+      - dist.linear / critic_linear weights and biases are adjacent, forming one [A+1, H] "heads"
+        matrix so a single GEMM produces logits and value.
+    The flat gradient buffer carries 4 extra floats at its tail for the three loss partial sums, so
+    that one NCCL all-reduce per minibatch moves gradients and losses together.
+  * activations: NHWC between the convolutions ( = row-major [B*OH*OW, C], what the GEMM writes);
+    the conv3 output is transposed per sample to NCHW so the flatten order is the reference's.
+  * rows of a minibatch are time-major (row = t*E + e), exactly as recurrent_generator yields them.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, check, lib
+
+ALIGN = 64  # floats (256 B)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def categorical_eval(z, num_actions, actions=None):
+    """log-prob of `actions` (or of the arg-max action), per-row entropy, mode and probs
+    (PKG/distributions.py:18-27) via ppd_categorical_eval."""
+    B, ld = z.shape
+    dev = z.device
+    logp = torch.empty(B, device=dev)
+    ent = torch.empty(B, device=dev)
+    mode = torch.empty(B, dtype=torch.int64, device=dev)
+    probs = torch.empty(B, num_actions, device=dev)
+    a = None
+    if actions is not None:
+        a = actions.to(device=dev, dtype=torch.int64).contiguous()
+    check(lib().ppd_categorical_eval(_lib.ptr(z, torch.float32), ld, num_actions, _lib.ptr(a), B, logp.data_ptr(),
+                                     ent.data_ptr(), mode.data_ptr(), probs.data_ptr(), _lib.stream_ptr(dev)),
+          "categorical_eval")
+    return dict(logp=logp, entropy=ent, mode=mode, probs=probs)
+
+
+class _Seg:
+    __slots__ = ("name", "off", "numel", "shape", "view")
+
+    def __init__(self, name, off, numel, shape, view):
+        self.name, self.off, self.numel, self.shape, self.view = name, off, numel, shape, view
+
+
+class PolicyEngine:
+    CONV = ((8, 4), (4, 2), (3, 1))   # (kernel, stride) of base.main.{0,2,4}
+
+    def __init__(self, policy):
+        self.policy = policy
+        base = policy.base
+        self.C = base.num_inputs
+        self.V = base.vector_obs_len
+        self.H = base._hidden_size
+        self.A = policy.num_actions
+        self.recurrent = base.is_recurrent
+        self.I = self.H + self.V
+        self.Ipad = _round_up(self.I, 4)
+        self.hw = policy.obs_shape[1]
+        assert policy.obs_shape[1] == policy.obs_shape[2], "square observations expected"
+        s = self.hw
+        self.sp = []
+        for k, st in self.CONV:
+            s = (s - k) // st + 1
+            self.sp.append(s)             # 20, 9, 7 for 84x84
+        assert 32 * self.sp[2] * self.sp[2] == base.main[7].in_features, "obs size does not match the FC layer"
+        self.flat_dim = 32 * self.sp[2] * self.sp[2]
+        self.precision = "fp32"
+        self.chunk_rows = 2048            # rows of the minibatch lowered to im2col at a time
+        self.device = None
+        self.flat = None
+        self._buffers = {}
+        self._cols_valid = False
+
+    # ------------------------------------------------------------------ parameters
+    def set_precision(self, precision):
+        if precision not in ("fp32",):
+            raise ValueError("supported precision modes: 'fp32' (SIMT, parity mode)")
+        self.precision = precision
+
+    def _layout(self):
+        base, pol = self.policy.base, self.policy
+        H, A, C = self.H, self.A, self.C
+        specs = []
+
+        def add(name, param, numel, make_view):
+            specs.append((name, param, numel, make_view))
+
+        m = base.main
+        add("conv1.w", m[0].weight, 32 * C * 64, lambda f: f.view(32, C, 8, 8))
+        add("conv1.b", m[0].bias, 32, lambda f: f)
+        add("conv2.w", m[2].weight, 64 * 512, lambda f: f.view(64, 4, 4, 32).permute(0, 3, 1, 2))
+        add("conv2.b", m[2].bias, 64, lambda f: f)
+        add("conv3.w", m[4].weight, 32 * 576, lambda f: f.view(32, 3, 3, 64).permute(0, 3, 1, 2))
+        add("conv3.b", m[4].bias, 32, lambda f: f)
+        add("fc.w", m[7].weight, H * self.flat_dim, lambda f: f.view(H, self.flat_dim))
+        add("fc.b", m[7].bias, H, lambda f: f)
+        if self.recurrent:
+            g = base.gru
+            add("gru.w_ih", g.weight_ih_l0, 3 * H * self.Ipad, lambda f: f.view(3 * H, self.Ipad)[:, :self.I])
+            add("gru.w_hh", g.weight_hh_l0, 3 * H * H, lambda f: f.view(3 * H, H))
+            add("gru.b_ih", g.bias_ih_l0, 3 * H, lambda f: f)
+            add("gru.b_hh", g.bias_hh_l0, 3 * H, lambda f: f)
+        # heads: dist rows then the critic row, adjacent -> one [A+1, H] matrix
+        add("heads.w", (pol.dist.linear.weight, base.critic_linear.weight), (A + 1) * H,
+            lambda f: (f.view(A + 1, H)[:A], f.view(A + 1, H)[A:]))
+        add("heads.b", (pol.dist.linear.bias, base.critic_linear.bias), A + 1, lambda f: (f[:A], f[A:]))
+        return specs
+
+    def _is_bound(self):
+        if self.flat is None:
+            return False
+        lo = self.flat.data_ptr()
+        hi = lo + self.flat.numel() * 4
+        for p in self.policy.parameters():
+            if p.device != self.flat.device or not (lo <= p.data_ptr() < hi):
+                return False
+        return True
+
+    def bind(self):
+        """(Re)build the flat buffers and make every parameter (and .grad) a view into them.
+        Called lazily; repeats itself if the module was moved (.to()) or reloaded since."""
+        if self._is_bound():
+            return
+        params = list(self.policy.parameters())
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise _lib.PpdError("Policy must be on a CUDA device (call .to(device)); ppodash_b200 has no CPU fallback")
+        specs = self._layout()
+        off = 0
+        offs = []
+        for _, _, numel, _ in specs:
+            offs.append(off)
+            off = _round_up(off + numel, ALIGN)
+        self.n_params = off                       # includes alignment padding (always zero)
+        self.loss_off = off                       # 4 floats of loss partials at the gradient tail
+        total = off + 4
+        old_state = getattr(self, "adam_state", None)
+        flat = torch.zeros(total, device=dev)
+        grad = torch.zeros(total, device=dev)
+        self.segs = {}
+        with torch.no_grad():
+            for (name, param, numel, make_view), o in zip(specs, offs):
+                view = make_view(flat[o:o + numel])
+                gview = make_view(grad[o:o + numel])
+                if isinstance(param, tuple):
+                    for p, v, gv in zip(param, view, gview):
+                        v.copy_(p.data.to(dev))
+                        p.data = v
+                        p.grad = gv
+                else:
+                    view.copy_(param.data.to(dev))
+                    param.data = view
+                    param.grad = gview
+                self.segs[name] = _Seg(name, o, numel, None, view)
+        self.flat, self.flat_grad, self.device = flat, grad, dev
+        if old_state is None or old_state["exp_avg"].numel() != total or old_state["exp_avg"].device != dev:
+            self.adam_state = dict(exp_avg=torch.zeros(total, device=dev), exp_avg_sq=torch.zeros(total, device=dev), step=0)
+        self._buffers = {}
+        self._cols_valid = False
+
+    def seg(self, name, grad=False):
+        s = self.segs[name]
+        buf = self.flat_grad if grad else self.flat
+        return buf[s.off:s.off + s.numel]
+
+    # ------------------------------------------------------------------ scratch
+    def buf(self, name, *shape, dtype=torch.float32):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        t = self._buffers.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._buffers[name] = t
+        return t[:n].view(*shape)
+
+    # ------------------------------------------------------------------ kernel wrappers
+    def _gemm(self, A, lda, a_k, B, ldb, b_k, C, ldc, I, J, KK, bias=None, mask=None, ldm=0, relu=0, acc=0):
+        g = GemmArgs()
+        g.A, g.lda, g.a_kmajor = A.data_ptr(), lda, a_k
+        g.B, g.ldb, g.b_kmajor = B.data_ptr(), ldb, b_k
+        g.C, g.ldc = C.data_ptr(), ldc
+        g.I, g.J, g.KK = I, J, KK
+        g.bias = bias.data_ptr() if bias is not None else None
+        g.mask = mask.data_ptr() if mask is not None else None
+        g.ldm = ldm
+        g.relu, g.accumulate = relu, acc
+        L = lib()
+        ws = _lib.workspace(L.ppd_sgemm_workspace(I, J, KK), self.device, "gemm")
+        check(L.ppd_sgemm(ctypes.byref(g), ws.data_ptr(), ws.numel(), self.stream), "sgemm")
+
+    def _colsum(self, X, ld, I, J, out, acc=0):
+        L = lib()
+        ws = _lib.workspace(L.ppd_colsum_workspace(I, J), self.device, "colsum")
+        check(L.ppd_colsum(X.data_ptr(), ld, I, J, out.data_ptr(), acc, ws.data_ptr(), ws.numel(), self.stream), "colsum")
+
+    # ------------------------------------------------------------------ trunk
+    def _trunk_forward(self, obs, B, feat, ldf, keep):
+        """obs [B,C,hw,hw] -> feat[:, :H] (row stride ldf) = ReLU(FC(flatten(conv stack))).
+        keep=True stores the activations needed by backward."""
+        L = lib()
+        C, H, hw = self.C, self.H, self.hw
+        s1, s2, s3 = self.sp
+        K1, K2, K3 = C * 64, 512, 576
+        a1 = self.buf("a1", B, s1 * s1 * 32)
+        a2 = self.buf("a2", B, s2 * s2 * 64)
+        a3 = self.buf("a3", B, s3 * s3 * 32)
+        a3t = self.buf("a3t", B, self.flat_dim)
+        ch = min(self.chunk_rows, B)
+        cols1 = self.buf("cols1", ch * s1 * s1, K1)
+        cols2 = self.buf("cols2", ch * s2 * s2, K2)
+        cols3 = self.buf("cols3", ch * s3 * s3, K3)
+        st = self.stream
+        w1, b1 = self.seg("conv1.w"), self.seg("conv1.b")
+        w2, b2 = self.seg("conv2.w"), self.seg("conv2.b")
+        w3, b3 = self.seg("conv3.w"), self.seg("conv3.b")
+        for r0 in range(0, B, ch):
+            n = min(ch, B - r0)
+            check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, cols1.data_ptr(), K1, st), "im2col1")
+            self._gemm(cols1, K1, 1, w1, K1, 1, a1[r0:], 32, n * s1 * s1, 32, K1, bias=b1, relu=1)
+            check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, cols2.data_ptr(), K2, st), "im2col2")
+            self._gemm(cols2, K2, 1, w2, K2, 1, a2[r0:], 64, n * s2 * s2, 64, K2, bias=b2, relu=1)
+            check(L.ppd_im2col_nhwc(a2[r0:].data_ptr(), n, s2, s2, 64, 3, 3, 1, cols3.data_ptr(), K3, st), "im2col3")
+            self._gemm(cols3, K3, 1, w3, K3, 1, a3[r0:], 32, n * s3 * s3, 32, K3, bias=b3, relu=1)
+        self._cols_valid = keep and ch >= B      # single chunk: backward can reuse the im2col matrices
+        check(L.ppd_batched_transpose(a3.data_ptr(), B, s3 * s3, 32, a3t.data_ptr(), st), "transpose")
+        self._gemm(a3t, self.flat_dim, 1, self.seg("fc.w"), self.flat_dim, 1, feat, ldf, B, H, self.flat_dim,
+                   bias=self.seg("fc.b"), relu=1)
+
+    def _trunk_backward(self, obs, B, dfeat, ldd):
+        """dfeat [B, H] (row stride ldd; already masked by feat > 0) -> conv/FC gradients (accumulated
+        into the zeroed flat gradient buffer)."""
+        L = lib()
+        C, H, hw = self.C, self.H, self.hw
+        s1, s2, s3 = self.sp
+        K1, K2, K3 = C * 64, 512, 576
+        st = self.stream
+        a1 = self.buf("a1", B, s1 * s1 * 32)
+        a2 = self.buf("a2", B, s2 * s2 * 64)
+        a3t = self.buf("a3t", B, self.flat_dim)
+        fd = self.flat_dim
+        # FC
+        self._gemm(dfeat, ldd, 0, a3t, fd, 0, self.seg("fc.w", True), fd, H, fd, B)
+        self._colsum(dfeat, ldd, B, H, self.seg("fc.b", True))
+        da3t = self.buf("da3t", B, fd)
+        self._gemm(dfeat, ldd, 1, self.seg("fc.w"), fd, 0, da3t, fd, B, fd, H, mask=a3t, ldm=fd)
+        dy3 = self.buf("dy3", B, s3 * s3 * 32)                   # NHWC = [B*49, 32]
+        check(L.ppd_batched_transpose(da3t.data_ptr(), B, 32, s3 * s3, dy3.data_ptr(), st), "transpose")
+        ch = min(self.chunk_rows, B)
+        cols1 = self.buf("cols1", ch * s1 * s1, K1)
+        cols2 = self.buf("cols2", ch * s2 * s2, K2)
+        cols3 = self.buf("cols3", ch * s3 * s3, K3)
+        dcols3 = self.buf("dcols3", ch * s3 * s3, K3)
+        dcols2 = self.buf("dcols2", ch * s2 * s2, K2)
+        dy2 = self.buf("dy2", ch, s2 * s2 * 64)
+        dy1 = self.buf("dy1", ch, s1 * s1 * 32)
+        w2, w3 = self.seg("conv2.w"), self.seg("conv3.w")
+        first = True
+        for r0 in range(0, B, ch):
+            n = min(ch, B - r0)
+            acc = 0 if first else 1
+            M3, M2, M1 = n * s3 * s3, n * s2 * s2, n * s1 * s1
+            # conv3
+            if not self._cols_valid:
+                check(L.ppd_im2col_nhwc(a2[r0:].data_ptr(), n, s2, s2, 64, 3, 3, 1, cols3.data_ptr(), K3, st), "im2col3")
+            self._gemm(dy3[r0:], 32, 0, cols3, K3, 0, self.seg("conv3.w", True), K3, 32, K3, M3, acc=acc)
+            self._colsum(dy3[r0:], 32, M3, 32, self.seg("conv3.b", True), acc)
+            self._gemm(dy3[r0:], 32, 1, w3, K3, 0, dcols3, K3, M3, K3, 32)
+            check(L.ppd_col2im_nhwc(dcols3.data_ptr(), K3, n, s2, s2, 64, 3, 3, 1, a2[r0:].data_ptr(), dy2.data_ptr(), st), "col2im3")
+            # conv2
+            if not self._cols_valid:
+                check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, cols2.data_ptr(), K2, st), "im2col2")
+            self._gemm(dy2, 64, 0, cols2, K2, 0, self.seg("conv2.w", True), K2, 64, K2, M2, acc=acc)
+            self._colsum(dy2, 64, M2, 64, self.seg("conv2.b", True), acc)
+            self._gemm(dy2, 64, 1, w2, K2, 0, dcols2, K2, M2, K2, 64)
+            check(L.ppd_col2im_nhwc(dcols2.data_ptr(), K2, n, s1, s1, 32, 4, 4, 2, a1[r0:].data_ptr(), dy1.data_ptr(), st), "col2im2")
+            # conv1 (no input gradient needed)
+            if not self._cols_valid:
+                check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, cols1.data_ptr(), K1, st), "im2col1")
+            self._gemm(dy1, 32, 0, cols1, K1, 0, self.seg("conv1.w", True), K1, 32, K1, M1, acc=acc)
+            self._colsum(dy1, 32, M1, 32, self.seg("conv1.b", True), acc)
+            first = False
+
+    # ------------------------------------------------------------------ forward
+    def _prep(self, visual, vector, rnn_hxs, masks):
+        self.bind()
+        dev = self.device
+        self.stream = _lib.stream_ptr(dev)
+        obs = visual.to(device=dev, dtype=torch.float32).contiguous()
+        B = obs.shape[0]
+        if tuple(obs.shape[1:]) != (self.C, self.hw, self.hw):
+            raise ValueError(f"expected observations of shape [B,{self.C},{self.hw},{self.hw}], got {tuple(obs.shape)}")
+        vobs = vector.to(device=dev, dtype=torch.float32).reshape(B, -1).contiguous() if vector is not None else None
+        if self.V and (vobs is None or vobs.shape[1] != self.V):
+            raise ValueError(f"expected vector observations of shape [B,{self.V}]")
+        h0 = rnn_hxs.to(device=dev, dtype=torch.float32).contiguous()
+        m = masks.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        return obs, vobs, h0, m, B
+
+    def forward(self, visual, vector, rnn_hxs, masks, keep=False, xcat_prefilled=None):
+        """CNNBase.forward + both heads (model.py:192-199, distributions.py:66-68).
+        Returns dict(value [B,1], z [B,A+1] (logits | value), rnn_hxs, feats)."""
+        obs, vobs, h0, m, B = self._prep(visual, vector, rnn_hxs, masks)
+        L = lib()
+        H, A = self.H, self.A
+        st = self.stream
+        tag = "t_" if keep else "i_"
+        z = self.buf(tag + "z", B, A + 1) if keep else torch.empty(B, A + 1, device=self.device)
+        if self.recurrent:
+            E = h0.shape[0]
+            if B % E != 0:
+                raise ValueError("rows must be a multiple of the number of hidden-state rows (T*E, E)")
+            T = B // E
+            Ipad = self.Ipad
+            xcat = xcat_prefilled if xcat_prefilled is not None else self.buf(tag + "xcat", B, Ipad)
+            if xcat_prefilled is None:
+                if Ipad != H:
+                    xcat[:, H:].zero_()
+                    if self.V:
+                        xcat[:, H:H + self.V].copy_(vobs)           # torch.cat((x, vector), 1), model.py:195
+            self._trunk_forward(obs, B, xcat, Ipad, keep)
+            gi = self.buf(tag + "gi", B, 3 * H)
+            self._gemm(xcat, Ipad, 1, self.seg("gru.w_ih"), Ipad, 1, gi, 3 * H, B, 3 * H, Ipad, bias=self.seg("gru.b_ih"))
+            hs = self.buf(tag + "hs", B, H) if keep else torch.empty(B, H, device=self.device)
+            hl = torch.empty(E, H, device=self.device)
+            if keep:
+                sv = [self.buf("t_s%d" % i, B, H) for i in range(4)]
+                svp = [s.data_ptr() for s in sv]
+            else:
+                svp = [None] * 4
+            check(L.ppd_gru_forward(gi.data_ptr(), h0.data_ptr(), m.data_ptr(), self.seg("gru.w_hh").data_ptr(),
+                                    self.seg("gru.b_hh").data_ptr(), T, E, H, hs.data_ptr(), hl.data_ptr(), *svp, st),
+                  "gru_forward")
+            feats, ldf, rnn_out = hs, H, hl
+            self._saved = dict(obs=obs, xcat=xcat, gi=gi, hs=hs, h0=h0, m=m, T=T, E=E, B=B) if keep else None
+        else:
+            feat = self.buf(tag + "feat", B, H) if keep else torch.empty(B, H, device=self.device)
+            self._trunk_forward(obs, B, feat, H, keep)
+            feats, ldf, rnn_out = feat, H, rnn_hxs
+            self._saved = dict(obs=obs, feat=feat, B=B) if keep else None
+        self._gemm(feats, ldf, 1, self.seg("heads.w"), H, 1, z, A + 1, B, A + 1, H, bias=self.seg("heads.b"))
+        if keep:
+            self._saved["z"] = z
+        return dict(value=z[:, A:A + 1], z=z, rnn_hxs=rnn_out, feats=feats)
+
+    # ------------------------------------------------------------------ training minibatch
+    def train_minibatch(self, sample, clip_param, value_coef, entropy_coef, use_clipped_value_loss=True,
+                        global_rows=None, xcat_prefilled=None):
+        """Forward, fused PPO loss forward+backward, full backward for one minibatch
+        (PKG/algo/ppo.py:57-81).  Leaves d(loss)/d(params) in the flat gradient buffer and the three
+        loss partial sums at its tail; nothing is synchronised."""
+        obs, vobs, h0, actions, old_v, ret, masks, old_logp, adv = sample
+        out = self.forward(obs, vobs, h0, masks, keep=True, xcat_prefilled=xcat_prefilled)
+        L = lib()
+        sv = self._saved
+        B, H, A = sv["B"], self.H, self.A
+        st = self.stream
+        dev = self.device
+        z = sv["z"]
+        dz = self.buf("t_dz", B, A + 1)
+        self.flat_grad.zero_()                                              # optimizer.zero_grad(), ppo.py:79
+        loss_out = self.flat_grad[self.loss_off:self.loss_off + 3]
+        ws = _lib.workspace(L.ppd_ppo_loss_workspace(B), dev, "loss")
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        act = actions.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        check(L.ppd_ppo_loss_fwd_bwd(z.data_ptr(), A + 1, A, act.data_ptr(), f32(old_logp).data_ptr(), f32(adv).data_ptr(),
+                                     f32(old_v).data_ptr(), f32(ret).data_ptr(), B, int(global_rows or B),
+                                     float(clip_param), float(value_coef), float(entropy_coef),
+                                     int(bool(use_clipped_value_loss)), dz.data_ptr(), None, None, loss_out.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), st), "ppo_loss")
+        # ---- heads backward
+        feats = sv["hs"] if self.recurrent else sv["feat"]
+        self._gemm(dz, A + 1, 0, feats, H, 0, self.seg("heads.w", True), H, A + 1, H, B)
+        self._colsum(dz, A + 1, B, A + 1, self.seg("heads.b", True))
+        if self.recurrent:
+            T, E, Ipad = sv["T"], sv["E"], self.Ipad
+            dhs = self.buf("t_dhs", B, H)
+            self._gemm(dz, A + 1, 1, self.seg("heads.w"), H, 0, dhs, H, B, H, A + 1)
+            dgi = self.buf("t_dgi", B, 3 * H)
+            dghn = self.buf("t_dghn", B, H)
+            s0, s1, s2, s3 = (self.buf("t_s%d" % i, B, H) for i in range(4))
+            w_hh = self.seg("gru.w_hh")
+            check(L.ppd_gru_backward(dhs.data_ptr(), sv["m"].data_ptr(), w_hh.data_ptr(), sv["h0"].data_ptr(),
+                                     sv["hs"].data_ptr(), s0.data_ptr(), s1.data_ptr(), s2.data_ptr(), s3.data_ptr(),
+                                     T, E, H, dgi.data_ptr(), dghn.data_ptr(), None, st), "gru_backward")
+            hm = self.buf("t_hm", B, H)
+            check(L.ppd_gru_masked_prev(sv["hs"].data_ptr(), sv["h0"].data_ptr(), sv["m"].data_ptr(), T, E, H,
+                                        hm.data_ptr(), st), "masked_prev")
+            xcat = sv["xcat"]
+            gw_hh = self.seg("gru.w_hh", True)
+            self._gemm(dgi, 3 * H, 0, xcat, Ipad, 0, self.seg("gru.w_ih", True), Ipad, 3 * H, Ipad, B)
+            self._colsum(dgi, 3 * H, B, 3 * H, self.seg("gru.b_ih", True))
+            self._gemm(dgi, 3 * H, 0, hm, H, 0, gw_hh, H, 2 * H, H, B)                    # r, z rows of dW_hh
+            self._gemm(dghn, H, 0, hm, H, 0, gw_hh[2 * H * H:], H, H, H, B)                # n rows
+            gb_hh = self.seg("gru.b_hh", True)
+            gb_hh[:2 * H].copy_(self.seg("gru.b_ih", True)[:2 * H])                      # same sums for r, z
+            self._colsum(dghn, H, B, H, gb_hh[2 * H:])
+            # d(feat) = dgi W_ih[:, :H], masked by feat > 0 (ReLU of the FC layer)
+            dfeat = self.buf("t_dfeat", B, H)
+            self._gemm(dgi, 3 * H, 1, self.seg("gru.w_ih"), Ipad, 0, dfeat, H, B, H, 3 * H, mask=xcat, ldm=Ipad)
+        else:
+            dfeat = self.buf("t_dfeat", B, H)
+            self._gemm(dz, A + 1, 1, self.seg("heads.w"), H, 0, dfeat, H, B, H, A + 1, mask=feats, ldm=H)
+        self._trunk_backward(sv["obs"], B, dfeat, H)
+        return out
+
+    # ------------------------------------------------------------------ optimiser
+    def adam_step(self, lr, betas, eps, max_grad_norm, loss_acc=None, grad_norm_out=None):
+        """clip_grad_norm_ + Adam.step over the flat buffers (ppo.py:82-84)."""
+        self.bind()
+        L = lib()
+        stt = self.adam_state
+        stt["step"] += 1
+        n = self.n_params
+        ws = _lib.workspace(L.ppd_clip_adam_workspace(n), self.device, "adam")
+        loss_in = self.flat_grad[self.loss_off:self.loss_off + 3] if loss_acc is not None else None
+        check(L.ppd_clip_adam_step(self.flat.data_ptr(), self.flat_grad.data_ptr(), stt["exp_avg"].data_ptr(),
+                                   stt["exp_avg_sq"].data_ptr(), n, stt["step"], float(lr), float(betas[0]), float(betas[1]),
+                                   float(eps), float(max_grad_norm) if max_grad_norm else 0.0,
+                                   grad_norm_out.data_ptr() if grad_norm_out is not None else None,
+                                   loss_in.data_ptr() if loss_in is not None else None,
+                                   loss_acc.data_ptr() if loss_acc is not None else None,
+                                   ws.data_ptr(), ws.numel(), _lib.stream_ptr(self.device)), "clip_adam_step")

@@ -1,0 +1,167 @@
+"""GPU parity of the drop-in classes (Policy / PPO / RolloutStorage) against the golden fixtures
+recorded from the reference and against the oracle on seeded synthetic rollouts."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import policy as o_pol  # noqa: E402
+from oracle import ppo_update as o_upd  # noqa: E402
+from oracle import returns as o_ret  # noqa: E402
+import ppodash_b200 as ppd  # noqa: E402
+from ppodash_b200 import synthetic  # noqa: E402
+
+DEV = "cuda:0"
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = n
+        self.shape = ()
+
+
+def T_(x):
+    return torch.as_tensor(np.asarray(x))
+
+
+def params_of(g, prefix):
+    return {k[len(prefix):]: T_(g[k]) for k in g.files if k.startswith(prefix)}
+
+
+def make_policy(C, A, V, recurrent, H, state=None):
+    pol = ppd.Policy((C, 84, 84), Discrete(A), base_kwargs={"recurrent": recurrent, "hidden_size": H}, vector_obs_len=V)
+    if state is not None:
+        missing, unexpected = pol.load_state_dict(state, strict=True)
+        assert not missing and not unexpected
+    return pol.to(DEV)
+
+
+@pytest.mark.parametrize("fixture,recurrent,C,A,V", [("policy_recurrent", True, 2, 5, 3), ("policy_feedforward", False, 1, 6, 0)])
+def test_policy_forward_matches_reference(golden, fixture, recurrent, C, A, V):
+    g = golden(fixture)
+    pol = make_policy(C, A, V, recurrent, 32, params_of(g, "param."))
+    d = lambda k: T_(g[k]).to(DEV)
+    v, lp, ent, hx = pol.evaluate_actions(d("obs"), d("vobs"), d("h0"), d("masks"), d("actions"))
+    tol = dict(rtol=1e-5, atol=2e-6)     # stated fp32 tolerance (1e-5 relative, + 2e-6 absolute near zero)
+    np.testing.assert_allclose(v.cpu().numpy(), g["out.values"], **tol)
+    np.testing.assert_allclose(lp.cpu().numpy(), g["out.logp"], **tol)
+    np.testing.assert_allclose(ent.item(), float(g["out.entropy"]), **tol)
+    np.testing.assert_allclose(hx.cpu().numpy(), g["out.hxs"], **tol)
+    if recurrent:
+        E = int(g["E"])
+        v, a, lp, h = pol.act(d("obs")[:E], d("vobs")[:E], d("h0"), d("act_masks"), deterministic=True)
+        assert torch.equal(a.cpu(), T_(g["act_action"]))
+        np.testing.assert_allclose(v.cpu().numpy(), g["act_value"], **tol)
+        np.testing.assert_allclose(lp.cpu().numpy(), g["act_logp"], **tol)
+        np.testing.assert_allclose(h.cpu().numpy(), g["act_hxs"], **tol)
+        gv = pol.get_value(d("obs")[:E], d("vobs")[:E], d("h0"), d("act_masks"))
+        np.testing.assert_allclose(gv.cpu().numpy(), g["get_value"], **tol)
+        # stochastic act: shapes / dtypes / log-prob consistency (sampling uses the device RNG)
+        v, a, lp, h = pol.act(d("obs")[:E], d("vobs")[:E], d("h0"), d("act_masks"))
+        assert a.shape == (E, 1) and a.dtype == torch.int64 and lp.shape == (E, 1) and h.shape == (E, 32)
+
+
+@pytest.mark.parametrize("fixture,recurrent,C,A,V", [("policy_recurrent", True, 2, 5, 3), ("policy_feedforward", False, 1, 6, 0)])
+def test_minibatch_gradients_match_reference_autograd(golden, fixture, recurrent, C, A, V):
+    g = golden(fixture)
+    pol = make_policy(C, A, V, recurrent, 32, params_of(g, "param."))
+    eng = pol.engine()
+    d = lambda k: T_(g[k]).to(DEV)
+    sample = (d("obs"), d("vobs"), d("h0"), d("actions"), d("old_v"), d("ret"), d("masks"), d("old_logp"), d("adv"))
+    eng.train_minibatch(sample, float(g["clip"]), float(g["vcoef"]), float(g["ecoef"]))
+    loss = eng.flat_grad[eng.loss_off:eng.loss_off + 3].cpu().numpy()
+    np.testing.assert_allclose(loss[0], float(g["out.value_loss"]), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(loss[1], float(g["out.action_loss"]), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(loss[2], float(g["out.entropy"]), rtol=1e-5, atol=1e-7)
+    for name, p in pol.named_parameters():
+        ref = g["grad." + name]
+        got = p.grad.cpu().numpy()
+        scale = max(1e-6, float(np.abs(ref).max()))
+        # stated tolerance: 1e-5 relative to the largest gradient entry of the tensor + 1e-4 elementwise relative
+        np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5 * scale, err_msg=name)
+
+
+@pytest.mark.parametrize("tag,recurrent", [("recurrent", True), ("feedforward", False)])
+def test_ppo_update_matches_reference(golden, tag, recurrent):
+    g = golden("update_" + tag)
+    C, V, A, H, T, N = (int(g[k]) for k in ("C", "V", "A", "H", "T", "N"))
+    pol = make_policy(C, A, V, recurrent, H, params_of(g, "init."))
+    st = ppd.RolloutStorage(T, N, (C, 84, 84), [V], Discrete(A), H if recurrent else 1)
+    for k in ppd.RolloutStorage._FIELDS:
+        getattr(st, k).copy_(T_(g["roll." + k]))
+    st.to(DEV)
+    agent = ppd.algo.PPO(pol, float(g["clip"]), int(g["epochs"]), int(g["nmb"]), float(g["vcoef"]), float(g["ecoef"]),
+                         lr=float(g["lr"]), eps=float(g["eps"]), max_grad_norm=float(g["max_grad_norm"]))
+    torch.manual_seed(int(g["seed"]))
+    out = agent.update(st)
+    assert all(isinstance(x, float) for x in out)
+    np.testing.assert_allclose(np.array(out), g["losses"], rtol=1e-4, atol=1e-6)
+    lr = float(g["lr"])
+    for name, p in pol.state_dict().items():
+        ref = g["final." + name]
+        # after epochs*nmb Adam steps of at most lr each: agree to 2% of one step
+        np.testing.assert_allclose(p.cpu().numpy(), ref, rtol=0, atol=0.02 * lr, err_msg=name)
+
+
+def test_c2_shaped_minibatch_vs_oracle():
+    """PPO-Dash full shapes (C=3, V=15, A=8, H=512, recurrent), T=24 x E=4 rows, resets inside."""
+    torch.manual_seed(0)
+    pol = ppd.Policy((3, 84, 84), Discrete(8), base_kwargs={"recurrent": True}, vector_obs_len=15)
+    p_cpu = {k: v.clone() for k, v in pol.state_dict().items()}
+    pol = pol.to(DEV)
+    T, E = 24, 4
+    cfg = synthetic.RolloutConfig("t", T, E, 3, 15, 8, True, 1, 1, 1e-4, 0.001)
+    roll = synthetic.make_rollout(cfg, seed=3, reset_prob=0.05)
+    B = T * E
+    obs = roll["obs"][:T].reshape(B, 3, 84, 84)
+    vobs = roll["vector_obs"][:T].reshape(B, 15)
+    h0 = roll["recurrent_hidden_states"][0]
+    masks = roll["masks"][:T].reshape(B, 1)
+    actions = roll["actions"].reshape(B, 1)
+    gen = torch.Generator().manual_seed(1)
+    old_v = 0.1 * torch.randn(B, 1, generator=gen); ret = 0.3 * torch.randn(B, 1, generator=gen)
+    adv = torch.randn(B, 1, generator=gen)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p_cpu.items()}
+    v, lp, ent, hx = o_pol.evaluate_actions(pr, obs, vobs, h0, masks, actions, True, True)
+    old_logp = (lp + 0.05 * torch.randn(B, 1, generator=gen)).detach()
+    vl, al = o_upd.ppo_losses(v, lp, ent, old_v, ret, old_logp, adv, 0.1)
+    (vl * 0.5 + al - ent * 0.001).backward()
+    eng = pol.engine()
+    dd = lambda t: t.to(DEV)
+    out = eng.train_minibatch((dd(obs), dd(vobs), dd(h0), dd(actions), dd(old_v), dd(ret), dd(masks), dd(old_logp), dd(adv)),
+                              0.1, 0.5, 0.001)
+    np.testing.assert_allclose(out["value"].cpu().numpy(), v.detach().numpy(), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(out["rnn_hxs"].cpu().numpy(), hx.detach().numpy(), rtol=1e-5, atol=2e-6)
+    loss = eng.flat_grad[eng.loss_off:eng.loss_off + 3].cpu().numpy()
+    np.testing.assert_allclose(loss, [vl.item(), al.item(), ent.item()], rtol=1e-5, atol=1e-7)
+    for name, p in pol.named_parameters():
+        ref = pr[name].grad.numpy()
+        scale = max(1e-6, float(np.abs(ref).max()))
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ref, rtol=1e-4, atol=1e-5 * scale, err_msg=name)
+    # chunked trunk (rows processed 40 at a time) gives the same gradients
+    g1 = eng.flat_grad.clone()
+    eng.chunk_rows = 40
+    eng.train_minibatch((dd(obs), dd(vobs), dd(h0), dd(actions), dd(old_v), dd(ret), dd(masks), dd(old_logp), dd(adv)),
+                        0.1, 0.5, 0.001)
+    np.testing.assert_allclose(eng.flat_grad.cpu().numpy(), g1.cpu().numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_state_dict_roundtrip_and_rebind():
+    torch.manual_seed(1)
+    pol = ppd.Policy((1, 84, 84), Discrete(8), base_kwargs={"recurrent": True, "hidden_size": 32}, vector_obs_len=2)
+    ref = {k: v.clone() for k, v in pol.state_dict().items()}
+    pol = pol.to(DEV)
+    obs = torch.randn(4, 1, 84, 84, device=DEV); vo = torch.rand(4, 2, device=DEV)
+    h = torch.zeros(4, 32, device=DEV); m = torch.ones(4, 1, device=DEV)
+    v0 = pol.get_value(obs, vo, h, m).clone()
+    sd = pol.state_dict()                       # parameters are now views into the flat buffer
+    assert set(sd) == set(ref)
+    for k in ref:
+        assert sd[k].shape == ref[k].shape and torch.equal(sd[k].cpu(), ref[k]), k
+    import io
+    buf = io.BytesIO(); torch.save(pol, buf); buf.seek(0)          # run.py:259 pickles the whole module
+    pol2 = torch.load(buf, weights_only=False)
+    assert torch.equal(pol2.get_value(obs, vo, h, m), v0)
+    pol.cpu(); pol.to(DEV)                       # moving the module drops the views; the engine re-binds
+    assert torch.equal(pol.get_value(obs, vo, h, m), v0)
