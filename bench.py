@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- PPO update env-steps/s (+ GAE steps/s) of the PPO-Dash hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2]
+
+One "step" = one pass of the hot path over one synthetic rollout: compute_returns (GAE) followed
+by PPO.update (all epochs x minibatches: gathers, network fwd/bwd, fused loss, clip+Adam).
+Workload at N=1: BASELINE.json configs[1], "PPO-Dash full" (recurrent GRU + vector obs, 3x84x84
+obs, 32 envs x 512 steps, 8 epochs x 8 minibatches).  N>1: every rank owns the same number of
+envs (weak scaling, envs sharded over GPUs), gradients all-reduced with NCCL once per minibatch.
+
+Prints ONE JSON line (rank 0).  `value` = env-steps/s with the rollout resident in HBM; `e2e` = the
+same through the public API with the rollout in pinned HOST memory (H2D of every rollout field and
+D2H of the losses inside the timed region).  `--impl reference` times the reference algorithm's
+CPU path (the oracle port, torch-CPU with all host threads) on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c3_12", "c5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-micro", action="store_true", help="skip the GAE / gather microbenchmarks")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"), how="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, how="fallback")
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = n
+        self.shape = ()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference(cfg, minibatches, warm, reps=1, threads=None):
+    """Times the oracle port (torch-CPU restatement of PKG/algo/ppo.py + PKG/storage.py) on the box's
+    host cores.  One sample = `minibatches` minibatches of the update (of epochs*num_mini_batch) plus
+    the full compute_returns; the update time is extrapolated linearly to the full update."""
+    import numpy as np
+    import torch
+    from oracle import policy as o_pol
+    from oracle import ppo_update as o_upd
+    from oracle import returns as o_ret
+    from ppodash_b200 import synthetic
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    roll = synthetic.make_rollout(cfg, seed=1234)
+    torch.manual_seed(0)
+    p = o_pol.init_params(cfg.channels, cfg.num_actions, cfg.vector_obs_len, cfg.recurrent, cfg.hidden_size,
+                          concat_vector=cfg.recurrent)
+    state = o_upd.UpdateState(p, lr=cfg.lr, eps=cfg.eps)
+    times_gae, times_mb = [], []
+    total_mb = cfg.ppo_epoch * cfg.num_mini_batch
+    for it in range(warm + reps):
+        t0 = time.perf_counter()
+        ret, v = o_ret.returns_recurrence(roll["rewards"].numpy(), roll["value_preds"].numpy(), roll["masks"].numpy(),
+                                          roll["bad_masks"].numpy(), roll["next_value"].numpy(), True, cfg.gamma,
+                                          cfg.gae_lambda, False)
+        t1 = time.perf_counter()
+        r2 = dict(roll)
+        r2["returns"] = torch.from_numpy(ret)
+        r2["value_preds"] = torch.from_numpy(v)
+        torch.manual_seed(99)
+        o_upd.ppo_update(state, r2, recurrent=cfg.recurrent, clip_param=cfg.clip_param, ppo_epoch=cfg.ppo_epoch,
+                         num_mini_batch=cfg.num_mini_batch, value_loss_coef=cfg.value_loss_coef,
+                         entropy_coef=cfg.entropy_coef, max_grad_norm=cfg.max_grad_norm,
+                         concat_vector=cfg.recurrent, max_minibatches=minibatches)
+        t2 = time.perf_counter()
+        times_gae.append(t1 - t0)
+        times_mb.append((t2 - t1) / minibatches)
+    t_gae = min(times_gae)
+    t_mb = min(times_mb[warm:]) if warm < len(times_mb) else times_mb[-1]
+    t_step = t_gae + t_mb * total_mb
+    steps = cfg.num_envs * cfg.num_steps
+    return dict(value=steps / t_step, unit="env-steps/s", cores=cores, kind="port",
+                sample=f"{minibatches} of {total_mb} minibatches of one {cfg.name} update (+ full compute_returns), "
+                       f"best of {len(times_mb) - warm} after {warm} warm-up, extrapolated linearly; torch-CPU oracle port",
+                gae_steps_per_sec=steps / t_gae, sec_per_minibatch=t_mb, sec_per_step_extrapolated=t_step)
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    # each "step" = a bounded sample (1 minibatch + GAE) of the workload, see cpu_reference()
+    res = cpu_reference(cfg, minibatches=1, warm=min(1, args.warmup), reps=max(1, min(args.steps, 3)))
+    v = res["value"]
+    steps = cfg.num_envs * cfg.num_steps
+    line = dict(impl="reference", metric="ppo_update_env_steps_per_sec", value=v, unit="env-steps/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * steps / v, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=cfg.name, envs=cfg.num_envs, num_steps=cfg.num_steps, ppo_epoch=cfg.ppo_epoch,
+                            num_mini_batch=cfg.num_mini_batch, recurrent=cfg.recurrent),
+                cpu_baseline=dict(value=v, unit="env-steps/s", cores=res["cores"], kind="port", sample=res["sample"]),
+                e2e=dict(value=v, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gae_steps_per_sec=res["gae_steps_per_sec"], wall_s=time.perf_counter() - t0)
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args, cfg):
+    import torch
+    import torch.distributed as dist
+    import ppodash_b200 as ppd
+    from ppodash_b200 import _lib, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+
+    T, N = cfg.num_steps, cfg.num_envs
+    Hs = cfg.hidden_size if cfg.recurrent else 1
+    roll = synthetic.make_rollout(cfg, seed=1234 + rank)
+    host = {k: roll[k].pin_memory() for k in ppd.RolloutStorage._FIELDS}
+    nv_host = roll["next_value"].pin_memory()
+    st = ppd.RolloutStorage(T, N, (cfg.channels, cfg.obs_hw, cfg.obs_hw), [cfg.vector_obs_len], Discrete(cfg.num_actions), Hs)
+    st.to(dev)
+    torch.manual_seed(0)                      # identical initial weights on every rank
+    pol = ppd.Policy((cfg.channels, cfg.obs_hw, cfg.obs_hw), Discrete(cfg.num_actions),
+                     base_kwargs={"recurrent": cfg.recurrent, "hidden_size": cfg.hidden_size},
+                     vector_obs_len=cfg.vector_obs_len).to(dev)
+    agent = ppd.algo.PPO(pol, cfg.clip_param, cfg.ppo_epoch, cfg.num_mini_batch, cfg.value_loss_coef, cfg.entropy_coef,
+                         lr=cfg.lr, eps=cfg.eps, max_grad_norm=cfg.max_grad_norm)
+    nv_dev = torch.empty(N, 1, device=dev)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values()) + nv_host.numel() * 4
+
+    def upload():
+        for k, t in host.items():
+            getattr(st, k).copy_(t, non_blocking=True)
+        nv_dev.copy_(nv_host, non_blocking=True)
+
+    def step(with_upload):
+        if with_upload:
+            upload()
+        st.compute_returns(nv_dev, True, cfg.gamma, cfg.gae_lambda, False)
+        torch.manual_seed(99)
+        return agent.update(st)               # ends with the 3-float device->host read
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, with_upload):
+        barrier()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(nsteps):
+            out = step(with_upload)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), out
+
+    upload()
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    ms_total, losses = timed(args.steps, False)
+    launches = _lib.launch_count()
+    ms_e2e, _ = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- attribute the step to kernels (one extra, untimed-for-the-metric step with per-call CUDA events)
+    with _lib.profiled() as prof:
+        step(False)
+    per_kernel = prof.summary()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    steps_per_update = N * T * world
+    ms_step = ms_total / args.steps
+    value = steps_per_update / (ms_step * 1e-3)
+    e2e_value = steps_per_update / (ms_e2e / args.steps * 1e-3)
+    total_ms = sum(d["ms"] for d in per_kernel.values())
+    shares = sorted(((d["ms"], k, d["calls"]) for k, d in per_kernel.items()), reverse=True)
+    top_ms, top_name, top_calls = shares[0]
+
+    # ---- roofline of the dominant kernel (algorithmic work per launch / measured launch time)
+    H, V, A, C = cfg.hidden_size, cfg.vector_obs_len, cfg.num_actions, cfg.channels
+    E = N // cfg.num_mini_batch
+    rows_mb = T * E if cfg.recurrent else (T * N) // cfg.num_mini_batch
+    avg_ms = top_ms / top_calls
+    roof = dict(kernel=top_name, launches_per_step=top_calls, avg_ms_per_launch=avg_ms,
+                share_of_step=top_ms / total_ms if total_ms else None, traffic=None)
+    if top_name in ("ppd_gru_forward", "ppd_gru_backward"):
+        # recurrent matvec: fwd 2*3H*H flops per (step, env); bwd the same contraction transposed
+        flops = 2.0 * 3 * H * H * rows_mb
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        roof.update(bound="tensor", achieved=ach, peak=pk["bf16"], unit="TFLOP/s", frac=ach / pk["bf16"],
+                    latency_us_per_timestep=avg_ms * 1e3 / T,
+                    note=f"strictly sequential over T={T} with E={E} envs per minibatch: latency-bound (one grid "
+                         f"barrier per timestep), the tensor roofline is not reachable at this E (SURVEY.md 7); "
+                         f"peak = bf16 burst {pk['how']}")
+    elif top_name == "ppd_sgemm":
+        fwd = 2.0 * (819200 * C + 2654208 + 903168 + 802816) / (84 * 84 / (cfg.obs_hw * cfg.obs_hw))
+        flops_step = 3.0 * fwd * rows_mb * cfg.ppo_epoch * cfg.num_mini_batch
+        ach = flops_step / (top_ms * 1e-3) / 1e12
+        roof.update(bound="tensor", achieved=ach, peak=pk["bf16"], unit="TFLOP/s", frac=ach / pk["bf16"],
+                    note=f"fp32 SIMT GEMM family (parity mode), all launches of one step pooled; peak = bf16 burst {pk['how']}")
+    else:
+        row_bytes = C * cfg.obs_hw ** 2 * 4 + V * 4 + 8 + 5 * 4
+        bytes_launch = 2.0 * row_bytes * rows_mb
+        ach = bytes_launch / (avg_ms * 1e-3) / 1e9
+        roof.update(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
+                    note=f"peak = copy bandwidth {pk['how']}")
+
+    line = dict(metric="ppo_update_env_steps_per_sec", value=value, unit="env-steps/s", n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=cfg.name, envs_per_gpu=N, num_steps=T, obs=[C, cfg.obs_hw, cfg.obs_hw],
+                            vector_obs=V, actions=A, recurrent=cfg.recurrent, ppo_epoch=cfg.ppo_epoch,
+                            num_mini_batch=cfg.num_mini_batch, precision=pol.engine().precision,
+                            parallelism=f"env-sharded dp{world}",
+                            l2="rollout (%.2f GiB) larger than L2; no flush needed" % (h2d_bytes / 2**30)),
+                e2e=dict(value=e2e_value, unit="env-steps/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12,
+                         ms_per_step=ms_e2e / args.steps),
+                gpu_launches=launches, roofline=roof, clocks=clocks, losses=list(losses),
+                sample_passes_per_sec=value * cfg.ppo_epoch,
+                kernel_ms_per_step={k: round(ms, 3) for ms, k, _ in shares})
+
+    # ---- HBM-bound kernels at BASELINE config 4 size (GAE 4096 x 2048) and a gather sweep
+    if not args.no_micro:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import microbench as mb
+        g = mb.bench_gae(2048, 4096)
+        line["gae_steps_per_sec"] = g["steps_per_s"]
+        ks = [dict(kernel="returns_scan", config="4096 envs x 2048 steps", bound="hbm", achieved=g["gbs"], peak=pk["hbm"],
+                   unit="GB/s", frac=g["gbs"] / pk["hbm"], ms=g["ms"])]
+        gg = mb.bench_gather(512, 256, 3, 15, True, 8)
+        ks.append(dict(kernel="gather_recurrent", config="256 envs x 512 steps, 3x84x84", bound="hbm", achieved=gg["gbs"],
+                       peak=pk["hbm"], unit="GB/s", frac=gg["gbs"] / pk["hbm"], ms_epoch=gg["ms_epoch"]))
+        ad = mb.bench_adam(pol.engine().n_params)
+        ks.append(dict(kernel="clip_adam", config=f"{pol.engine().n_params} params", bound="hbm", achieved=ad["gbs"],
+                       peak=pk["hbm"], unit="GB/s", frac=ad["gbs"] / pk["hbm"], ms=ad["ms"]))
+        line["kernels"] = ks
+
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_reference(cfg, minibatches=2, warm=1)
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from ppodash_b200 import synthetic
+    cfg = synthetic.CONFIGS[args.workload]
+    if args.gpus > 1 and "RANK" not in os.environ and args.impl == "b200":
+        port = os.environ.get("MASTER_PORT", "29531")
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", port,
+                                   os.path.abspath(__file__)] + sys.argv[1:])
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_b200(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

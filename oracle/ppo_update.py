@@ -35,12 +35,14 @@ class UpdateState:
 
 def ppo_update(state, roll, *, recurrent, clip_param, ppo_epoch, num_mini_batch, value_loss_coef,
                entropy_coef, max_grad_norm, use_clipped_value_loss=True, concat_vector=True,
-               on_minibatch=None):
+               on_minibatch=None, max_minibatches=None):
     """Run all epochs x minibatches; returns (value_loss, action_loss, dist_entropy) means.
 
     ``roll`` holds torch CPU tensors under the reference attribute names.
     ``on_minibatch(k, info)`` (optional) receives per-minibatch losses and grads
-    before the optimiser step -- used by the parity tests.
+    before the optimiser step -- used by the parity tests.  ``max_minibatches`` stops early after
+    that many minibatches (bench.py times a bounded sample of the CPU path) and returns the means
+    over the minibatches actually run.
     """
     p = state.params
     adv = roll["returns"][:-1] - roll["value_preds"][:-1]
@@ -70,5 +72,7 @@ def ppo_update(state, roll, *, recurrent, clip_param, ppo_epoch, num_mini_batch,
             tot_a += a_loss.item()
             tot_e += entropy.item()
             k += 1
+            if max_minibatches is not None and k >= max_minibatches:
+                return tot_v / k, tot_a / k, tot_e / k
     n = ppo_epoch * num_mini_batch
     return tot_v / n, tot_a / n, tot_e / n

@@ -157,6 +157,54 @@ def workspace(nbytes, device, tag="default", zero=False):
     return buf
 
 
+class _Profile:
+    """CUDA-event timing of every C-ABI call made while active (used by bench.py to attribute the
+    step time to kernels).  Events are recorded on the stream the kernels are launched on."""
+
+    def __init__(self):
+        self.records = []          # (name, start_event, end_event)
+        self._saved = {}
+
+    def __enter__(self):
+        handle = lib()
+        for name in _PROTOTYPES:
+            fn = getattr(handle, name)
+            restype, argtypes = _PROTOTYPES[name]
+            if restype is not c_int or not argtypes:
+                continue
+            self._saved[name] = fn
+
+            def wrapped(*args, _fn=fn, _name=name):
+                a = torch.cuda.Event(enable_timing=True)
+                b = torch.cuda.Event(enable_timing=True)
+                a.record()
+                rc = _fn(*args)
+                b.record()
+                self.records.append((_name, a, b))
+                return rc
+            setattr(handle, name, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        handle = lib()
+        for name, fn in self._saved.items():
+            setattr(handle, name, fn)
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.records:
+            d = out.setdefault(name, dict(ms=0.0, calls=0))
+            d["ms"] += a.elapsed_time(b)
+            d["calls"] += 1
+        return out
+
+
+def profiled():
+    return _Profile()
+
+
 def launch_count():
     return int(lib().ppd_launch_count())
 
