@@ -221,6 +221,10 @@ int ppd_gru_backward(const float* dhs, const float* masks, const float* w_hh, co
                      void* stream);
 int ppd_gru_masked_prev(const float* hs, const float* h0, const float* masks, int T, int E, int H,
                         float* hm, void* stream);
+/* Kernel selection for the two calls above: 0 (default) = thread-block-cluster / DSMEM kernels when
+ * E <= 8 and H % 16 == 0 (one 16-CTA cluster per env, W_hh slices resident in shared memory, one
+ * cluster barrier per step), else the grid-cooperative kernels; 1 = always grid-cooperative. */
+void ppd_gru_set_mode(int mode);
 
 #ifdef __cplusplus
 }

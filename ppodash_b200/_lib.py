@@ -82,6 +82,7 @@ _PROTOTYPES = {
     "ppd_gru_forward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "ppd_gru_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "ppd_gru_masked_prev": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "ppd_gru_set_mode": (None, [c_int]),
 }
 
 _lib = None

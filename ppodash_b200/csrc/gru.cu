@@ -19,6 +19,17 @@
 
 namespace cg = cooperative_groups;
 
+namespace ppd {
+// gru_cluster.cu: cluster/DSMEM path for small E; returns -1 when it does not apply
+int gru_forward_cluster(const float* gi, const float* h0, const float* masks, const float* w_hh, const float* b_hh,
+                        int T, int E, int H, float* hs, float* h_last, float* sr, float* sz, float* sn, float* sghn,
+                        cudaStream_t s);
+int gru_backward_cluster(const float* dhs, const float* masks, const float* w_hh, const float* h0, const float* hs,
+                         const float* sr, const float* sz, const float* sn, const float* sghn, int T, int E, int H,
+                         float* dgi, float* dghn, float* dh0, cudaStream_t s);
+static int g_gru_mode = 0;   // 0 = auto (cluster path when it applies), 1 = always the grid-cooperative kernels
+}  // namespace ppd
+
 namespace {
 
 constexpr int kThreads = 384;
@@ -278,6 +289,11 @@ extern "C" int ppd_gru_forward(const float* gi, const float* h0, const float* ma
     PPD_REQUIRE(T > 0 && E > 0 && H > 0, "sizes must be positive");
     PPD_REQUIRE((save_r != nullptr) == (save_z != nullptr) && (save_r != nullptr) == (save_n != nullptr) &&
                 (save_r != nullptr) == (save_ghn != nullptr), "save buffers must be all set or all NULL");
+    if (ppd::g_gru_mode == 0) {
+        const int rc = ppd::gru_forward_cluster(gi, h0, masks, w_hh, b_hh, T, E, H, hs, h_last, save_r, save_z, save_n,
+                                                save_ghn, ppd::as_stream(stream));
+        if (rc >= 0) return rc;
+    }
     Cfg c;
     if (pick(gru_fwd_kernel, true, E, H, &c)) {
         ppd::set_error("ppd_gru_forward: no co-resident tiling for E=%d H=%d", E, H);
@@ -302,6 +318,11 @@ extern "C" int ppd_gru_backward(const float* dhs, const float* masks, const floa
     PPD_REQUIRE(dhs && masks && w_hh && h0 && hs && save_r && save_z && save_n && save_ghn && dgi && dghn,
                 "null pointer");
     PPD_REQUIRE(T > 0 && E > 0 && H > 0, "sizes must be positive");
+    if (ppd::g_gru_mode == 0) {
+        const int rc = ppd::gru_backward_cluster(dhs, masks, w_hh, h0, hs, save_r, save_z, save_n, save_ghn, T, E, H, dgi,
+                                                 dghn, dh0, ppd::as_stream(stream));
+        if (rc >= 0) return rc;
+    }
     Cfg c;
     if (pick(gru_bwd_kernel, false, E, H, &c)) {
         ppd::set_error("ppd_gru_backward: no co-resident tiling for E=%d H=%d", E, H);
@@ -318,6 +339,8 @@ extern "C" int ppd_gru_backward(const float* dhs, const float* masks, const floa
     }
     return ppd::launch_status("gru_bwd_kernel");
 }
+
+extern "C" void ppd_gru_set_mode(int mode) { ppd::g_gru_mode = mode; }
 
 extern "C" int ppd_gru_masked_prev(const float* hs, const float* h0, const float* masks, int T, int E, int H,
                                    float* hm, void* stream) {

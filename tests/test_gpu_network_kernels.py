@@ -137,8 +137,19 @@ def test_batched_transpose():
     assert torch.equal(y.cpu(), x.transpose(1, 2).contiguous())
 
 
-@pytest.mark.parametrize("T,E,H,I", [(5, 3, 32, 35), (16, 4, 512, 527), (1, 32, 512, 527), (4, 40, 64, 64), (64, 4, 512, 527)])
-def test_gru_forward_backward_vs_torch(T, E, H, I):
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("T,E,H,I", [(5, 3, 32, 35), (16, 4, 512, 527), (1, 32, 512, 527), (4, 40, 64, 64), (64, 4, 512, 527),
+                                     (1, 2, 512, 527), (33, 8, 512, 512)])
+def test_gru_forward_backward_vs_torch(T, E, H, I, mode):
+    """mode 0: cluster/DSMEM kernels where they apply (E <= 8); mode 1: grid-cooperative kernels."""
+    _lib.lib().ppd_gru_set_mode(mode)
+    try:
+        _gru_case(T, E, H, I)
+    finally:
+        _lib.lib().ppd_gru_set_mode(0)
+
+
+def _gru_case(T, E, H, I):
     g = torch.Generator().manual_seed(T * 100 + E)
     p = {"base.gru.weight_ih_l0": torch.randn(3 * H, I, generator=g) / np.sqrt(I),
          "base.gru.weight_hh_l0": torch.randn(3 * H, H, generator=g) / np.sqrt(H),
