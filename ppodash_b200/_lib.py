@@ -73,6 +73,9 @@ _PROTOTYPES = {
                                              _P, _P]),
     "ppd_sgemm_workspace": (c_size_t, [c_int64, c_int64, c_int64]),
     "ppd_sgemm": (c_int, [POINTER(GemmArgs), _P, c_size_t, _P]),
+    "ppd_tc_gemm_workspace": (c_size_t, [c_int64, c_int64, c_int64]),
+    "ppd_tc_gemm_supported": (c_int, [POINTER(GemmArgs)]),
+    "ppd_tc_gemm": (c_int, [POINTER(GemmArgs), c_int, _P, c_size_t, _P]),
     "ppd_colsum_workspace": (c_size_t, [c_int64, c_int64]),
     "ppd_colsum": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, _P, c_size_t, _P]),
     "ppd_im2col_nchw": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P]),

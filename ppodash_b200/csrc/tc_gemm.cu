@@ -1,0 +1,434 @@
+// tcgen05 (5th-gen tensor core) GEMM for the policy network's dense contractions, TF32 inputs with
+// fp32 accumulation in tensor memory.  Same problem statement as sgemm.cu:
+//   C[i,j] (+)= sum_kk OpA(i,kk) * OpB(j,kk),  operands row-major fp32 in HBM, either contraction-
+//   contiguous ("k-major": OpA(i,kk) = A[i*lda + kk]) or output-contiguous ("mn-major": A[kk*lda + i]).
+// fp32 operands are fed to the tensor cores as they are (kind::tf32 reads the top 19 bits), so there
+// are no conversion passes and no second copy of weights or activations.
+//
+// Structure (one 128 x BLOCK_N output tile per CTA, optional split of the contraction over gridDim.z):
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d loads of 128B-swizzled tiles into a 4-stage
+//            shared-memory ring, completion on mbarriers (expect_tx)
+//   warp 1   MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BLOCK_N,
+//            K=8 per instruction, 4 per 32-wide k-block) from shared-memory descriptors into a TMEM
+//            accumulator; tcgen05.commit releases ring slots / signals the epilogue
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias / ReLU / ReLU-backward mask /
+//            accumulate, vectorised global stores (or transposed stores, or raw split-K partials)
+// Shared-memory tile layouts are the canonical UMMA ones (cute/atom/mma_traits_sm100.hpp):
+//   k-major : rows of 32 floats (128 B), 8-row 1024 B swizzle atoms, SBO = 1024 B; one TMA box
+//             {32 k, rows}; successive MMAs advance the descriptor start address by 32 B
+//   mn-major: 1024 B atoms of [8 k][32 mn]; one TMA box {32 mn, 32 k} per 32 output rows, atoms along
+//             mn LBO = 4096 B apart, along k SBO = 1024 B apart; successive MMAs advance by 1024 B
+#include <cuda.h>
+
+#include "ppd_common.cuh"
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr int BM = 128;            // UMMA M
+constexpr int BK = 32;             // floats per k-block (one 128-byte swizzle row)
+constexpr int kTmemCols = 256;
+
+struct Args {
+    float* C; int64_t ldc;
+    int64_t I, J, KK;
+    const float* bias; const float* mask; int64_t ldm;
+    int relu, accumulate, transpose_out;
+    int block_n, a_mn, b_mn;
+    int64_t kk_per_split;
+    float* partial;
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
+// version 1 <<46 | layout SWIZZLE_128B (2) <<61
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format TF32 (2) @7/@10,
+// a_major @15, b_major @16, N>>3 @17, M>>4 @24
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
+    uint32_t d = 0;
+    d |= 1u << 4;
+    d |= 2u << 7;
+    d |= 2u << 10;
+    d |= (uint32_t)(a_mn ? 1 : 0) << 15;
+    d |= (uint32_t)(b_mn ? 1 : 0) << 16;
+    d |= (uint32_t)(n >> 3) << 17;
+    d |= (uint32_t)(BM >> 4) << 24;
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    // 1024-byte aligned ring: [stage][A tile 16 KB | B tile block_n*128 B]
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int bn = a.block_n;
+    const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)bn * BK * 4;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i0 = (int64_t)blockIdx.y * BM;
+    const int64_t j0 = (int64_t)blockIdx.x * bn;
+    const int64_t kk_begin = (int64_t)blockIdx.z * a.kk_per_split;
+    const int64_t kk_end = min(a.KK, kk_begin + a.kk_per_split);
+    const int nkb = (int)((kk_end - kk_begin + BK - 1) / BK);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* sa = smem + (size_t)s * stage_bytes;
+                uint8_t* sb = sa + a_bytes;
+                mbar_expect_tx(&full_bar[s], stage_bytes);
+                const int kk = (int)(kk_begin + (int64_t)kb * BK);
+                if (!a.a_mn) {
+                    tma_load_2d(&tmA, &full_bar[s], sa, kk, (int)i0);                         // box {32 k, 128 rows}
+                } else {
+                    for (int q = 0; q < BM / 32; ++q)                                          // box {32 rows(i), 32 k}
+                        tma_load_2d(&tmA, &full_bar[s], sa + q * 4096, (int)i0 + 32 * q, kk);
+                }
+                if (!a.b_mn) {
+                    tma_load_2d(&tmB, &full_bar[s], sb, kk, (int)j0);                         // box {32 k, block_n rows}
+                } else {
+                    for (int q = 0; q < bn / 32; ++q)
+                        tma_load_2d(&tmB, &full_bar[s], sb + q * 4096, (int)j0 + 32 * q, kk);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer
+            const uint32_t idesc = make_idesc(bn, a.a_mn, a.b_mn);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t sb = sa + a_bytes;
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t da = a.a_mn ? make_desc(sa + k * 1024, 4096, 1024) : make_desc(sa + k * 32, 0, 1024);
+                    const uint64_t db = a.b_mn ? make_desc(sb + k * 1024, 4096, 1024) : make_desc(sb + k * 32, 0, 1024);
+                    umma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);          // ring slot free once these MMAs have read it
+            }
+            umma_commit(&tmem_full_bar);             // accumulator complete
+        }
+    } else {
+        // ================= epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+        const int q = warp & 3;
+        mbar_wait(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t i = i0 + q * 32 + lane;
+        for (int c0 = 0; c0 < bn; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (nkb == 0) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = 0.f;
+            }
+            const int64_t jb = j0 + c0;
+            if (a.partial) {
+                if (i < a.I) {
+                    float* P = a.partial + ((int64_t)blockIdx.z * a.I + i) * a.J;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (jb + c < a.J) P[jb + c] = v[c];
+                }
+                continue;
+            }
+            if (a.bias) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] += (jb + c < a.J) ? __ldg(a.bias + jb + c) : 0.f;
+            }
+            if (a.relu) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+            }
+            if (a.transpose_out) {
+                // C is [J, I] row-major: for fixed column the 32 lanes write 32 consecutive floats
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (i < a.I && jb + c < a.J) {
+                        float* p = a.C + (jb + c) * a.ldc + i;
+                        float x = v[c];
+                        if (a.mask) x = (__ldg(a.mask + (jb + c) * a.ldm + i) > 0.f) ? x : 0.f;
+                        *p = a.accumulate ? (*p + x) : x;
+                    }
+                }
+            } else if (i < a.I) {
+                float* crow = a.C + i * a.ldc + jb;
+                const float* mrow = a.mask ? a.mask + i * a.ldm + jb : nullptr;
+                const bool vec = (jb + 31 < a.J) && ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) &&
+                                 (!mrow || (((a.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)));
+                if (vec) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        float4 x = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                        if (mrow) {
+                            const float4 m = __ldg(reinterpret_cast<const float4*>(mrow + c));
+                            x.x = m.x > 0.f ? x.x : 0.f; x.y = m.y > 0.f ? x.y : 0.f;
+                            x.z = m.z > 0.f ? x.z : 0.f; x.w = m.w > 0.f ? x.w : 0.f;
+                        }
+                        float4* p = reinterpret_cast<float4*>(crow + c);
+                        if (a.accumulate) { const float4 o = *p; x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w; }
+                        *p = x;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if (jb + c < a.J) {
+                            float x = v[c];
+                            if (mrow) x = (__ldg(mrow + c) > 0.f) ? x : 0.f;
+                            crow[c] = a.accumulate ? (crow[c] + x) : x;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tc_splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t I, int64_t J, float* __restrict__ C,
+                        int64_t ldc, const float* __restrict__ bias, const float* __restrict__ mask, int64_t ldm,
+                        int relu, int accumulate, int transpose_out) {
+    const int64_t n = I * J;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
+        float v = 0.f;
+        for (int z = 0; z < splits; ++z) v += partial[(int64_t)z * n + e];
+        const int64_t i = e / J, j = e - i * J;
+        if (bias) v += __ldg(bias + j);
+        if (relu) v = fmaxf(v, 0.f);
+        const int64_t co = transpose_out ? (j * ldc + i) : (i * ldc + j);
+        if (mask) v = (__ldg(mask + (transpose_out ? (j * ldm + i) : (i * ldm + j))) > 0.f) ? v : 0.f;
+        C[co] = accumulate ? (C[co] + v) : v;
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map over a row-major matrix [rows, cols] (cols contiguous, row stride ld floats),
+// box = {box_cols, box_rows}, 128-byte swizzle, out-of-bounds elements read as zero.
+int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { ppd::set_error("ppd_tc_gemm: cuTensorMapEncodeTiled not available"); return PPD_EINVAL; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ppd::set_error("ppd_tc_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r); return PPD_EINVAL; }
+    return 0;
+}
+
+struct Plan { int bn; int64_t gx, gy; int splits; int64_t kk_per_split; size_t ws; };
+
+int pick_bn(int64_t J) {
+    if (J <= 32) return 32;
+    if (J <= 64) return 64;
+    if (J <= 128) return 128;
+    if (J <= 256 && J > 192) return 256;
+    return 128;
+}
+
+Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_avail, bool limit) {
+    Plan p;
+    p.bn = pick_bn(J);
+    p.gx = (J + p.bn - 1) / p.bn;
+    p.gy = (I + BM - 1) / BM;
+    const int64_t tiles = p.gx * p.gy;
+    int64_t splits = 1;
+    const int64_t target = 2 * ppd::kNumSMs;
+    if (tiles < target && KK >= 16 * BK) {
+        splits = (target + tiles - 1) / tiles;
+        const int64_t max_splits = KK / (8 * BK);
+        if (splits > max_splits) splits = max_splits;
+        if (splits > 1024) splits = 1024;
+        if (splits < 1) splits = 1;
+    }
+    if (limit) {
+        while (splits > 1 && (size_t)splits * I * J * sizeof(float) > ws_avail) --splits;
+    }
+    int64_t per = (KK + splits - 1) / splits;
+    per = (per + BK - 1) / BK * BK;
+    splits = (KK + per - 1) / per;
+    if (splits < 1) splits = 1;
+    p.splits = (int)splits;
+    p.kk_per_split = per;
+    p.ws = splits > 1 ? (size_t)splits * I * J * sizeof(float) : 0;
+    return p;
+}
+
+}  // namespace
+
+extern "C" size_t ppd_tc_gemm_workspace(int64_t I, int64_t J, int64_t KK) {
+    if (I <= 0 || J <= 0 || KK <= 0) return 0;
+    return make_plan(I, J, KK, 0, false).ws;
+}
+
+// 1 if ppd_tc_gemm can run this problem (alignment of the operands for TMA), else 0.
+extern "C" int ppd_tc_gemm_supported(const ppd_gemm_args* g) {
+    if (!g || !g->A || !g->B || !g->C) return 0;
+    if (g->I <= 0 || g->J <= 0 || g->KK <= 0) return 0;
+    if ((g->lda & 3) || (g->ldb & 3)) return 0;
+    if (((uintptr_t)g->A & 15) || ((uintptr_t)g->B & 15)) return 0;
+    if (g->I > 0x7fffffffLL || g->J > 0x7fffffffLL || g->KK > 0x7fffffffLL) return 0;
+    return 1;
+}
+
+extern "C" int ppd_tc_gemm(const ppd_gemm_args* g, int transpose_out, void* workspace, size_t workspace_bytes, void* stream) {
+    PPD_REQUIRE(ppd_tc_gemm_supported(g), "operands must be 16-byte aligned with leading dimensions that are multiples of 4");
+    PPD_REQUIRE(transpose_out ? g->ldc >= g->I : g->ldc >= g->J, "bad ldc");
+    const Plan p = make_plan(g->I, g->J, g->KK, workspace ? workspace_bytes : 0, true);
+    PPD_REQUIRE(p.gy <= 65535 && p.splits <= 65535, "grid too large");
+    CUtensorMap tmA, tmB;
+    int rc;
+    // k-major operand: matrix [rows = I or J, cols = KK]; mn-major: matrix [rows = KK, cols = I or J]
+    if (g->a_kmajor) rc = make_map(&tmA, g->A, g->I, g->KK, g->lda, BK, BM);
+    else             rc = make_map(&tmA, g->A, g->KK, g->I, g->lda, 32, BK);
+    if (rc) return rc;
+    if (g->b_kmajor) rc = make_map(&tmB, g->B, g->J, g->KK, g->ldb, BK, p.bn);
+    else             rc = make_map(&tmB, g->B, g->KK, g->J, g->ldb, 32, BK);
+    if (rc) return rc;
+    Args a;
+    a.C = g->C; a.ldc = g->ldc; a.I = g->I; a.J = g->J; a.KK = g->KK;
+    a.bias = g->bias; a.mask = g->mask; a.ldm = g->ldm; a.relu = g->relu; a.accumulate = g->accumulate;
+    a.transpose_out = transpose_out;
+    a.block_n = p.bn; a.a_mn = g->a_kmajor ? 0 : 1; a.b_mn = g->b_kmajor ? 0 : 1;
+    a.kk_per_split = p.kk_per_split;
+    a.partial = p.splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
+    const size_t smem = (size_t)kStages * (BM * BK * 4 + (size_t)p.bn * BK * 4) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) { ppd::set_error("ppd_tc_gemm: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
+        attr_set = true;
+    }
+    cudaStream_t s = ppd::as_stream(stream);
+    dim3 grid((unsigned)p.gx, (unsigned)p.gy, (unsigned)p.splits);
+    tc_gemm_kernel<<<grid, kThreads, smem, s>>>(tmA, tmB, a);
+    rc = ppd::launch_status("tc_gemm_kernel");
+    if (rc || p.splits == 1) return rc;
+    int64_t nb = (g->I * g->J + 255) / 256;
+    if (nb > 4 * ppd::kNumSMs) nb = 4 * ppd::kNumSMs;
+    tc_splitk_reduce_kernel<<<(unsigned)nb, 256, 0, s>>>(a.partial, p.splits, g->I, g->J, g->C, g->ldc, g->bias, g->mask,
+                                                         g->ldm, g->relu, g->accumulate, transpose_out);
+    return ppd::launch_status("tc_splitk_reduce_kernel");
+}

@@ -194,3 +194,71 @@ def _gru_case(T, E, H, I):
     dgh = torch.cat([dgi[:, :2 * H], dghn], 1).cpu()
     dwhh = dgh.t() @ hm.cpu()
     np.testing.assert_allclose(dwhh.numpy(), w_hh.grad.numpy(), rtol=1e-4, atol=5e-5)
+
+
+# --------------------------------------------------------------------------- tcgen05 TF32 GEMM
+def tc_gemm(A, lda, a_k, Bm, ldb, b_k, C, ldc, I, J, KK, bias=None, mask=None, ldm=0, relu=0, acc=0, transpose_out=0):
+    L = _lib.lib()
+    g = GemmArgs()
+    g.A, g.lda, g.a_kmajor = A.data_ptr(), lda, a_k
+    g.B, g.ldb, g.b_kmajor = Bm.data_ptr(), ldb, b_k
+    g.C, g.ldc = C.data_ptr(), ldc
+    g.I, g.J, g.KK = I, J, KK
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.mask = mask.data_ptr() if mask is not None else None
+    g.ldm = ldm
+    g.relu, g.accumulate = relu, acc
+    assert L.ppd_tc_gemm_supported(ctypes.byref(g)) == 1
+    ws = _lib.workspace(L.ppd_tc_gemm_workspace(I, J, KK), DEV, "tcgemm")
+    _lib.check(L.ppd_tc_gemm(ctypes.byref(g), transpose_out, ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+
+
+def _tf32_close(got, want, K):
+    """TF32 inputs carry a 10-bit mantissa (rel. 2^-11 each); stated tolerance for a length-K dot product
+    of O(1)-scaled terms: 4e-3 * sqrt-free bound on the row scale."""
+    scale = float(want.abs().max()) + 1e-6
+    err = float((got - want).abs().max())
+    assert err <= 4e-3 * scale, (err, scale, K)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 32), (4096, 32, 192), (1000, 64, 512), (777, 32, 576), (2048, 512, 1568),
+                                   (2048, 1536, 528), (130, 100, 40)])
+def test_tc_gemm_forward_k_major(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    X = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / np.sqrt(K)
+    b = torch.randn(N, generator=g)
+    want = torch.relu(X.double() @ W.double().t() + b.double()).float()
+    C = torch.full((M, N + 4), -5.0, device=DEV)
+    tc_gemm(X.to(DEV), K, 1, W.to(DEV), K, 1, C, N + 4, M, N, K, bias=b.to(DEV), relu=1)
+    _tf32_close(C[:, :N].cpu(), want, K)
+    assert torch.all(C[:, N:] == -5.0)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 64), (3000, 32, 576), (1000, 64, 512), (2048, 512, 1568), (2048, 1536, 512)])
+def test_tc_gemm_dgrad_b_mn_major_with_mask(M, N, K):
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    dY = torch.randn(M, N, generator=g)
+    W = torch.randn(N, K, generator=g) / np.sqrt(N)
+    act = torch.randn(M, K, generator=g)
+    want = ((dY.double() @ W.double()) * (act > 0)).float()
+    dX = torch.zeros(M, K, device=DEV)
+    tc_gemm(dY.to(DEV), N, 1, W.to(DEV), K, 0, dX, K, M, K, N, mask=act.to(DEV), ldm=K)
+    _tf32_close(dX.cpu(), want, N)
+
+
+@pytest.mark.parametrize("M,N,K,swap", [(4096, 128, 192, False), (81 * 64, 64, 512, True), (2048, 512, 1568, False),
+                                        (2048, 1536, 528, False), (40000, 32, 192, True), (5000, 32, 576, True)])
+def test_tc_gemm_wgrad_both_mn_major_splitk(M, N, K, swap):
+    g = torch.Generator().manual_seed(M + 7 * N + K)
+    dY = torch.randn(M, N, generator=g) / np.sqrt(M)
+    X = torch.randn(M, K, generator=g)
+    dW0 = torch.randn(N, K, generator=g)
+    want = (dW0.double() + dY.double().t() @ X.double()).float()
+    dW = dW0.to(DEV).clone()
+    if swap:   # wide dimension (K) on the 128-row MMA axis, result stored transposed into dW[N, K]
+        tc_gemm(X.to(DEV), K, 0, dY.to(DEV), N, 0, dW, K, K, N, M, acc=1, transpose_out=1)
+    else:
+        tc_gemm(dY.to(DEV), N, 0, X.to(DEV), K, 0, dW, K, N, K, M, acc=1)
+    scale = float((want - dW0).abs().max()) + 1e-6
+    assert float((dW.cpu() - want).abs().max()) <= 4e-3 * scale
