@@ -34,6 +34,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c3_12", "c5"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"],
+                    help="GEMM arithmetic of the policy network (see PolicyEngine.set_precision)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-micro", action="store_true", help="skip the GAE / gather microbenchmarks")
     return ap.parse_args()
@@ -196,6 +198,7 @@ def run_b200(args, cfg):
     pol = ppd.Policy((cfg.channels, cfg.obs_hw, cfg.obs_hw), Discrete(cfg.num_actions),
                      base_kwargs={"recurrent": cfg.recurrent, "hidden_size": cfg.hidden_size},
                      vector_obs_len=cfg.vector_obs_len).to(dev)
+    pol.engine(args.precision)
     agent = ppd.algo.PPO(pol, cfg.clip_param, cfg.ppo_epoch, cfg.num_mini_batch, cfg.value_loss_coef, cfg.entropy_coef,
                          lr=cfg.lr, eps=cfg.eps, max_grad_norm=cfg.max_grad_norm)
     nv_dev = torch.empty(N, 1, device=dev)
@@ -278,12 +281,13 @@ def run_b200(args, cfg):
                     note=f"strictly sequential over T={T} with E={E} envs per minibatch: latency-bound (one grid "
                          f"barrier per timestep), the tensor roofline is not reachable at this E (SURVEY.md 7); "
                          f"peak = bf16 burst {pk['how']}")
-    elif top_name == "ppd_sgemm":
+    elif top_name in ("ppd_sgemm", "ppd_tc_gemm"):
         fwd = 2.0 * (819200 * C + 2654208 + 903168 + 802816) / (84 * 84 / (cfg.obs_hw * cfg.obs_hw))
         flops_step = 3.0 * fwd * rows_mb * cfg.ppo_epoch * cfg.num_mini_batch
         ach = flops_step / (top_ms * 1e-3) / 1e12
         roof.update(bound="tensor", achieved=ach, peak=pk["bf16"], unit="TFLOP/s", frac=ach / pk["bf16"],
-                    note=f"fp32 SIMT GEMM family (parity mode), all launches of one step pooled; peak = bf16 burst {pk['how']}")
+                    note=f"GEMM family ({args.precision}), all launches of one step pooled against the network's 3x-forward "
+                         f"training FLOPs; peak = bf16 burst {pk['how']}")
     else:
         row_bytes = C * cfg.obs_hw ** 2 * 4 + V * 4 + 8 + 5 * 4
         bytes_launch = 2.0 * row_bytes * rows_mb
@@ -293,7 +297,8 @@ def run_b200(args, cfg):
 
     line = dict(metric="ppo_update_env_steps_per_sec", value=value, unit="env-steps/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic",
+                dtype={"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core split, fp32-level accuracy)",
+                       "tf32": "tf32"}[args.precision], data="synthetic",
                 config=dict(workload=cfg.name, envs_per_gpu=N, num_steps=T, obs=[C, cfg.obs_hw, cfg.obs_hw],
                             vector_obs=V, actions=A, recurrent=cfg.recurrent, ppo_epoch=cfg.ppo_epoch,
                             num_mini_batch=cfg.num_mini_batch, precision=pol.engine().precision,

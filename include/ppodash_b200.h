@@ -180,13 +180,19 @@ int ppd_sgemm(const ppd_gemm_args* g, void* workspace, size_t workspace_bytes, v
 /* Same contraction on the 5th-generation tensor cores: tcgen05.mma kind::tf32 (fp32 operands read as
  * TF32, fp32 accumulation in tensor memory), TMA-fed 4-stage shared-memory ring.  Operands must be
  * 16-byte aligned with leading dimensions that are multiples of 4 floats (ppd_tc_gemm_supported).
- * transpose_out != 0 stores the result transposed (C is then [J, I] with row stride ldc; bias is
- * still indexed by j and mask uses C's layout) -- used to put the wide dimension of a weight
- * gradient on the 128-row MMA axis.  "tf32" precision mode of the network; results agree with the
- * fp32 kernels to ~1e-3 relative (10-bit mantissa inputs), not to the 1e-5 parity gate. */
+ * flags:
+ *   PPD_TC_TRANSPOSE_OUT  store the result transposed (C is then [J, I] with row stride ldc; bias is
+ *                         still indexed by j and mask uses C's layout) -- puts the wide dimension of a
+ *                         weight gradient on the 128-row MMA axis;
+ *   PPD_TC_SPLIT3         "3xTF32": every operand tile x is split in shared memory into hi (the 19 bits
+ *                         the tensor core reads) and lo = x - hi, and A_lo*B_hi + A_hi*B_lo + A_hi*B_hi is
+ *                         accumulated, which restores fp32-level accuracy (~1e-6 relative) on the
+ *                         tensor cores.  Without it ("tf32" mode) results agree with fp32 to ~1e-3. */
+#define PPD_TC_TRANSPOSE_OUT 1
+#define PPD_TC_SPLIT3 2
 size_t ppd_tc_gemm_workspace(int64_t I, int64_t J, int64_t KK);
 int ppd_tc_gemm_supported(const ppd_gemm_args* g);
-int ppd_tc_gemm(const ppd_gemm_args* g, int transpose_out, void* workspace, size_t workspace_bytes, void* stream);
+int ppd_tc_gemm(const ppd_gemm_args* g, int flags, void* workspace, size_t workspace_bytes, void* stream);
 /* out[j] (+)= sum_i X[i*ld + j]  (bias gradients) */
 size_t ppd_colsum_workspace(int64_t I, int64_t J);
 int ppd_colsum(const float* X, int64_t ld, int64_t I, int64_t J, float* out, int accumulate,

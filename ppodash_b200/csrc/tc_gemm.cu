@@ -16,16 +16,19 @@
 // Shared-memory tile layouts are the canonical UMMA ones (cute/atom/mma_traits_sm100.hpp):
 //   k-major : rows of 32 floats (128 B), 8-row 1024 B swizzle atoms, SBO = 1024 B; one TMA box
 //             {32 k, rows}; successive MMAs advance the descriptor start address by 32 B
-//   mn-major: 1024 B atoms of [8 k][32 mn]; one TMA box {32 mn, 32 k} per 32 output rows, atoms along
-//             mn LBO = 4096 B apart, along k SBO = 1024 B apart; successive MMAs advance by 1024 B
+//   mn-major: 32-bit mn-major operands must use the 128B swizzle with 32-byte atomicity
+//             (UMMA SWIZZLE_128B_BASE32B / TMA SWIZZLE_128B_ATOM_32B): 512 B atoms of [4 k][32 mn]; one
+//             TMA box {32 mn, 32 k} per 32 output rows, atoms along mn LBO = 4096 B apart, along k
+//             SBO = 512 B apart; successive MMAs (8 k each) advance by 1024 B
 #include <cuda.h>
 
 #include "ppd_common.cuh"
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;
 constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;   // warps 2-5
 constexpr int BM = 128;            // UMMA M
 constexpr int BK = 32;             // floats per k-block (one 128-byte swizzle row)
 constexpr int kTmemCols = 256;
@@ -36,6 +39,8 @@ struct Args {
     const float* bias; const float* mask; int64_t ldm;
     int relu, accumulate, transpose_out;
     int block_n, a_mn, b_mn;
+    int split3;                // 3xTF32: also multiply the low-order residuals (fp32-level accuracy)
+    int stages;
     int64_t kk_per_split;
     float* partial;
 };
@@ -98,16 +103,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
-// version 1 <<46 | layout SWIZZLE_128B (2) <<61
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// version 1 <<46 | layout type <<61
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout << 61;
     return d;
 }
+constexpr uint32_t kLayoutSw128 = 2;        // UMMA::LayoutType::SWIZZLE_128B          (k-major tiles)
+constexpr uint32_t kLayoutSw128Base32 = 1;  // UMMA::LayoutType::SWIZZLE_128B_BASE32B  (mn-major 32-bit tiles)
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format TF32 (2) @7/@10,
 // a_major @15, b_major @16, N>>3 @17, M>>4 @24
@@ -126,16 +133,19 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-    __shared__ __align__(8) uint64_t empty_bar[kStages];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t ready_bar[kMaxStages];     // split3: residual tiles written
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
 
-    // 1024-byte aligned ring: [stage][A tile 16 KB | B tile block_n*128 B]
+    // 1024-byte aligned ring: [stage][A tile 16 KB | B tile block_n*128 B | (split3: A residual | B residual)]
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int bn = a.block_n;
+    const int kStages = a.stages;
     const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)bn * BK * 4;
-    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t tx_bytes = a_bytes + b_bytes;
+    const uint32_t stage_bytes = a.split3 ? 2 * tx_bytes : tx_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i0 = (int64_t)blockIdx.y * BM;
@@ -145,7 +155,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nkb = (int)((kk_end - kk_begin + BK - 1) / BK);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&ready_bar[s], kEpiThreads);
+        }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -171,7 +185,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 uint8_t* sa = smem + (size_t)s * stage_bytes;
                 uint8_t* sb = sa + a_bytes;
-                mbar_expect_tx(&full_bar[s], stage_bytes);
+                mbar_expect_tx(&full_bar[s], tx_bytes);
                 const int kk = (int)(kk_begin + (int64_t)kb * BK);
                 if (!a.a_mn) {
                     tma_load_2d(&tmA, &full_bar[s], sa, kk, (int)i0);                         // box {32 k, 128 rows}
@@ -194,21 +208,59 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(a.split3 ? &ready_bar[s] : &full_bar[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t sb = sa + a_bytes;
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
-                    const uint64_t da = a.a_mn ? make_desc(sa + k * 1024, 4096, 1024) : make_desc(sa + k * 32, 0, 1024);
-                    const uint64_t db = a.b_mn ? make_desc(sb + k * 1024, 4096, 1024) : make_desc(sb + k * 32, 0, 1024);
-                    umma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    const uint32_t oa = a.a_mn ? k * 1024 : k * 32, ob = a.b_mn ? k * 1024 : k * 32;
+                    const uint64_t da = a.a_mn ? make_desc(sa + oa, 4096, 512, kLayoutSw128Base32)
+                                               : make_desc(sa + oa, 0, 1024, kLayoutSw128);
+                    const uint64_t db = a.b_mn ? make_desc(sb + ob, 4096, 512, kLayoutSw128Base32)
+                                               : make_desc(sb + ob, 0, 1024, kLayoutSw128);
+                    if (a.split3) {
+                        // x = hi + lo with hi = the 19 bits the tensor core reads; add the small terms first
+                        const uint64_t dal = a.a_mn ? make_desc(sa + tx_bytes + oa, 4096, 512, kLayoutSw128Base32)
+                                                    : make_desc(sa + tx_bytes + oa, 0, 1024, kLayoutSw128);
+                        const uint64_t dbl = a.b_mn ? make_desc(sb + tx_bytes + ob, 4096, 512, kLayoutSw128Base32)
+                                                    : make_desc(sb + tx_bytes + ob, 0, 1024, kLayoutSw128);
+                        umma_tf32(tmem_base, dal, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(tmem_base, da, dbl, idesc, 1u);
+                        umma_tf32(tmem_base, da, db, idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty_bar[s]);          // ring slot free once these MMAs have read it
             }
             umma_commit(&tmem_full_bar);             // accumulator complete
         }
     } else {
+        // ================= (split3) residual tiles: lo = x - (x with the 13 low mantissa bits cleared),
+        // written next to the TMA tiles at the same (swizzled) offsets, then handed to the async proxy
+        if (a.split3) {
+            const int et = threadIdx.x - 64;                         // 0..127
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                const float4* src = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
+                float4* dst = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + tx_bytes);
+                const int nvec = (int)(tx_bytes >> 4);
+                for (int v = et; v < nvec; v += kEpiThreads) {
+                    const float4 x = src[v];
+                    float4 r;
+                    r.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    r.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    r.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                    r.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                    dst[v] = r;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
+            }
+        }
         // ================= epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
         const int q = warp & 3;
         mbar_wait(&tmem_full_bar, 0);
@@ -324,7 +376,8 @@ EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor map over a row-major matrix [rows, cols] (cols contiguous, row stride ld floats),
 // box = {box_cols, box_rows}, 128-byte swizzle, out-of-bounds elements read as zero.
-int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+             CUtensorMapSwizzle swz) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { ppd::set_error("ppd_tc_gemm: cuTensorMapEncodeTiled not available"); return PPD_EINVAL; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -332,7 +385,7 @@ int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int6
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ppd::set_error("ppd_tc_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r); return PPD_EINVAL; }
     return 0;
@@ -340,17 +393,17 @@ int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int6
 
 struct Plan { int bn; int64_t gx, gy; int splits; int64_t kk_per_split; size_t ws; };
 
-int pick_bn(int64_t J) {
+int pick_bn(int64_t J, bool split3) {
     if (J <= 32) return 32;
     if (J <= 64) return 64;
     if (J <= 128) return 128;
-    if (J <= 256 && J > 192) return 256;
+    if (!split3 && J <= 256 && J > 192) return 256;
     return 128;
 }
 
-Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_avail, bool limit) {
+Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_avail, bool limit, bool split3 = false) {
     Plan p;
-    p.bn = pick_bn(J);
+    p.bn = pick_bn(J, split3);
     p.gx = (J + p.bn - 1) / p.bn;
     p.gy = (I + BM - 1) / BM;
     const int64_t tiles = p.gx * p.gy;
@@ -380,7 +433,7 @@ Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_avail, bool limit) {
 
 extern "C" size_t ppd_tc_gemm_workspace(int64_t I, int64_t J, int64_t KK) {
     if (I <= 0 || J <= 0 || KK <= 0) return 0;
-    return make_plan(I, J, KK, 0, false).ws;
+    return make_plan(I, J, KK, 0, false).ws;    // independent of the flags (same split plan)
 }
 
 // 1 if ppd_tc_gemm can run this problem (alignment of the operands for TMA), else 0.
@@ -393,19 +446,21 @@ extern "C" int ppd_tc_gemm_supported(const ppd_gemm_args* g) {
     return 1;
 }
 
-extern "C" int ppd_tc_gemm(const ppd_gemm_args* g, int transpose_out, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int ppd_tc_gemm(const ppd_gemm_args* g, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+    const int transpose_out = flags & PPD_TC_TRANSPOSE_OUT;
+    const int split3 = (flags & PPD_TC_SPLIT3) ? 1 : 0;
     PPD_REQUIRE(ppd_tc_gemm_supported(g), "operands must be 16-byte aligned with leading dimensions that are multiples of 4");
     PPD_REQUIRE(transpose_out ? g->ldc >= g->I : g->ldc >= g->J, "bad ldc");
-    const Plan p = make_plan(g->I, g->J, g->KK, workspace ? workspace_bytes : 0, true);
+    const Plan p = make_plan(g->I, g->J, g->KK, workspace ? workspace_bytes : 0, true, split3);
     PPD_REQUIRE(p.gy <= 65535 && p.splits <= 65535, "grid too large");
     CUtensorMap tmA, tmB;
     int rc;
     // k-major operand: matrix [rows = I or J, cols = KK]; mn-major: matrix [rows = KK, cols = I or J]
-    if (g->a_kmajor) rc = make_map(&tmA, g->A, g->I, g->KK, g->lda, BK, BM);
-    else             rc = make_map(&tmA, g->A, g->KK, g->I, g->lda, 32, BK);
+    if (g->a_kmajor) rc = make_map(&tmA, g->A, g->I, g->KK, g->lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    else             rc = make_map(&tmA, g->A, g->KK, g->I, g->lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    if (g->b_kmajor) rc = make_map(&tmB, g->B, g->J, g->KK, g->ldb, BK, p.bn);
-    else             rc = make_map(&tmB, g->B, g->KK, g->J, g->ldb, 32, BK);
+    if (g->b_kmajor) rc = make_map(&tmB, g->B, g->J, g->KK, g->ldb, BK, p.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+    else             rc = make_map(&tmB, g->B, g->KK, g->J, g->ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
     Args a;
     a.C = g->C; a.ldc = g->ldc; a.I = g->I; a.J = g->J; a.KK = g->KK;
@@ -414,7 +469,12 @@ extern "C" int ppd_tc_gemm(const ppd_gemm_args* g, int transpose_out, void* work
     a.block_n = p.bn; a.a_mn = g->a_kmajor ? 0 : 1; a.b_mn = g->b_kmajor ? 0 : 1;
     a.kk_per_split = p.kk_per_split;
     a.partial = p.splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
-    const size_t smem = (size_t)kStages * (BM * BK * 4 + (size_t)p.bn * BK * 4) + 1024;
+    a.split3 = split3;
+    const size_t stage = (size_t)(split3 ? 2 : 1) * (BM * BK * 4 + (size_t)p.bn * BK * 4);
+    int stages = (int)((196 * 1024) / stage);
+    if (stages > kMaxStages) stages = kMaxStages;
+    a.stages = stages;
+    const size_t smem = (size_t)stages * stage + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

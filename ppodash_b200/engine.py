@@ -78,7 +78,8 @@ class PolicyEngine:
             self.sp.append(s)             # 20, 9, 7 for 84x84
         assert 32 * self.sp[2] * self.sp[2] == base.main[7].in_features, "obs size does not match the FC layer"
         self.flat_dim = 32 * self.sp[2] * self.sp[2]
-        self.precision = "fp32"
+        self.precision = "tf32x3"
+        self.tc_min_work = 1 << 21        # I*J*KK below this: launch latency dominates, stay on the SIMT kernel
         self.chunk_rows = 2048            # rows of the minibatch lowered to im2col at a time
         self.device = None
         self.flat = None
@@ -86,9 +87,16 @@ class PolicyEngine:
         self._cols_valid = False
 
     # ------------------------------------------------------------------ parameters
+    PRECISIONS = ("fp32", "tf32x3", "tf32")
+
     def set_precision(self, precision):
-        if precision not in ("fp32",):
-            raise ValueError("supported precision modes: 'fp32' (SIMT, parity mode)")
+        """'fp32'  : SIMT fp32 GEMMs everywhere (reference arithmetic; slowest)
+        'tf32x3': tcgen05 tensor cores with the 3xTF32 hi/lo split -> fp32-level accuracy (default)
+        'tf32'  : tcgen05 tensor cores, single TF32 pass (~1e-3 relative per GEMM; fastest)
+        GEMMs whose operands do not meet the TMA alignment rules (e.g. the 9-wide heads) and the
+        sequential GRU recurrence always run in fp32 SIMT."""
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"supported precision modes: {self.PRECISIONS}")
         self.precision = precision
 
     def _layout(self):
@@ -200,6 +208,17 @@ class PolicyEngine:
         g.ldm = ldm
         g.relu, g.accumulate = relu, acc
         L = lib()
+        if self.precision != "fp32" and I * J * KK >= self.tc_min_work and L.ppd_tc_gemm_supported(ctypes.byref(g)):
+            flags = 2 if self.precision == "tf32x3" else 0
+            if not a_k and not b_k and I < J and I <= 64 and bias is None and mask is None:
+                # weight gradient with few output rows: put the wide dimension on the 128-row MMA axis
+                # and store the tile transposed
+                g.A, g.lda, g.B, g.ldb = g.B, g.ldb, g.A, g.lda
+                g.I, g.J = J, I
+                flags |= 1
+            ws = _lib.workspace(L.ppd_tc_gemm_workspace(g.I, g.J, KK), self.device, "tcgemm")
+            check(L.ppd_tc_gemm(ctypes.byref(g), flags, ws.data_ptr(), ws.numel(), self.stream), "tc_gemm")
+            return
         ws = _lib.workspace(L.ppd_sgemm_workspace(I, J, KK), self.device, "gemm")
         check(L.ppd_sgemm(ctypes.byref(g), ws.data_ptr(), ws.numel(), self.stream), "sgemm")
 

@@ -29,18 +29,25 @@ def params_of(g, prefix):
     return {k[len(prefix):]: T_(g[k]) for k in g.files if k.startswith(prefix)}
 
 
-def make_policy(C, A, V, recurrent, H, state=None):
+def make_policy(C, A, V, recurrent, H, state=None, precision=None):
     pol = ppd.Policy((C, 84, 84), Discrete(A), base_kwargs={"recurrent": recurrent, "hidden_size": H}, vector_obs_len=V)
     if state is not None:
         missing, unexpected = pol.load_state_dict(state, strict=True)
         assert not missing and not unexpected
-    return pol.to(DEV)
+    pol = pol.to(DEV)
+    if precision:
+        pol.engine(precision)
+    return pol
 
 
+PARITY_MODES = ["fp32", "tf32x3"]      # both must meet the fp32 parity gate
+
+
+@pytest.mark.parametrize("precision", PARITY_MODES)
 @pytest.mark.parametrize("fixture,recurrent,C,A,V", [("policy_recurrent", True, 2, 5, 3), ("policy_feedforward", False, 1, 6, 0)])
-def test_policy_forward_matches_reference(golden, fixture, recurrent, C, A, V):
+def test_policy_forward_matches_reference(golden, fixture, recurrent, C, A, V, precision):
     g = golden(fixture)
-    pol = make_policy(C, A, V, recurrent, 32, params_of(g, "param."))
+    pol = make_policy(C, A, V, recurrent, 32, params_of(g, "param."), precision)
     d = lambda k: T_(g[k]).to(DEV)
     v, lp, ent, hx = pol.evaluate_actions(d("obs"), d("vobs"), d("h0"), d("masks"), d("actions"))
     tol = dict(rtol=1e-5, atol=2e-6)     # stated fp32 tolerance (1e-5 relative, + 2e-6 absolute near zero)
@@ -62,10 +69,11 @@ def test_policy_forward_matches_reference(golden, fixture, recurrent, C, A, V):
         assert a.shape == (E, 1) and a.dtype == torch.int64 and lp.shape == (E, 1) and h.shape == (E, 32)
 
 
+@pytest.mark.parametrize("precision", PARITY_MODES)
 @pytest.mark.parametrize("fixture,recurrent,C,A,V", [("policy_recurrent", True, 2, 5, 3), ("policy_feedforward", False, 1, 6, 0)])
-def test_minibatch_gradients_match_reference_autograd(golden, fixture, recurrent, C, A, V):
+def test_minibatch_gradients_match_reference_autograd(golden, fixture, recurrent, C, A, V, precision):
     g = golden(fixture)
-    pol = make_policy(C, A, V, recurrent, 32, params_of(g, "param."))
+    pol = make_policy(C, A, V, recurrent, 32, params_of(g, "param."), precision)
     eng = pol.engine()
     d = lambda k: T_(g[k]).to(DEV)
     sample = (d("obs"), d("vobs"), d("h0"), d("actions"), d("old_v"), d("ret"), d("masks"), d("old_logp"), d("adv"))
@@ -82,11 +90,12 @@ def test_minibatch_gradients_match_reference_autograd(golden, fixture, recurrent
         np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5 * scale, err_msg=name)
 
 
+@pytest.mark.parametrize("precision", PARITY_MODES)
 @pytest.mark.parametrize("tag,recurrent", [("recurrent", True), ("feedforward", False)])
-def test_ppo_update_matches_reference(golden, tag, recurrent):
+def test_ppo_update_matches_reference(golden, tag, recurrent, precision):
     g = golden("update_" + tag)
     C, V, A, H, T, N = (int(g[k]) for k in ("C", "V", "A", "H", "T", "N"))
-    pol = make_policy(C, A, V, recurrent, H, params_of(g, "init."))
+    pol = make_policy(C, A, V, recurrent, H, params_of(g, "init."), precision)
     st = ppd.RolloutStorage(T, N, (C, 84, 84), [V], Discrete(A), H if recurrent else 1)
     for k in ppd.RolloutStorage._FIELDS:
         getattr(st, k).copy_(T_(g["roll." + k]))
@@ -104,12 +113,16 @@ def test_ppo_update_matches_reference(golden, tag, recurrent):
         np.testing.assert_allclose(p.cpu().numpy(), ref, rtol=0, atol=0.02 * lr, err_msg=name)
 
 
-def test_c2_shaped_minibatch_vs_oracle():
+@pytest.mark.parametrize("precision", PARITY_MODES + ["tf32"])
+def test_c2_shaped_minibatch_vs_oracle(precision):
     """PPO-Dash full shapes (C=3, V=15, A=8, H=512, recurrent), T=24 x E=4 rows, resets inside."""
     torch.manual_seed(0)
     pol = ppd.Policy((3, 84, 84), Discrete(8), base_kwargs={"recurrent": True}, vector_obs_len=15)
     p_cpu = {k: v.clone() for k, v in pol.state_dict().items()}
     pol = pol.to(DEV)
+    pol.engine(precision)
+    # stated tolerances: fp32 / tf32x3 = the 1e-5 parity gate; single-pass tf32 = 1e-2 of the tensor's scale
+    loose = precision == "tf32"
     T, E = 24, 4
     cfg = synthetic.RolloutConfig("t", T, E, 3, 15, 8, True, 1, 1, 1e-4, 0.001)
     roll = synthetic.make_rollout(cfg, seed=3, reset_prob=0.05)
@@ -131,14 +144,19 @@ def test_c2_shaped_minibatch_vs_oracle():
     dd = lambda t: t.to(DEV)
     out = eng.train_minibatch((dd(obs), dd(vobs), dd(h0), dd(actions), dd(old_v), dd(ret), dd(masks), dd(old_logp), dd(adv)),
                               0.1, 0.5, 0.001)
-    np.testing.assert_allclose(out["value"].cpu().numpy(), v.detach().numpy(), rtol=1e-5, atol=2e-6)
-    np.testing.assert_allclose(out["rnn_hxs"].cpu().numpy(), hx.detach().numpy(), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(out["value"].cpu().numpy(), v.detach().numpy(), rtol=1e-2 if loose else 1e-5,
+                               atol=2e-3 if loose else 2e-6)
+    np.testing.assert_allclose(out["rnn_hxs"].cpu().numpy(), hx.detach().numpy(), rtol=1e-2 if loose else 1e-5,
+                               atol=2e-3 if loose else 2e-6)
     loss = eng.flat_grad[eng.loss_off:eng.loss_off + 3].cpu().numpy()
-    np.testing.assert_allclose(loss, [vl.item(), al.item(), ent.item()], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(loss, [vl.item(), al.item(), ent.item()], rtol=1e-2 if loose else 1e-5, atol=1e-7)
     for name, p in pol.named_parameters():
         ref = pr[name].grad.numpy()
         scale = max(1e-6, float(np.abs(ref).max()))
-        np.testing.assert_allclose(p.grad.cpu().numpy(), ref, rtol=1e-4, atol=1e-5 * scale, err_msg=name)
+        if loose:
+            assert float(np.abs(p.grad.cpu().numpy() - ref).max()) <= 2e-2 * scale, name
+        else:
+            np.testing.assert_allclose(p.grad.cpu().numpy(), ref, rtol=1e-4, atol=1e-5 * scale, err_msg=name)
     # chunked trunk (rows processed 40 at a time) gives the same gradients
     g1 = eng.flat_grad.clone()
     eng.chunk_rows = 40
