@@ -184,10 +184,10 @@ int ppd_sgemm(const ppd_gemm_args* g, void* workspace, size_t workspace_bytes, v
  *   PPD_TC_TRANSPOSE_OUT  store the result transposed (C is then [J, I] with row stride ldc; bias is
  *                         still indexed by j and mask uses C's layout) -- puts the wide dimension of a
  *                         weight gradient on the 128-row MMA axis;
- *   PPD_TC_SPLIT3         "3xTF32": every operand tile x is split in shared memory into hi (the 19 bits
- *                         the tensor core reads) and lo = x - hi, and A_lo*B_hi + A_hi*B_lo + A_hi*B_hi is
- *                         accumulated, which restores fp32-level accuracy (~1e-6 relative) on the
- *                         tensor cores.  Without it ("tf32" mode) results agree with fp32 to ~1e-3. */
+ *   PPD_TC_SPLIT3         "3xTF32": every operand tile x is split in shared memory into hi = TF32(x)
+ *                         (round to nearest) and lo = TF32(x - hi), and A_lo*B_hi + A_hi*B_lo + A_hi*B_hi is
+ *                         accumulated, which restores fp32-level accuracy (~2^-23 per product, zero-mean)
+ *                         on the tensor cores.  Without it ("tf32" mode) results agree with fp32 to ~1e-3. */
 #define PPD_TC_TRANSPOSE_OUT 1
 #define PPD_TC_SPLIT3 2
 size_t ppd_tc_gemm_workspace(int64_t I, int64_t J, int64_t KK);

@@ -8,10 +8,11 @@
 //     memory (96 rows x 512 x 4 B = 192 KB at H = 512) for all T steps -- W_hh is read from HBM once;
 //   * forward : per step each CTA forms its 3*HU dot products with the (masked) previous state,
 //     applies the gates and writes its HU new state values straight into the shared memory of all
-//     16 CTAs (st.shared::cluster); one cluster barrier (arrive.release / wait.acquire) per step;
+//     16 CTAs with st.async (data + mbarrier complete_tx in one DSMEM transaction), so each CTA only
+//     waits on a local mbarrier for "all 512 state values of step t are here" -- no cluster barrier;
 //   * backward: per step each CTA turns dh of its units into d(gates), multiplies by its W_hh rows
 //     to get its partial sum of dh_{t-1} for ALL units and scatters the partials to their owner CTAs
-//     through DSMEM (a reduce-scatter); again one cluster barrier per step.
+//     through DSMEM (a reduce-scatter) with the same st.async + local mbarrier handshake.
 // Envs are independent sequences, so E envs run as E clusters side by side (E*16 SMs busy).
 // Global loads of the next step's operands are issued one step ahead (software pipelining).
 #include <cooperative_groups.h>
@@ -28,8 +29,38 @@ constexpr int kWarps = kThreads / 32;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// ---- DSMEM push with completion: st.async writes a value into a peer CTA's shared memory and
+// performs complete_tx on that CTA's mbarrier, so data and "it has arrived" travel together and the
+// receiver only waits on a local mbarrier (no cluster-wide barrier per step).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "r"(__float_as_uint(v)), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arm(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
 
 struct FwdArgs {
     const float* gi; const float* h0; const float* masks; const float* w_hh; const float* b_hh;
@@ -51,7 +82,16 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_cluster_kernel(const FwdA
     float* hb = W + (size_t)R * H;         // [2][H]  masked previous state, double-buffered by step parity
     float* gh = hb + 2 * H;                // [R]
     float* stage = gh + R;                 // [HU]    new state of this CTA's units, masked for the next step
+    __shared__ __align__(8) uint64_t hbar[2];   // hbar[b]: all H values of state buffer b have arrived
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t step_bytes = (uint32_t)H * 4;
+    if (tid == 0) {
+        mbar_init(&hbar[0], 1);
+        mbar_init(&hbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arm(&hbar[1], step_bytes);        // first use: step 1
+        mbar_arm(&hbar[0], step_bytes);        // first use: step 2
+    }
 
     for (int idx = tid; idx < R * H; idx += kThreads) {
         const int r = idx / H, k = idx - r * H;
@@ -78,6 +118,10 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_cluster_kernel(const FwdA
     const int rows_per_warp = (R + kWarps - 1) / kWarps;
     for (int t = 0; t < a.T; ++t) {
         const float* hcur = hb + (t & 1) * H;
+        if (t > 0) {
+            // the previous step's state: pushed by all 16 CTAs into buffer t&1; use u of that buffer -> parity u&1
+            mbar_wait(&hbar[t & 1], (uint32_t)((t - 1) >> 1) & 1u);
+        }
         // ---- dot products: warp w owns rows [w*rows_per_warp, ...)
         float hreg[KI > 0 ? KI : 1];
         if (KI > 0) {
@@ -119,16 +163,16 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_cluster_kernel(const FwdA
             }
         }
         if (t + 1 == a.T) break;
-        __syncthreads();
-        // ---- broadcast the masked new state of own units into every CTA's next-step buffer
+        __syncthreads();           // stage[] written; every warp is done reading buffer t&1
+        if (tid == 0 && t >= 1 && t + 2 < a.T) mbar_arm(&hbar[t & 1], step_bytes);   // re-arm for step t+2
+        // ---- push the masked new state of own units into every CTA's next-step buffer
         float* hnext = hb + ((t + 1) & 1) * H;
+        const uint32_t local_dst = smem_u32(hnext + j0);
+        const uint32_t local_bar = smem_u32(&hbar[(t + 1) & 1]);
         for (int idx = tid; idx < CS * HU; idx += kThreads) {
             const int dst = idx / HU, u = idx - dst * HU;
-            float* remote = cluster.map_shared_rank(hnext, dst);
-            remote[j0 + u] = stage[u];
+            st_async_f32(map_to_rank(local_dst + 4u * u, (uint32_t)dst), stage[u], map_to_rank(local_bar, (uint32_t)dst));
         }
-        cluster_arrive();
-        cluster_wait();
     }
     cluster.sync();          // do not exit while a peer may still be writing into this CTA's smem
 }
@@ -151,7 +195,16 @@ __global__ void __launch_bounds__(kThreads, 1) gru_bwd_cluster_kernel(const BwdA
     float* dgh = W + (size_t)R * H;        // [R]      d(hidden-side pre-activations) of own units at step t
     float* recv = dgh + R;                 // [2][CS][HU]  partial dh_{t-1} for own units from every CTA
     float* part = recv + 2 * CS * HU;      // [H]      this CTA's partial dh_{t-1} for all units
+    __shared__ __align__(8) uint64_t rbar[2];   // rbar[b]: all 16 partial slices of recv buffer b have arrived
     const int tid = threadIdx.x;
+    const uint32_t step_bytes = (uint32_t)(CS * HU) * 4;
+    if (tid == 0) {
+        mbar_init(&rbar[0], 1);
+        mbar_init(&rbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arm(&rbar[0], step_bytes);
+        mbar_arm(&rbar[1], step_bytes);
+    }
 
     for (int idx = tid; idx < R * H; idx += kThreads) {
         const int r = idx / H, k = idx - r * H;
@@ -208,13 +261,16 @@ __global__ void __launch_bounds__(kThreads, 1) gru_bwd_cluster_kernel(const BwdA
         __syncthreads();
         // ---- (c) reduce-scatter through DSMEM: unit k's partial goes to its owner CTA
         float* rbuf = recv + (t & 1) * CS * HU;
-        for (int k = tid; k < H; k += kThreads) {
-            const int dst = k / HU, u = k - dst * HU;
-            float* remote = cluster.map_shared_rank(rbuf, dst);
-            remote[rank * HU + u] = part[k];
+        {
+            const uint32_t local_dst = smem_u32(rbuf + rank * HU);
+            const uint32_t local_bar = smem_u32(&rbar[t & 1]);
+            for (int k = tid; k < H; k += kThreads) {
+                const int dst = k / HU, u = k - dst * HU;
+                st_async_f32(map_to_rank(local_dst + 4u * u, (uint32_t)dst), part[k], map_to_rank(local_bar, (uint32_t)dst));
+            }
         }
-        cluster_arrive();
-        cluster_wait();
+        // use u of buffer t&1 (uses go t = T-1, T-3, ... / T-2, T-4, ...) -> parity u&1
+        mbar_wait(&rbar[t & 1], (uint32_t)((a.T - 1 - t) >> 1) & 1u);
         // ---- (d) carry for own units
         if (gate_thread) {
             float s = 0.f;
@@ -223,6 +279,8 @@ __global__ void __launch_bounds__(kThreads, 1) gru_bwd_cluster_kernel(const BwdA
             carry = (s + dhz) * m_t;
             if (t == 0 && a.dh0) a.dh0[(size_t)env * H + ju] = carry;
         }
+        __syncthreads();           // every reader of recv buffer t&1 is done before it is re-armed
+        if (tid == 0 && t >= 2) mbar_arm(&rbar[t & 1], step_bytes);   // for step t-2
     }
     cluster.sync();
 }

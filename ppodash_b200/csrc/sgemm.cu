@@ -217,7 +217,12 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t I, i
 }
 
 // Column sums: out[j] (+)= sum_i X[i*ld + j]   (bias gradients).  Two deterministic stages.
-constexpr int kColRows = 256;   // rows per partial block
+//   narrow matrices (256 % J == 0 and dense rows, the conv bias gradients: J = 32 / 64 with up to 819 200
+//   rows): the matrix is one contiguous stream; a thread striding by 256 always lands on column
+//   tid % J, so loads are fully coalesced and the per-column fold happens once per block in shared memory;
+//   wide matrices: one thread per column over a slab of rows.
+constexpr int kColRows = 64;     // rows per partial block (wide path)
+constexpr int kNarrowElems = 256 * 64;   // elements per partial block (narrow path)
 __global__ void __launch_bounds__(kThreads)
 colsum_partial_kernel(const float* __restrict__ X, int64_t ld, int64_t I, int64_t J, float* __restrict__ partial) {
     const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -228,12 +233,40 @@ colsum_partial_kernel(const float* __restrict__ X, int64_t ld, int64_t I, int64_
     partial[(int64_t)blockIdx.y * J + j] = s;
 }
 __global__ void __launch_bounds__(kThreads)
+colsum_narrow_partial_kernel(const float* __restrict__ X, int64_t n, int J, float* __restrict__ partial) {
+    __shared__ float sm[kThreads];
+    const int64_t e0 = (int64_t)blockIdx.x * kNarrowElems, e1 = min(n, e0 + kNarrowElems);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int64_t e = e0 + threadIdx.x;
+    for (; e + 3 * kThreads < e1; e += 4 * kThreads) {
+        s0 += __ldg(X + e); s1 += __ldg(X + e + kThreads); s2 += __ldg(X + e + 2 * kThreads); s3 += __ldg(X + e + 3 * kThreads);
+    }
+    for (; e < e1; e += kThreads) s0 += __ldg(X + e);
+    sm[threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (threadIdx.x < J) {            // e0 is a multiple of 256, hence of J: thread t holds column t % J
+        float s = 0.f;
+        for (int t = threadIdx.x; t < kThreads; t += J) s += sm[t];
+        partial[(int64_t)blockIdx.x * J + threadIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(kThreads)
 colsum_final_kernel(const float* __restrict__ partial, int64_t nparts, int64_t J, float* __restrict__ out, int accumulate) {
     const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (j >= J) return;
-    float s = 0.f;
-    for (int64_t p = 0; p < nparts; ++p) s += partial[p * J + j];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int64_t p = 0;
+    for (; p + 3 < nparts; p += 4) {
+        s0 += partial[p * J + j]; s1 += partial[(p + 1) * J + j]; s2 += partial[(p + 2) * J + j]; s3 += partial[(p + 3) * J + j];
+    }
+    for (; p < nparts; ++p) s0 += partial[p * J + j];
+    const float s = (s0 + s1) + (s2 + s3);
     out[j] = accumulate ? (out[j] + s) : s;
+}
+
+bool colsum_narrow(int64_t ld, int64_t J) { return ld == J && J <= kThreads && (kThreads % J) == 0; }
+int64_t colsum_parts(int64_t ld, int64_t I, int64_t J) {
+    return colsum_narrow(ld, J) ? (I * J + kNarrowElems - 1) / kNarrowElems : (I + kColRows - 1) / kColRows;
 }
 
 struct Plan { int bi, bj; int64_t gx, gy; int splits; int64_t kk_per_split; size_t ws; };
@@ -315,24 +348,30 @@ extern "C" int ppd_sgemm(const ppd_gemm_args* g, void* workspace, size_t workspa
 
 extern "C" size_t ppd_colsum_workspace(int64_t I, int64_t J) {
     if (I <= 0 || J <= 0) return 0;
-    return (size_t)((I + kColRows - 1) / kColRows) * J * sizeof(float);
+    const int64_t a = (I * J + kNarrowElems - 1) / kNarrowElems, b = (I + kColRows - 1) / kColRows;
+    return (size_t)(a > b ? a : b) * J * sizeof(float);
 }
 
 extern "C" int ppd_colsum(const float* X, int64_t ld, int64_t I, int64_t J, float* out, int accumulate,
                           void* workspace, size_t workspace_bytes, void* stream) {
     PPD_REQUIRE(X && out && workspace, "null pointer");
     PPD_REQUIRE(I > 0 && J > 0 && ld >= J, "bad sizes");
-    const int64_t parts = (I + kColRows - 1) / kColRows;
+    const int64_t parts = colsum_parts(ld, I, J);
     if (workspace_bytes < (size_t)parts * J * sizeof(float)) {
         ppd::set_error("ppd_colsum: workspace too small");
         return PPD_EWORKSPACE;
     }
-    PPD_REQUIRE(parts <= 65535, "too many rows");
     cudaStream_t s = ppd::as_stream(stream);
-    dim3 grid((unsigned)((J + kThreads - 1) / kThreads), (unsigned)parts);
-    colsum_partial_kernel<<<grid, kThreads, 0, s>>>(X, ld, I, J, (float*)workspace);
+    const unsigned gx = (unsigned)((J + kThreads - 1) / kThreads);
+    if (colsum_narrow(ld, J)) {
+        PPD_REQUIRE(parts <= 0x7fffffffLL, "too many rows");
+        colsum_narrow_partial_kernel<<<(unsigned)parts, kThreads, 0, s>>>(X, I * J, (int)J, (float*)workspace);
+    } else {
+        PPD_REQUIRE(parts <= 65535, "too many rows");
+        colsum_partial_kernel<<<dim3(gx, (unsigned)parts), kThreads, 0, s>>>(X, ld, I, J, (float*)workspace);
+    }
     int rc = ppd::launch_status("colsum_partial_kernel");
     if (rc) return rc;
-    colsum_final_kernel<<<grid.x, kThreads, 0, s>>>((const float*)workspace, parts, J, out, accumulate);
+    colsum_final_kernel<<<gx, kThreads, 0, s>>>((const float*)workspace, parts, J, out, accumulate);
     return ppd::launch_status("colsum_final_kernel");
 }

@@ -102,6 +102,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+    lo = __uint_as_float(l);
+}
+
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
 // version 1 <<46 | layout type <<61
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -237,24 +245,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(&tmem_full_bar);             // accumulator complete
         }
     } else {
-        // ================= (split3) residual tiles: lo = x - (x with the 13 low mantissa bits cleared),
-        // written next to the TMA tiles at the same (swizzled) offsets, then handed to the async proxy
+        // ================= (split3) hi = round-to-nearest TF32 of x (written back in place), lo = TF32(x - hi)
+        // written next to it at the same (swizzled) offsets; both are then handed to the async proxy.
+        // Rounding (instead of the tensor core's truncation of the raw fp32 bits) keeps the neglected
+        // lo*lo term and the rounding of lo zero-mean, so long sums with cancellation (weight gradients)
+        // do not pick up a bias.
         if (a.split3) {
             const int et = threadIdx.x - 64;                         // 0..127
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
                 mbar_wait(&full_bar[s], ph);
-                const float4* src = reinterpret_cast<const float4*>(smem + (size_t)s * stage_bytes);
+                float4* src = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
                 float4* dst = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + tx_bytes);
                 const int nvec = (int)(tx_bytes >> 4);
                 for (int v = et; v < nvec; v += kEpiThreads) {
                     const float4 x = src[v];
-                    float4 r;
-                    r.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-                    r.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-                    r.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-                    r.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                    float4 h, r;
+                    split_tf32(x.x, h.x, r.x);
+                    split_tf32(x.y, h.y, r.y);
+                    split_tf32(x.z, h.z, r.z);
+                    split_tf32(x.w, h.w, r.w);
+                    src[v] = h;
                     dst[v] = r;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

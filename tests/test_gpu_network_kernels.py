@@ -74,7 +74,7 @@ def test_sgemm_wgrad_tn_splitk_accumulate(M, N, K):
 
 def test_colsum():
     L = _lib.lib()
-    for (I, J, ld) in [(1, 1, 1), (1000, 9, 12), (5000, 1536, 1536)]:
+    for (I, J, ld) in [(1, 1, 1), (1000, 9, 12), (5000, 1536, 1536), (100000, 32, 32), (5184, 64, 64), (777, 32, 32), (300, 64, 70)]:
         X = torch.randn(I, ld)
         out0 = torch.randn(J)
         Xd = X.to(DEV)
