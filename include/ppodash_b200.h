@@ -239,7 +239,9 @@ int ppd_gru_masked_prev(const float* hs, const float* h0, const float* masks, in
                         float* hm, void* stream);
 /* Kernel selection for the two calls above: 0 (default) = thread-block-cluster / DSMEM kernels when
  * E <= 8 and H % 16 == 0 (one 16-CTA cluster per env, W_hh slices resident in shared memory, one
- * cluster barrier per step), else the grid-cooperative kernels; 1 = always grid-cooperative. */
+ * mbarrier handshake per step; at H = 512 the W_hh slice lives in registers), else the grid-cooperative
+ * kernels; 1 = always grid-cooperative; 2 = cluster kernels with the W_hh slice in shared memory even at
+ * H = 512 (the generic-H variant, kept selectable for testing). */
 void ppd_gru_set_mode(int mode);
 
 #ifdef __cplusplus

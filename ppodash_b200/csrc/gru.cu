@@ -27,6 +27,7 @@ int gru_forward_cluster(const float* gi, const float* h0, const float* masks, co
 int gru_backward_cluster(const float* dhs, const float* masks, const float* w_hh, const float* h0, const float* hs,
                          const float* sr, const float* sz, const float* sn, const float* sghn, int T, int E, int H,
                          float* dgi, float* dghn, float* dh0, cudaStream_t s);
+extern int g_reg_kernels;
 static int g_gru_mode = 0;   // 0 = auto (cluster path when it applies), 1 = always the grid-cooperative kernels
 }  // namespace ppd
 
@@ -340,7 +341,10 @@ extern "C" int ppd_gru_backward(const float* dhs, const float* masks, const floa
     return ppd::launch_status("gru_bwd_kernel");
 }
 
-extern "C" void ppd_gru_set_mode(int mode) { ppd::g_gru_mode = mode; }
+extern "C" void ppd_gru_set_mode(int mode) {
+    ppd::g_gru_mode = (mode == 1) ? 1 : 0;
+    ppd::g_reg_kernels = (mode == 2) ? 0 : 1;
+}
 
 extern "C" int ppd_gru_masked_prev(const float* hs, const float* h0, const float* masks, int T, int E, int H,
                                    float* hm, void* stream) {

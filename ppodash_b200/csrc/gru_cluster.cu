@@ -285,17 +285,229 @@ __global__ void __launch_bounds__(kThreads, 1) gru_bwd_cluster_kernel(const BwdA
     cluster.sync();
 }
 
+// =====================================================================================================
+// H = 512 specialisations with the W_hh slice held in REGISTERS (the generic kernels above stream the
+// 192 KB slice from shared memory every step: 1536 cycles at 128 B/clk, the dominant per-step cost).
+//   forward : 384 threads; thread (row r = tid/4, quarter q = tid%4) keeps W_hh[row r][q*128 .. +128) in
+//             128 registers; per step 32 broadcast LDS.128 of the state + 128 FMAs + 2 shuffles.
+//   backward: 512 threads; thread k keeps the column W_hh[own rows][k] in 96 registers; per step 24
+//             broadcast LDS.128 of d(gates) + 96 FMAs, no reduction, result pushed straight to its owner.
+// =====================================================================================================
+constexpr int kH = 512, kHU = kH / CS, kR = 3 * kHU;      // 32 units, 96 rows per CTA
+constexpr int kFwdThreads = kR * 4;                        // 384
+constexpr int kQ = kH / 4;                                 // 128 state values per quarter
+constexpr int kQPad = kQ + 4;                              // quarter stride in smem: conflict-free broadcast reads
+
+__device__ __forceinline__ int hpad(int j) { return (j / kQ) * kQPad + (j % kQ); }
+
+__global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(const FwdArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ __align__(16) float hb[2][4 * kQPad];      // masked previous state, padded quarters, double-buffered
+    __shared__ float gh[kR];
+    __shared__ float stage[kHU];
+    __shared__ __align__(8) uint64_t hbar[2];
+    const int E = a.E;
+    const int rank = (int)cluster.block_rank();
+    const int env = blockIdx.x / CS;
+    const int j0 = rank * kHU;
+    const int tid = threadIdx.x;
+    const int r = tid >> 2, q = tid & 3;
+    const uint32_t step_bytes = kH * 4;
+    if (tid == 0) {
+        mbar_init(&hbar[0], 1);
+        mbar_init(&hbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arm(&hbar[1], step_bytes);
+        mbar_arm(&hbar[0], step_bytes);
+    }
+    float w[kQ];
+    {
+        const int g = r / kHU, u = r - g * kHU;
+        const float4* src = reinterpret_cast<const float4*>(a.w_hh + (size_t)(g * kH + j0 + u) * kH + q * kQ);
+#pragma unroll
+        for (int i = 0; i < kQ / 4; ++i) {
+            const float4 v = __ldg(src + i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+    }
+    {
+        const float m0 = __ldg(a.masks + env);
+        for (int k = tid; k < kH; k += kFwdThreads) hb[0][hpad(k)] = __ldg(a.h0 + (size_t)env * kH + k) * m0;
+    }
+    const bool gate_thread = tid < kHU;
+    const int ju = j0 + tid;
+    float bh_r = 0.f, bh_z = 0.f, bh_n = 0.f, gi_r = 0.f, gi_z = 0.f, gi_n = 0.f, m_next = 0.f;
+    if (gate_thread) {
+        bh_r = __ldg(a.b_hh + ju); bh_z = __ldg(a.b_hh + kH + ju); bh_n = __ldg(a.b_hh + 2 * kH + ju);
+        const float* g = a.gi + (size_t)env * 3 * kH;
+        gi_r = __ldg(g + ju); gi_z = __ldg(g + kH + ju); gi_n = __ldg(g + 2 * kH + ju);
+        m_next = (a.T > 1) ? __ldg(a.masks + (size_t)E + env) : 0.f;
+    }
+    __syncthreads();
+    cluster.sync();
+
+    for (int t = 0; t < a.T; ++t) {
+        const float* hcur = hb[t & 1];
+        if (t > 0) mbar_wait(&hbar[t & 1], (uint32_t)((t - 1) >> 1) & 1u);
+        // ---- quarter dot product, 4 independent accumulators
+        {
+            const float4* h4 = reinterpret_cast<const float4*>(hcur + q * kQPad);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < kQ / 4; ++i) {
+                const float4 hv = h4[i];
+                a0 = fmaf(w[4 * i], hv.x, a0);
+                a1 = fmaf(w[4 * i + 1], hv.y, a1);
+                a2 = fmaf(w[4 * i + 2], hv.z, a2);
+                a3 = fmaf(w[4 * i + 3], hv.w, a3);
+            }
+            float acc = (a0 + a1) + (a2 + a3);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (q == 0) gh[r] = acc;
+        }
+        __syncthreads();
+        const size_t row = (size_t)t * E + env;
+        if (gate_thread) {
+            const float ghr = gh[tid] + bh_r, ghz = gh[kHU + tid] + bh_z, ghn = gh[2 * kHU + tid] + bh_n;
+            const float rg = sigmoidf_(gi_r + ghr);
+            const float z = sigmoidf_(gi_z + ghz);
+            const float n = tanhf(gi_n + rg * ghn);
+            const float hm = hcur[hpad(ju)];
+            const float hn = n + z * (hm - n);
+            stage[tid] = hn * m_next;
+            a.hs[row * kH + ju] = hn;
+            if (a.sr) { a.sr[row * kH + ju] = rg; a.sz[row * kH + ju] = z; a.sn[row * kH + ju] = n; a.sghn[row * kH + ju] = ghn; }
+            if (a.h_last && t == a.T - 1) a.h_last[(size_t)env * kH + ju] = hn;
+            if (t + 1 < a.T) {
+                const float* g = a.gi + (row + E) * 3 * kH;
+                gi_r = __ldg(g + ju); gi_z = __ldg(g + kH + ju); gi_n = __ldg(g + 2 * kH + ju);
+                m_next = (t + 2 < a.T) ? __ldg(a.masks + row + 2 * (size_t)E) : 0.f;
+            }
+        }
+        if (t + 1 == a.T) break;
+        __syncthreads();
+        if (tid == 0 && t >= 1 && t + 2 < a.T) mbar_arm(&hbar[t & 1], step_bytes);
+        {
+            const uint32_t local_base = smem_u32(&hb[(t + 1) & 1][0]);
+            const uint32_t local_bar = smem_u32(&hbar[(t + 1) & 1]);
+            for (int idx = tid; idx < CS * kHU; idx += kFwdThreads) {
+                const int dst = idx / kHU, u = idx - dst * kHU;
+                st_async_f32(map_to_rank(local_base + 4u * (uint32_t)hpad(j0 + u), (uint32_t)dst), stage[u],
+                             map_to_rank(local_bar, (uint32_t)dst));
+            }
+        }
+    }
+    cluster.sync();
+}
+
+__global__ void __launch_bounds__(kH, 1) gru_bwd_cluster512_kernel(const BwdArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ __align__(16) float dgh[kR];
+    __shared__ float recv[2][CS * kHU];
+    __shared__ __align__(8) uint64_t rbar[2];
+    const int E = a.E;
+    const int rank = (int)cluster.block_rank();
+    const int env = blockIdx.x / CS;
+    const int j0 = rank * kHU;
+    const int tid = threadIdx.x;                 // = unit index k this thread produces partial sums for
+    const uint32_t step_bytes = CS * kHU * 4;
+    if (tid == 0) {
+        mbar_init(&rbar[0], 1);
+        mbar_init(&rbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arm(&rbar[0], step_bytes);
+        mbar_arm(&rbar[1], step_bytes);
+    }
+    float wc[kR];                                 // W_hh[own row r][k = tid]
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+        const int g = r / kHU, u = r - g * kHU;
+        wc[r] = __ldg(a.w_hh + (size_t)(g * kH + j0 + u) * kH + tid);
+    }
+    const bool gate_thread = tid < kHU;
+    const int ju = j0 + tid;
+    float carry = 0.f;
+    float p_dh = 0.f, p_r = 0.f, p_z = 0.f, p_n = 0.f, p_ghn = 0.f, p_hp = 0.f, p_m = 0.f;
+    auto prefetch = [&](int t) {
+        const size_t row = (size_t)t * E + env;
+        p_dh = __ldg(a.dhs + row * kH + ju);
+        p_r = __ldg(a.sr + row * kH + ju); p_z = __ldg(a.sz + row * kH + ju);
+        p_n = __ldg(a.sn + row * kH + ju); p_ghn = __ldg(a.sghn + row * kH + ju);
+        p_m = __ldg(a.masks + row);
+        p_hp = (t == 0) ? __ldg(a.h0 + (size_t)env * kH + ju) : __ldg(a.hs + (row - E) * kH + ju);
+    };
+    if (gate_thread) prefetch(a.T - 1);
+    // owner of this thread's unit and the slot of this CTA's contribution in the owner's receive buffers
+    const uint32_t dst_rank = (uint32_t)(tid / kHU);
+    const uint32_t slot = (uint32_t)(rank * kHU + (tid % kHU));
+    __syncthreads();
+    cluster.sync();
+
+    for (int t = a.T - 1; t >= 0; --t) {
+        const size_t row = (size_t)t * E + env;
+        float dhz = 0.f, m_t = 0.f;
+        if (gate_thread) {
+            const float dh = p_dh + carry;
+            const float rg = p_r, z = p_z, n = p_n, ghn = p_ghn;
+            m_t = p_m;
+            const float hm = p_hp * m_t;
+            const float dz = dh * (hm - n);
+            const float dn = dh * (1.f - z);
+            const float dpn = dn * (1.f - n * n);
+            const float dpz = dz * z * (1.f - z);
+            const float dpr = (dpn * ghn) * rg * (1.f - rg);
+            float* g = a.dgi + row * 3 * kH;
+            g[ju] = dpr; g[kH + ju] = dpz; g[2 * kH + ju] = dpn;
+            const float dgn = dpn * rg;
+            a.dghn[row * kH + ju] = dgn;
+            dgh[tid] = dpr; dgh[kHU + tid] = dpz; dgh[2 * kHU + tid] = dgn;
+            dhz = dh * z;
+            if (t > 0) prefetch(t - 1);
+        }
+        __syncthreads();
+        // ---- partial dh_{t-1}[k] over this CTA's 96 rows
+        float s;
+        {
+            const float4* d4 = reinterpret_cast<const float4*>(dgh);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < kR / 4; ++i) {
+                const float4 dv = d4[i];
+                a0 = fmaf(dv.x, wc[4 * i], a0);
+                a1 = fmaf(dv.y, wc[4 * i + 1], a1);
+                a2 = fmaf(dv.z, wc[4 * i + 2], a2);
+                a3 = fmaf(dv.w, wc[4 * i + 3], a3);
+            }
+            s = (a0 + a1) + (a2 + a3);
+        }
+        // ---- reduce-scatter: push to the owner of unit k
+        st_async_f32(map_to_rank(smem_u32(&recv[t & 1][slot]), dst_rank), s, map_to_rank(smem_u32(&rbar[t & 1]), dst_rank));
+        mbar_wait(&rbar[t & 1], (uint32_t)((a.T - 1 - t) >> 1) & 1u);
+        if (gate_thread) {
+            float acc = 0.f;
+#pragma unroll
+            for (int src = 0; src < CS; ++src) acc += recv[t & 1][src * kHU + tid];
+            carry = (acc + dhz) * m_t;
+            if (t == 0 && a.dh0) a.dh0[(size_t)env * kH + ju] = carry;
+        }
+        __syncthreads();           // dgh and recv[t&1] are free again
+        if (tid == 0 && t >= 2) mbar_arm(&rbar[t & 1], step_bytes);
+    }
+    cluster.sync();
+}
+
 size_t fwd_smem(int H) { const int HU = H / CS; return (size_t)(3 * HU * H + 2 * H + 3 * HU + HU) * sizeof(float); }
 size_t bwd_smem(int H) { const int HU = H / CS; return (size_t)(3 * HU * H + 3 * HU + 2 * CS * HU + H) * sizeof(float); }
 
 template <typename K>
-int launch_cluster(K kernel, const void* args_struct, size_t args_size, int E, size_t smem, cudaStream_t s, const char* what) {
+int launch_cluster(K kernel, const void* args_struct, int threads, int E, size_t smem, cudaStream_t s, const char* what) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && smem > 0) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cudaGetLastError(); return -1; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS * E);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -306,7 +518,6 @@ int launch_cluster(K kernel, const void* args_struct, size_t args_size, int E, s
     int nclusters = 0;
     e = cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg);
     if (e != cudaSuccess || nclusters < 1) { cudaGetLastError(); return -1; }
-    (void)args_size;
     void* params[] = {const_cast<void*>(args_struct)};
     e = cudaLaunchKernelExC(&cfg, (const void*)kernel, params);
     if (e != cudaSuccess) {
@@ -321,14 +532,17 @@ int launch_cluster(K kernel, const void* args_struct, size_t args_size, int E, s
 
 namespace ppd {
 
+int g_reg_kernels = 1;   // 0 (ppd_gru_set_mode(2)): use the generic shared-memory cluster kernels even at H = 512
+
 // Return 0 on success, -1 if the cluster path does not apply (caller falls back to gru.cu), >0 on CUDA error.
 int gru_forward_cluster(const float* gi, const float* h0, const float* masks, const float* w_hh, const float* b_hh,
                         int T, int E, int H, float* hs, float* h_last, float* sr, float* sz, float* sn, float* sghn,
                         cudaStream_t s) {
     if (E > 8 || H % CS != 0 || H / CS > kThreads || fwd_smem(H) > 227 * 1024) return -1;
     FwdArgs a{gi, h0, masks, w_hh, b_hh, hs, h_last, sr, sz, sn, sghn, T, E, H};
-    if (H == 512) return launch_cluster(gru_fwd_cluster_kernel<16>, &a, sizeof(a), E, fwd_smem(H), s, "gru_fwd_cluster_kernel");
-    return launch_cluster(gru_fwd_cluster_kernel<0>, &a, sizeof(a), E, fwd_smem(H), s, "gru_fwd_cluster_kernel");
+    if (H == kH && g_reg_kernels) return launch_cluster(gru_fwd_cluster512_kernel, &a, kFwdThreads, E, 0, s, "gru_fwd_cluster512_kernel");
+    if (H == 512) return launch_cluster(gru_fwd_cluster_kernel<16>, &a, kThreads, E, fwd_smem(H), s, "gru_fwd_cluster_kernel");
+    return launch_cluster(gru_fwd_cluster_kernel<0>, &a, kThreads, E, fwd_smem(H), s, "gru_fwd_cluster_kernel");
 }
 
 int gru_backward_cluster(const float* dhs, const float* masks, const float* w_hh, const float* h0, const float* hs,
@@ -336,7 +550,8 @@ int gru_backward_cluster(const float* dhs, const float* masks, const float* w_hh
                          float* dgi, float* dghn, float* dh0, cudaStream_t s) {
     if (E > 8 || H % CS != 0 || H / CS > kThreads || bwd_smem(H) > 227 * 1024) return -1;
     BwdArgs a{dhs, masks, w_hh, h0, hs, sr, sz, sn, sghn, dgi, dghn, dh0, T, E, H};
-    return launch_cluster(gru_bwd_cluster_kernel, &a, sizeof(a), E, bwd_smem(H), s, "gru_bwd_cluster_kernel");
+    if (H == kH && g_reg_kernels) return launch_cluster(gru_bwd_cluster512_kernel, &a, kH, E, 0, s, "gru_bwd_cluster512_kernel");
+    return launch_cluster(gru_bwd_cluster_kernel, &a, kThreads, E, bwd_smem(H), s, "gru_bwd_cluster_kernel");
 }
 
 }  // namespace ppd
