@@ -193,6 +193,8 @@ int ppd_sgemm(const ppd_gemm_args* g, void* workspace, size_t workspace_bytes, v
 size_t ppd_tc_gemm_workspace(int64_t I, int64_t J, int64_t KK);
 int ppd_tc_gemm_supported(const ppd_gemm_args* g);
 int ppd_tc_gemm(const ppd_gemm_args* g, int flags, void* workspace, size_t workspace_bytes, void* stream);
+/* Tuning switch (default 1): narrow tiles run as two co-resident CTAs with a 2-deep ring each. */
+void ppd_tc_gemm_set_option(int two_ctas);
 /* out[j] (+)= sum_i X[i*ld + j]  (bias gradients) */
 size_t ppd_colsum_workspace(int64_t I, int64_t J);
 int ppd_colsum(const float* X, int64_t ld, int64_t I, int64_t J, float* out, int accumulate,

@@ -76,6 +76,7 @@ _PROTOTYPES = {
     "ppd_tc_gemm_workspace": (c_size_t, [c_int64, c_int64, c_int64]),
     "ppd_tc_gemm_supported": (c_int, [POINTER(GemmArgs)]),
     "ppd_tc_gemm": (c_int, [POINTER(GemmArgs), c_int, _P, c_size_t, _P]),
+    "ppd_tc_gemm_set_option": (None, [c_int]),
     "ppd_colsum_workspace": (c_size_t, [c_int64, c_int64]),
     "ppd_colsum": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, _P, c_size_t, _P]),
     "ppd_im2col_nchw": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P]),

@@ -403,6 +403,7 @@ int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int6
     return 0;
 }
 
+int g_two_ctas = 1;
 struct Plan { int bn; int64_t gx, gy; int splits; int64_t kk_per_split; size_t ws; };
 
 int pick_bn(int64_t J, bool split3) {
@@ -442,6 +443,8 @@ Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_avail, bool limit, bo
 }
 
 }  // namespace
+
+extern "C" void ppd_tc_gemm_set_option(int two_ctas) { g_two_ctas = two_ctas; }
 
 extern "C" size_t ppd_tc_gemm_workspace(int64_t I, int64_t J, int64_t KK) {
     if (I <= 0 || J <= 0 || KK <= 0) return 0;
@@ -483,7 +486,11 @@ extern "C" int ppd_tc_gemm(const ppd_gemm_args* g, int flags, void* workspace, s
     a.partial = p.splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
     a.split3 = split3;
     const size_t stage = (size_t)(split3 ? 2 : 1) * (BM * BK * 4 + (size_t)p.bn * BK * 4);
-    int stages = (int)((196 * 1024) / stage);
+    // Ring depth: if two CTAs (2 x 256 TMEM columns) can be co-resident with at least a 2-deep ring each, size
+    // the ring for that -- one CTA's prologue / epilogue then hides behind the other's main loop (the kernel
+    // is not persistent); otherwise give the single CTA as deep a ring as fits.
+    int stages = (int)((110 * 1024) / stage);
+    if (stages < 2 || !g_two_ctas) stages = (int)((196 * 1024) / stage);
     if (stages > kMaxStages) stages = kMaxStages;
     a.stages = stages;
     const size_t smem = (size_t)stages * stage + 1024;
