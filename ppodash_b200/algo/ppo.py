@@ -16,6 +16,7 @@ the loss partial sums in its tail) once per minibatch; all ranks then apply the 
 import torch
 
 from .. import _lib
+from .. import dist as ppd_dist
 from .._lib import check, lib
 from ..storage import FusedAdvantages
 
@@ -84,12 +85,7 @@ class PPO():
         self.last_grad_norm = None
 
     def _world(self):
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()):
-            return 1, None
-        pg = self.process_group
-        ws = dist.get_world_size(pg)
-        return ws, dist
+        return ppd_dist.world(self.process_group)[0]
 
     def advantage_stats(self, rollouts):
         """Device tensor [mean, std + 1e-5] of returns[:-1] - value_preds[:-1] over all ranks."""
@@ -103,9 +99,7 @@ class PPO():
         st = _lib.stream_ptr(dev)
         check(L.ppd_advantage_moments(_lib.ptr(rollouts.returns, torch.float32), _lib.ptr(rollouts.value_preds, torch.float32),
                                       n, mom.data_ptr(), ws.data_ptr(), ws.numel(), st), "advantage_moments")
-        world, dist = self._world()
-        if world > 1:
-            dist.all_reduce(mom, group=self.process_group)
+        ppd_dist.all_reduce_sum(mom, self.process_group)        # {sum, sum of squares, count} over all ranks
         check(L.ppd_advantage_finalize(mom.data_ptr(), stats.data_ptr(), st), "advantage_finalize")
         return stats
 
@@ -114,7 +108,7 @@ class PPO():
         eng = pol.engine()
         eng.bind()
         dev = eng.device
-        world, dist = self._world()
+        world = self._world()
         stats = self.advantage_stats(rollouts)
         advantages = FusedAdvantages(stats)
         loss_acc = torch.zeros(3, dtype=torch.float32, device=dev)
@@ -130,8 +124,7 @@ class PPO():
                 rows = sample[0].shape[0]
                 eng.train_minibatch(sample, self.clip_param, self.value_loss_coef, self.entropy_coef,
                                     self.use_clipped_value_loss, global_rows=rows * world)
-                if world > 1:
-                    dist.all_reduce(eng.flat_grad, group=self.process_group)     # grads + loss partials
+                ppd_dist.all_reduce_sum(eng.flat_grad, self.process_group)        # grads + loss partials
                 self.optimizer.step(loss_acc=loss_acc, grad_norm_out=gnorm)
 
         num_updates = self.ppo_epoch * self.num_mini_batch
