@@ -112,16 +112,20 @@ def bench_adam(n):
 
 def main():
     peak, how = peak_hbm()
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"
     res = []
-    for T, N in ((512, 32), (512, 1024), (2048, 4096)):
-        res.append(bench_gae(T, N))
-    res.append(bench_gae(2048, 4096, proper=True))
-    res.append(bench_gather(512, 32, 3, 15, True, 8))
-    res.append(bench_gather(128, 32, 4, 0, False, 4))
-    res.append(bench_gather(512, 256, 3, 15, True, 8))
-    res.append(bench_gather(512, 256, 3, 15, False, 8))
-    res.append(bench_adam(2464393))
-    res.append(bench_adam(1 << 26))
+    if only in ("all", "returns"):
+        for T, N in ((512, 32), (512, 1024), (2048, 4096)):
+            res.append(bench_gae(T, N))
+        res.append(bench_gae(2048, 4096, proper=True))
+    if only in ("all", "gather"):
+        res.append(bench_gather(512, 32, 3, 15, True, 8))
+        res.append(bench_gather(128, 32, 4, 0, False, 4))
+        res.append(bench_gather(512, 256, 3, 15, True, 8))
+        res.append(bench_gather(512, 256, 3, 15, False, 8))
+    if only in ("all", "adam"):
+        res.append(bench_adam(2464393))
+        res.append(bench_adam(1 << 26))
     for r in res:
         r["frac_of_hbm_peak"] = r["gbs"] / peak
         r["peak"] = how
