@@ -193,6 +193,15 @@ int ppd_sgemm(const ppd_gemm_args* g, void* workspace, size_t workspace_bytes, v
 size_t ppd_tc_gemm_workspace(int64_t I, int64_t J, int64_t KK);
 int ppd_tc_gemm_supported(const ppd_gemm_args* g);
 int ppd_tc_gemm(const ppd_gemm_args* g, int flags, void* workspace, size_t workspace_bytes, void* stream);
+/* dgrad of an NHWC convolution with col2im fused into the epilogue: the product dY[M,N] W[N,(ky,kx,c)] is not
+ * stored but scatter-added (red.global.add.v4.f32) into dx[B,H,W,C], which the caller has zeroed; follow with
+ * ppd_relu_mask.  Replaces the dcols round trip through HBM (write + col2im read).  g->C = dx, g->ldc ignored.
+ * Summation order of the overlapping taps is not fixed (fp32 atomics); the "fp32" mode keeps the deterministic
+ * ppd_sgemm + ppd_col2im_nhwc pair. */
+typedef struct ppd_conv_geom { int B, H, W, C, kh, kw, stride; } ppd_conv_geom;   /* input tensor [B,H,W,C] and the filter */
+int ppd_tc_gemm_col2im(const ppd_gemm_args* g, const ppd_conv_geom* geom, int flags, void* stream);
+/* x[i] = act[i] > 0 ? x[i] : 0 */
+int ppd_relu_mask(float* x, const float* act, int64_t n, void* stream);
 /* Tuning switch (default 1): narrow tiles run as two co-resident CTAs with a 2-deep ring each. */
 void ppd_tc_gemm_set_option(int two_ctas);
 /* out[j] (+)= sum_i X[i*ld + j]  (bias gradients) */

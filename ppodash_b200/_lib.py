@@ -47,6 +47,11 @@ class GemmArgs(Structure):
     ]
 
 
+class ConvGeom(Structure):
+    """Mirror of ``ppd_conv_geom``."""
+    _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("C", c_int), ("kh", c_int), ("kw", c_int), ("stride", c_int)]
+
+
 _P = c_void_p
 _PROTOTYPES = {
     "ppd_abi_version": (c_int, []),
@@ -77,6 +82,8 @@ _PROTOTYPES = {
     "ppd_tc_gemm_supported": (c_int, [POINTER(GemmArgs)]),
     "ppd_tc_gemm": (c_int, [POINTER(GemmArgs), c_int, _P, c_size_t, _P]),
     "ppd_tc_gemm_set_option": (None, [c_int]),
+    "ppd_tc_gemm_col2im": (c_int, [POINTER(GemmArgs), POINTER(ConvGeom), c_int, _P]),
+    "ppd_relu_mask": (c_int, [_P, _P, c_int64, _P]),
     "ppd_colsum_workspace": (c_size_t, [c_int64, c_int64]),
     "ppd_colsum": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, _P, c_size_t, _P]),
     "ppd_im2col_nchw": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P]),

@@ -119,6 +119,17 @@ batched_transpose_kernel(const float* __restrict__ x, int R, int Cc, float* __re
     }
 }
 
+// x = act > 0 ? x : 0   (ReLU backward applied after a scatter-added col2im)
+__global__ void __launch_bounds__(kThreads)
+relu_mask_kernel(float* __restrict__ x, const float* __restrict__ act, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kThreads) {
+        float4 v = reinterpret_cast<float4*>(x)[i];
+        const float4 a = __ldg(reinterpret_cast<const float4*>(act) + i);
+        v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
+        reinterpret_cast<float4*>(x)[i] = v;
+    }
+}
+
 int grid_for(int64_t total) {
     int64_t b = (total + kThreads - 1) / kThreads;
     const int64_t cap = 16 * (int64_t)ppd::kNumSMs;
@@ -178,4 +189,11 @@ extern "C" int ppd_batched_transpose(const float* x, int64_t B, int R, int Cc, f
     PPD_REQUIRE(smem <= 48 * 1024, "matrix too large for the shared-memory transpose");
     batched_transpose_kernel<<<(unsigned)B, kThreads, smem, ppd::as_stream(stream)>>>(x, R, Cc, y);
     return ppd::launch_status("batched_transpose_kernel");
+}
+
+extern "C" int ppd_relu_mask(float* x, const float* act, int64_t n, void* stream) {
+    PPD_REQUIRE(x && act, "null pointer");
+    PPD_REQUIRE(n > 0 && n % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)act % 16 == 0, "n must be a multiple of 4, buffers 16-byte aligned");
+    relu_mask_kernel<<<grid_for(n / 4), kThreads, 0, ppd::as_stream(stream)>>>(x, act, n / 4);
+    return ppd::launch_status("relu_mask_kernel");
 }

@@ -15,9 +15,8 @@
 //            one 8-byte store)
 //   look-back the carry entering the segment is the fold of the maps of all LATER segments of
 //            the same env block; each warp polls a contiguous range of them (they were
-//            scheduled earlier because segments are handed out latest-first through an atomic
-//            ticket, and their maps do not depend on any carry, so there is no serial chain
-//            between CTAs)
+//            scheduled earlier because segments are ordered latest-first by block index, and
+//            their maps do not depend on any carry, so there is no serial chain between CTAs)
 //   phase B  fold the in-CTA maps to get the carry entering this warp's chunk
 //   phase C  replay the chunk from the true carry with the reference's exact op order and
 //            write returns[t].
@@ -33,10 +32,10 @@ constexpr int kSeg = kSteps * kWarps;     // steps per CTA
 constexpr int kHeaderBytes = 128;
 
 // Workspace header.  The workspace must be zero-filled once when it is allocated; every launch
-// leaves it ready for the next one (the last CTA to finish resets the ticket and bumps the epoch),
+// leaves it ready for the next one (the last CTA to finish bumps the epoch that tags published maps),
 // so no memset is enqueued per call.
 struct Header {
-    unsigned ticket;   // next CTA ticket of the running launch
+    unsigned unused;
     unsigned done;     // CTAs that finished
     unsigned epoch;    // number of completed launches; flags of the running launch carry epoch + 1
 };
@@ -70,16 +69,12 @@ returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ value
     __shared__ float sQ[kWarps][32];
     __shared__ float lP[kWarps][32];
     __shared__ float lQ[kWarps][32];
-    __shared__ unsigned s_ticket, s_epoch;
-    if (threadIdx.x == 0) {
-        s_epoch = *reinterpret_cast<volatile unsigned*>(&hdr->epoch) + 1u;
-        s_ticket = atomicAdd(&hdr->ticket, 1u);
-    }
-    __syncthreads();
-    const unsigned epoch = s_epoch;
-    const int ticket = (int)s_ticket;
-    const int seg = ticket / nblk;            // 0 = latest segment in time (handed out first)
-    const int blk = ticket - seg * nblk;
+    // Segments are ordered latest-first by block index; like CUB's decoupled look-back this relies on the
+    // hardware dispatching CTAs in block-index order (a CTA only ever waits for lower-indexed CTAs).  The epoch
+    // load is independent of the data loads below, so its latency is hidden behind them.
+    const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&hdr->epoch) + 1u;
+    const int seg = blockIdx.x / nblk;        // 0 = latest segment in time
+    const int blk = blockIdx.x - seg * nblk;
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
     const int n = blk * 32 + lane;
@@ -191,7 +186,6 @@ returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ value
     if (threadIdx.x == 0) {
         const unsigned prev = atomicAdd(&hdr->done, 1u);
         if (prev == gridDim.x - 1) {
-            hdr->ticket = 0;
             hdr->done = 0;
             __threadfence();
             *reinterpret_cast<volatile unsigned*>(&hdr->epoch) = epoch;

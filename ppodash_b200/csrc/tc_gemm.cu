@@ -43,6 +43,9 @@ struct Args {
     int stages;
     int64_t kk_per_split;
     float* partial;
+    // fused col2im (dgrad of an NHWC convolution): column j = (ky, kx, c), row i = (b, oy, ox);
+    // the tile is scatter-added into dx[b, oy*stride+ky, ox*stride+kx, c] instead of being stored
+    int scatter, OH, OW, kw, cstride, Cin, Hin, Win;
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -303,7 +306,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
             }
-            if (a.transpose_out) {
+            if (a.scatter) {
+                // 32 consecutive columns = 32 consecutive input channels of one filter tap (Cin is a multiple of 32)
+                if (i < a.I && jb < a.J) {
+                    const int tap = (int)(jb / a.Cin), c0 = (int)(jb - (int64_t)tap * a.Cin);
+                    const int ky = tap / a.kw, kx = tap - ky * a.kw;
+                    const int64_t b = i / ((int64_t)a.OH * a.OW);
+                    const int rem = (int)(i - b * a.OH * a.OW);
+                    const int oy = rem / a.OW, ox = rem - oy * a.OW;
+                    float* dst = a.C + (((b * a.Hin + (oy * a.cstride + ky)) * (int64_t)a.Win + (ox * a.cstride + kx)) * a.Cin + c0);
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v[c]), "f"(v[c + 1]),
+                                     "f"(v[c + 2]), "f"(v[c + 3])
+                                     : "memory");
+                }
+            } else if (a.transpose_out) {
                 // C is [J, I] row-major: for fixed column the 32 lanes write 32 consecutive floats
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -461,12 +479,37 @@ extern "C" int ppd_tc_gemm_supported(const ppd_gemm_args* g) {
     return 1;
 }
 
+namespace {
+int tc_gemm_impl(const ppd_gemm_args* g, int flags, const ppd_conv_geom* geom, void* workspace, size_t workspace_bytes,
+                 void* stream);
+}
+
 extern "C" int ppd_tc_gemm(const ppd_gemm_args* g, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+    return tc_gemm_impl(g, flags, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ppd_tc_gemm_col2im(const ppd_gemm_args* g, const ppd_conv_geom* geom, int flags, void* stream) {
+    PPD_REQUIRE(g && geom, "null pointer");
+    PPD_REQUIRE(!(flags & PPD_TC_TRANSPOSE_OUT) && !g->bias && !g->mask && !g->relu, "plain product only");
+    PPD_REQUIRE(geom->C % 32 == 0 && geom->kh > 0 && geom->kw > 0 && geom->stride > 0, "channels must be a multiple of 32");
+    const int OH = (geom->H - geom->kh) / geom->stride + 1, OW = (geom->W - geom->kw) / geom->stride + 1;
+    PPD_REQUIRE(g->I == (int64_t)geom->B * OH * OW && g->J == (int64_t)geom->kh * geom->kw * geom->C, "GEMM shape does not match the geometry");
+    PPD_REQUIRE(((uintptr_t)g->C & 15) == 0, "dx must be 16-byte aligned");
+    return tc_gemm_impl(g, flags, geom, nullptr, 0, stream);
+}
+
+namespace {
+int tc_gemm_impl(const ppd_gemm_args* g, int flags, const ppd_conv_geom* geom, void* workspace, size_t workspace_bytes,
+                 void* stream) {
     const int transpose_out = flags & PPD_TC_TRANSPOSE_OUT;
     const int split3 = (flags & PPD_TC_SPLIT3) ? 1 : 0;
     PPD_REQUIRE(ppd_tc_gemm_supported(g), "operands must be 16-byte aligned with leading dimensions that are multiples of 4");
-    PPD_REQUIRE(transpose_out ? g->ldc >= g->I : g->ldc >= g->J, "bad ldc");
-    const Plan p = make_plan(g->I, g->J, g->KK, workspace ? workspace_bytes : 0, true, split3);
+    PPD_REQUIRE(geom || (transpose_out ? g->ldc >= g->I : g->ldc >= g->J), "bad ldc");
+    Plan p = make_plan(g->I, g->J, g->KK, workspace ? workspace_bytes : 0, true, split3);
+    if (geom && p.splits > 1) {           // the scatter epilogue adds complete products only
+        p.splits = 1;
+        p.kk_per_split = (g->KK + BK - 1) / BK * BK;
+    }
     PPD_REQUIRE(p.gy <= 65535 && p.splits <= 65535, "grid too large");
     CUtensorMap tmA, tmB;
     int rc;
@@ -485,6 +528,13 @@ extern "C" int ppd_tc_gemm(const ppd_gemm_args* g, int flags, void* workspace, s
     a.kk_per_split = p.kk_per_split;
     a.partial = p.splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
     a.split3 = split3;
+    a.scatter = geom ? 1 : 0;
+    if (geom) {
+        a.OH = (geom->H - geom->kh) / geom->stride + 1; a.OW = (geom->W - geom->kw) / geom->stride + 1;
+        a.kw = geom->kw; a.cstride = geom->stride; a.Cin = geom->C; a.Hin = geom->H; a.Win = geom->W;
+    } else {
+        a.OH = a.OW = a.kw = a.cstride = a.Cin = a.Hin = a.Win = 0;
+    }
     const size_t stage = (size_t)(split3 ? 2 : 1) * (BM * BK * 4 + (size_t)p.bn * BK * 4);
     // Ring depth: if two CTAs (2 x 256 TMEM columns) can be co-resident with at least a 2-deep ring each, size
     // the ring for that -- one CTA's prologue / epilogue then hides behind the other's main loop (the kernel
@@ -511,3 +561,4 @@ extern "C" int ppd_tc_gemm(const ppd_gemm_args* g, int flags, void* workspace, s
                                                          g->ldm, g->relu, g->accumulate, transpose_out);
     return ppd::launch_status("tc_splitk_reduce_kernel");
 }
+}  // namespace

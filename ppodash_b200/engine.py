@@ -22,7 +22,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, check, lib
+from ._lib import ConvGeom, GemmArgs, check, lib
 
 ALIGN = 64  # floats (256 B)
 
@@ -222,6 +222,30 @@ class PolicyEngine:
         ws = _lib.workspace(L.ppd_sgemm_workspace(I, J, KK), self.device, "gemm")
         check(L.ppd_sgemm(ctypes.byref(g), ws.data_ptr(), ws.numel(), self.stream), "sgemm")
 
+    def _dgrad_col2im(self, dY, N, W, K, n, Hin, Cin, k, stride, act, dx):
+        """dx[n,Hin,Hin,Cin] = ReLU'(act) * col2im(dY[M,N] @ W[N,K]).  Tensor-core modes fuse col2im into the GEMM
+        epilogue (scatter-add, no dcols matrix in HBM); fp32 mode uses the deterministic SIMT GEMM + gather col2im."""
+        L = lib()
+        OH = (Hin - k) // stride + 1
+        M = n * OH * OH
+        if self.precision == "fp32":
+            dcols = self.buf("dcols", M, K)
+            self._gemm(dY, N, 1, W, K, 0, dcols, K, M, K, N)
+            check(L.ppd_col2im_nhwc(dcols.data_ptr(), K, n, Hin, Hin, Cin, k, k, stride, act.data_ptr(), dx.data_ptr(),
+                                    self.stream), "col2im")
+            return
+        g = GemmArgs()
+        g.A, g.lda, g.a_kmajor = dY.data_ptr(), N, 1
+        g.B, g.ldb, g.b_kmajor = W.data_ptr(), K, 0
+        g.C, g.ldc = dx.data_ptr(), K
+        g.I, g.J, g.KK = M, K, N
+        geom = ConvGeom(n, Hin, Hin, Cin, k, k, stride)
+        cnt = n * Hin * Hin * Cin
+        dx.view(-1)[:cnt].zero_()
+        check(L.ppd_tc_gemm_col2im(ctypes.byref(g), ctypes.byref(geom), 2 if self.precision == "tf32x3" else 0, self.stream),
+              "tc_gemm_col2im")
+        check(L.ppd_relu_mask(dx.data_ptr(), act.data_ptr(), cnt, self.stream), "relu_mask")
+
     def _colsum(self, X, ld, I, J, out, acc=0):
         L = lib()
         ws = _lib.workspace(L.ppd_colsum_workspace(I, J), self.device, "colsum")
@@ -283,8 +307,6 @@ class PolicyEngine:
         cols1 = self.buf("cols1", ch * s1 * s1, K1)
         cols2 = self.buf("cols2", ch * s2 * s2, K2)
         cols3 = self.buf("cols3", ch * s3 * s3, K3)
-        dcols3 = self.buf("dcols3", ch * s3 * s3, K3)
-        dcols2 = self.buf("dcols2", ch * s2 * s2, K2)
         dy2 = self.buf("dy2", ch, s2 * s2 * 64)
         dy1 = self.buf("dy1", ch, s1 * s1 * 32)
         w2, w3 = self.seg("conv2.w"), self.seg("conv3.w")
@@ -298,15 +320,13 @@ class PolicyEngine:
                 check(L.ppd_im2col_nhwc(a2[r0:].data_ptr(), n, s2, s2, 64, 3, 3, 1, cols3.data_ptr(), K3, st), "im2col3")
             self._gemm(dy3[r0:], 32, 0, cols3, K3, 0, self.seg("conv3.w", True), K3, 32, K3, M3, acc=acc)
             self._colsum(dy3[r0:], 32, M3, 32, self.seg("conv3.b", True), acc)
-            self._gemm(dy3[r0:], 32, 1, w3, K3, 0, dcols3, K3, M3, K3, 32)
-            check(L.ppd_col2im_nhwc(dcols3.data_ptr(), K3, n, s2, s2, 64, 3, 3, 1, a2[r0:].data_ptr(), dy2.data_ptr(), st), "col2im3")
+            self._dgrad_col2im(dy3[r0:], 32, w3, K3, n, s2, 64, 3, 1, a2[r0:], dy2)
             # conv2
             if not self._cols_valid:
                 check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, cols2.data_ptr(), K2, st), "im2col2")
             self._gemm(dy2, 64, 0, cols2, K2, 0, self.seg("conv2.w", True), K2, 64, K2, M2, acc=acc)
             self._colsum(dy2, 64, M2, 64, self.seg("conv2.b", True), acc)
-            self._gemm(dy2, 64, 1, w2, K2, 0, dcols2, K2, M2, K2, 64)
-            check(L.ppd_col2im_nhwc(dcols2.data_ptr(), K2, n, s1, s1, 32, 4, 4, 2, a1[r0:].data_ptr(), dy1.data_ptr(), st), "col2im2")
+            self._dgrad_col2im(dy2, 64, w2, K2, n, s1, 32, 4, 2, a1[r0:], dy1)
             # conv1 (no input gradient needed)
             if not self._cols_valid:
                 check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, cols1.data_ptr(), K1, st), "im2col1")

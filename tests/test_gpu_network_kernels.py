@@ -268,3 +268,31 @@ def test_tc_gemm_wgrad_both_mn_major_splitk(M, N, K, swap, split3):
         tc_gemm(dY.to(DEV), N, 0, X.to(DEV), K, 0, dW, K, N, K, M, acc=1, split3=split3)
     scale = float((want - dW0).abs().max()) + 1e-6
     assert float((dW.cpu() - want).abs().max()) <= (2e-5 if split3 else 4e-3) * scale
+
+
+@pytest.mark.parametrize("split3", [0, 1])
+@pytest.mark.parametrize("B,H,C,k,s,N", [(7, 9, 64, 3, 1, 32), (5, 20, 32, 4, 2, 64), (40, 20, 32, 4, 2, 64)])
+def test_tc_gemm_fused_col2im(B, H, C, k, s, N, split3):
+    """Conv dgrad with col2im in the GEMM epilogue (scatter-add) + ReLU mask == unfold-transpose reference."""
+    from ppodash_b200._lib import ConvGeom
+    L = _lib.lib()
+    g0 = torch.Generator().manual_seed(B + H + C)
+    OH = (H - k) // s + 1
+    M, K = B * OH * OH, k * k * C
+    dY = torch.randn(M, N, generator=g0)
+    W = torch.randn(N, K, generator=g0) / np.sqrt(N)                       # columns ordered (ky,kx,c)
+    act = torch.randn(B, H, H, C, generator=g0)
+    dcols = dY.double() @ W.double()
+    d_u = dcols.reshape(B, OH * OH, k, k, C).permute(0, 4, 2, 3, 1).reshape(B, C * k * k, OH * OH)
+    want = (F.fold(d_u, (H, H), k, stride=s).permute(0, 2, 3, 1) * (act > 0)).float()
+    dYd, Wd, actd = dY.to(DEV), W.to(DEV), act.to(DEV)
+    dx = torch.zeros(B, H, H, C, device=DEV)
+    g = GemmArgs()
+    g.A, g.lda, g.a_kmajor = dYd.data_ptr(), N, 1
+    g.B, g.ldb, g.b_kmajor = Wd.data_ptr(), K, 0
+    g.C, g.ldc, g.I, g.J, g.KK = dx.data_ptr(), K, M, K, N
+    geom = ConvGeom(B, H, H, C, k, k, s)
+    _lib.check(L.ppd_tc_gemm_col2im(ctypes.byref(g), ctypes.byref(geom), 2 if split3 else 0, _lib.stream_ptr()))
+    _lib.check(L.ppd_relu_mask(dx.data_ptr(), actd.data_ptr(), dx.numel(), _lib.stream_ptr()))
+    scale = float(want.abs().max())
+    assert float((dx.cpu() - want).abs().max()) <= (2e-5 if split3 else 4e-3) * scale
