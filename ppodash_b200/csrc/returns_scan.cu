@@ -58,6 +58,96 @@ __device__ __forceinline__ void wait_map(const uint2* slot, unsigned epoch, floa
     Q = __uint_as_float(b.x);
 }
 
+// Loads of one warp-chunk (kSteps steps of one env per lane, all issued before any use) and phase A:
+// the chunk evaluated with zero incoming carry -> affine map (P, Q); per-step values kept for the replay.
+template <bool GAE, bool PROPER, bool FULL>
+__device__ __forceinline__ void load_and_fold(const float* __restrict__ rewards, const float* __restrict__ value_preds,
+                                              const float* __restrict__ masks, const float* __restrict__ bad_masks,
+                                              int T, int N, int n, int t0, float nv, float g, float gl, bool live,
+                                              float (&f0)[kSteps], float (&f1)[kSteps], float (&f2)[kSteps],
+                                              float (&f3)[kSteps], float& P, float& Q) {
+    float r_[kSteps], v_[kSteps + 1], m_[kSteps], b_[kSteps];
+    if (FULL) {
+        const size_t o0 = (size_t)t0 * N + n;
+        const float* pr = rewards + o0;
+        const float* pm = masks + o0 + N;
+        const float* pb = PROPER ? bad_masks + o0 + N : nullptr;
+        const float* pv = value_preds + o0;
+#pragma unroll
+        for (int i = 0; i < kSteps; ++i) {
+            r_[i] = __ldg(pr + (size_t)i * N);
+            m_[i] = __ldg(pm + (size_t)i * N);                      // m_{t+1}
+            if (PROPER) b_[i] = __ldg(pb + (size_t)i * N);          // b_{t+1}
+            if (GAE || PROPER) v_[i] = pv[(size_t)i * N];
+        }
+        if (GAE) v_[kSteps] = (t0 + kSteps >= T) ? nv : pv[(size_t)kSteps * N];
+    } else {
+#pragma unroll
+        for (int i = 0; i < kSteps; ++i) {
+            const int t = t0 + i;
+            const bool ok = live && t >= 0;
+            const size_t o = (size_t)(ok ? t : 0) * N + (live ? n : 0);
+            r_[i] = ok ? __ldg(rewards + o) : 0.f;
+            m_[i] = ok ? __ldg(masks + o + N) : 1.f;
+            if (PROPER) b_[i] = ok ? __ldg(bad_masks + o + N) : 1.f;
+            if (GAE || PROPER) v_[i] = ok ? value_preds[o] : 0.f;
+        }
+        if (GAE) {
+            const int tt = t0 + kSteps;
+            v_[kSteps] = (tt >= T) ? nv : ((live && tt >= 0) ? value_preds[(size_t)tt * N + n] : 0.f);
+        }
+    }
+    P = 1.f; Q = 0.f;
+#pragma unroll
+    for (int i = kSteps - 1; i >= 0; --i) {
+        const bool in = FULL || (t0 + i) >= 0;
+        if (GAE) {
+            const float delta = (r_[i] + (g * v_[i + 1]) * m_[i]) - v_[i];   // storage.py:93-95
+            const float coef = gl * m_[i];                                    // storage.py:96-97
+            f0[i] = delta; f1[i] = coef; f2[i] = v_[i];
+            if (PROPER) f3[i] = b_[i];
+            if (in) {
+                Q = delta + coef * Q;
+                P = coef * P;
+                if (PROPER) { Q = Q * b_[i]; P = P * b_[i]; }
+            }
+        } else {
+            f0[i] = r_[i]; f1[i] = m_[i];
+            if (PROPER) { f2[i] = v_[i]; f3[i] = b_[i]; }
+            if (in) {
+                Q = (Q * g) * m_[i] + r_[i];
+                P = (P * g) * m_[i];
+                if (PROPER) { Q = Q * b_[i] + (1.f - b_[i]) * v_[i]; P = P * b_[i]; }
+            }
+        }
+    }
+}
+
+// Phase C: replay of the chunk from the true carry x, in the reference's exact operation order.
+template <bool GAE, bool PROPER, bool FULL>
+__device__ __forceinline__ void replay_and_store(float* __restrict__ returns, int N, int n, int t0, float g, bool live,
+                                                 const float (&f0)[kSteps], const float (&f1)[kSteps],
+                                                 const float (&f2)[kSteps], const float (&f3)[kSteps], float x) {
+    float* po = returns + (size_t)(FULL ? t0 : 0) * N + n;
+#pragma unroll
+    for (int i = kSteps - 1; i >= 0; --i) {
+        const int t = t0 + i;
+        if (!FULL && t < 0) continue;
+        float out;
+        if (GAE) {
+            x = f0[i] + f1[i] * x;                     // gae = delta + gamma*lambda*m*gae
+            if (PROPER) x = x * f3[i];                 // gae = gae * bad_mask   (storage.py:98)
+            out = x + f2[i];                           // returns = gae + V_t
+        } else {
+            x = (x * g) * f1[i] + f0[i];               // storage.py:120-121
+            if (PROPER) x = x * f3[i] + (1.f - f3[i]) * f2[i];   // storage.py:104-105
+            out = x;
+        }
+        if (FULL) __stcs(po + (size_t)i * N, out);
+        else if (live) __stcs(returns + (size_t)t * N + n, out);
+    }
+}
+
 template <bool GAE, bool PROPER>
 __global__ void __launch_bounds__(kWarps * 32)
 returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ value_preds,
@@ -87,51 +177,14 @@ returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ value
     }
 
     const int t0 = t_hi - (w + 1) * kSteps;   // first step of this warp's chunk (may be < 0)
+    // FULL chunk: every step in range and every lane a real env -> no per-element predicates or clamps
+    const bool full = (t0 >= 0) && (blk * 32 + 32 <= N);
     float f0[kSteps], f1[kSteps], f2[kSteps], f3[kSteps];
-    {
-        float r_[kSteps], v_[kSteps + 1], m_[kSteps], b_[kSteps];
-#pragma unroll
-        for (int i = 0; i < kSteps; ++i) {
-            const int t = t0 + i;
-            const bool ok = live && t >= 0;
-            const size_t o = (size_t)(ok ? t : 0) * N + (live ? n : 0);
-            r_[i] = ok ? __ldg(rewards + o) : 0.f;
-            m_[i] = ok ? __ldg(masks + o + N) : 1.f;                    // m_{t+1}
-            if (PROPER) b_[i] = ok ? __ldg(bad_masks + o + N) : 1.f;    // b_{t+1}
-            if (GAE || PROPER) v_[i] = ok ? value_preds[o] : 0.f;
-        }
-        if (GAE) {
-            const int tt = t0 + kSteps;       // V_{t+1} of the chunk's last step
-            v_[kSteps] = (tt >= T) ? nv : ((live && tt >= 0) ? value_preds[(size_t)tt * N + n] : 0.f);
-        }
-        // ---- phase A: chunk with zero carry
-        float P = 1.f, Q = 0.f;
-#pragma unroll
-        for (int i = kSteps - 1; i >= 0; --i) {
-            const bool in = (t0 + i) >= 0;
-            if (GAE) {
-                const float delta = (r_[i] + (g * v_[i + 1]) * m_[i]) - v_[i];   // storage.py:93-95
-                const float coef = gl * m_[i];                                    // storage.py:96-97
-                f0[i] = delta; f1[i] = coef; f2[i] = v_[i];
-                if (PROPER) f3[i] = b_[i];
-                if (in) {
-                    Q = delta + coef * Q;
-                    P = coef * P;
-                    if (PROPER) { Q = Q * b_[i]; P = P * b_[i]; }
-                }
-            } else {
-                f0[i] = r_[i]; f1[i] = m_[i];
-                if (PROPER) { f2[i] = v_[i]; f3[i] = b_[i]; }
-                if (in) {
-                    Q = (Q * g) * m_[i] + r_[i];
-                    P = (P * g) * m_[i];
-                    if (PROPER) { Q = Q * b_[i] + (1.f - b_[i]) * v_[i]; P = P * b_[i]; }
-                }
-            }
-        }
-        sP[w][lane] = P;
-        sQ[w][lane] = Q;
-    }
+    float P, Q;
+    if (full) load_and_fold<GAE, PROPER, true>(rewards, value_preds, masks, bad_masks, T, N, n, t0, nv, g, gl, true, f0, f1, f2, f3, P, Q);
+    else      load_and_fold<GAE, PROPER, false>(rewards, value_preds, masks, bad_masks, T, N, n, t0, nv, g, gl, live, f0, f1, f2, f3, P, Q);
+    sP[w][lane] = P;
+    sQ[w][lane] = Q;
     __syncthreads();
     // ---- publish this segment's map (warp 0): fold of the kWarps chunk maps, latest chunk first
     if (w == 0 && seg + 1 < nseg) {
@@ -165,22 +218,8 @@ returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ value
     // ---- phase B: carry entering this warp's chunk
     for (int ww = 0; ww < w; ++ww) x = sP[ww][lane] * x + sQ[ww][lane];
     // ---- phase C: replay with the reference's exact operation order
-#pragma unroll
-    for (int i = kSteps - 1; i >= 0; --i) {
-        const int t = t0 + i;
-        if (t < 0) continue;
-        float out;
-        if (GAE) {
-            x = f0[i] + f1[i] * x;                     // gae = delta + gamma*lambda*m*gae
-            if (PROPER) x = x * f3[i];                 // gae = gae * bad_mask   (storage.py:98)
-            out = x + f2[i];                           // returns = gae + V_t
-        } else {
-            x = (x * g) * f1[i] + f0[i];               // storage.py:120-121
-            if (PROPER) x = x * f3[i] + (1.f - f3[i]) * f2[i];   // storage.py:104-105
-            out = x;
-        }
-        if (live) __stcs(returns + (size_t)t * N + n, out);
-    }
+    if (full) replay_and_store<GAE, PROPER, true>(returns, N, n, t0, g, true, f0, f1, f2, f3, x);
+    else      replay_and_store<GAE, PROPER, false>(returns, N, n, t0, g, live, f0, f1, f2, f3, x);
     // ---- last CTA out re-arms the workspace for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {

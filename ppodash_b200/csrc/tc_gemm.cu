@@ -11,8 +11,9 @@
 //   warp 1   MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BLOCK_N,
 //            K=8 per instruction, 4 per 32-wide k-block) from shared-memory descriptors into a TMEM
 //            accumulator; tcgen05.commit releases ring slots / signals the epilogue
-//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias / ReLU / ReLU-backward mask /
-//            accumulate, vectorised global stores (or transposed stores, or raw split-K partials)
+//   warps 2-9 (3xTF32 mode) split every landed tile into hi / lo TF32 parts in shared memory; then the
+//            epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias / ReLU / ReLU-backward mask /
+//            accumulate, vectorised global stores (or transposed / scatter-added / raw split-K partials)
 // Shared-memory tile layouts are the canonical UMMA ones (cute/atom/mma_traits_sm100.hpp):
 //   k-major : rows of 32 floats (128 B), 8-row 1024 B swizzle atoms, SBO = 1024 B; one TMA box
 //             {32 k, rows}; successive MMAs advance the descriptor start address by 32 B
@@ -27,8 +28,8 @@
 namespace {
 
 constexpr int kMaxStages = 4;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;   // warps 2-5
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;   // warps 2-9: operand split during the main loop, then the epilogue
 constexpr int BM = 128;            // UMMA M
 constexpr int BK = 32;             // floats per k-block (one 128-byte swizzle row)
 constexpr int kTmemCols = 256;
@@ -141,7 +142,7 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
     return d;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -254,7 +255,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // lo*lo term and the rounding of lo zero-mean, so long sums with cancellation (weight gradients)
         // do not pick up a bias.
         if (a.split3) {
-            const int et = threadIdx.x - 64;                         // 0..127
+            const int et = threadIdx.x - 64;                         // 0..255
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
@@ -277,11 +278,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
         // ================= epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+        // two warps share each TMEM lane quarter (a warp may only touch lanes [32*(warp%4), +32)): warps 2-5 take
+        // the even 32-column chunks, warps 6-9 the odd ones
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int64_t i = i0 + q * 32 + lane;
-        for (int c0 = 0; c0 < bn; c0 += 32) {
+        for (int c0 = 32 * half; c0 < bn; c0 += 64) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             if (nkb == 0) {
