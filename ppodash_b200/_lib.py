@@ -59,6 +59,7 @@ _PROTOTYPES = {
     "ppd_launch_count": (c_int64, []),
     "ppd_reset_launch_count": (None, []),
     "ppd_compute_returns_workspace": (c_size_t, [c_int, c_int]),
+    "ppd_compute_returns_set_tuning": (None, [c_int, c_int]),
     "ppd_compute_returns": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_double, c_double, c_int, c_int,
                                     _P, c_size_t, _P]),
     "ppd_advantage_moments_workspace": (c_size_t, [c_int64]),

@@ -23,13 +23,15 @@
 // Each input element is read from HBM exactly once and each output written once:
 // 16 B/step (GAE), 20 B/step with bad_masks.
 #include "ppd_common.cuh"
+#include "tma_utils.cuh"
 
 namespace {
 
-constexpr int kSteps = 16;
-constexpr int kWarps = 8;
-constexpr int kSeg = kSteps * kWarps;     // steps per CTA
+constexpr int kSteps = 16;                // steps per warp chunk (held in registers)
 constexpr int kHeaderBytes = 128;
+int g_warps = 8;                          // warps per CTA: 4, 8 or 16 (ppd_compute_returns_set_tuning)
+int g_min_blocks = 3;                     // __launch_bounds__ min blocks per SM for the 8-warp variant: 3 or 4
+int g_tma_mode = 1;                       // 1 = auto (persistent TMA kernel for large rollouts), 0 = never, 2 = always
 
 // Workspace header.  The workspace must be zero-filled once when it is allocated; every launch
 // leaves it ready for the next one (the last CTA to finish bumps the epoch that tags published maps),
@@ -148,8 +150,8 @@ __device__ __forceinline__ void replay_and_store(float* __restrict__ returns, in
     }
 }
 
-template <bool GAE, bool PROPER>
-__global__ void __launch_bounds__(kWarps * 32)
+template <bool GAE, bool PROPER, int kWarps, int kMinBlocks>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ value_preds,
                     const float* __restrict__ masks, const float* __restrict__ bad_masks,
                     float* __restrict__ returns, const float* __restrict__ next_value,
@@ -170,6 +172,7 @@ returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ value
     const int n = blk * 32 + lane;
     const bool live = n < N;
     const float nv = live ? next_value[n] : 0.f;
+    constexpr int kSeg = kSteps * kWarps;     // steps per CTA
     const int t_hi = T - seg * kSeg;          // exclusive upper step of this segment
     if (seg == 0 && w == 0 && live) {
         if (GAE) value_preds[(size_t)T * N + n] = nv;   // storage.py:90,108
@@ -232,9 +235,171 @@ returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ value
     }
 }
 
+// =====================================================================================================
+// Persistent TMA variant (large rollouts): one CTA per SM walks the (segment, env-block) items in
+// latest-first order; the r / V / m (/ b) tiles of the next kTmaStages items are already in flight as
+// cp.async.bulk.tensor.2d loads into a shared-memory ring (mbarrier expect_tx), so HBM streams
+// continuously while the current item is folded, looked back and replayed.  Same maths, same carries.
+// =====================================================================================================
+constexpr int kTW = 8;                       // warps per CTA
+constexpr int kTSeg = kSteps * kTW;          // 128 steps per item
+constexpr int kMaxTmaStages = 4;
+constexpr int kTileRows = kTSeg;             // r, m, b tiles: 128 rows x 32 envs
+constexpr int kVRows = kTSeg + 1;            // V tile: 129 rows (V_t and V_{t+1})
+constexpr int kVRowsPad = kTSeg + 2;
+
+struct TmaArgs {
+    float* value_preds; float* returns; const float* next_value;
+    int T, N; float g, gl; int nblk, nseg; Header* hdr; uint2* seg_pq; int stages;
+};
+
+template <bool GAE, bool PROPER>
+__global__ void __launch_bounds__(kTW * 32, 1)
+returns_scan_tma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmV,
+                        const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmB, const TmaArgs a) {
+    namespace tma = ppd::tma;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxTmaStages];
+    __shared__ float sP[kTW][32], sQ[kTW][32], lP[kTW][32], lQ[kTW][32];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    constexpr uint32_t kTileBytes = kTileRows * 32 * 4, kVBytes = kVRows * 32 * 4, kVBytesPad = kVRowsPad * 32 * 4;
+    constexpr uint32_t kStageBytes = kTileBytes + kVBytesPad + kTileBytes + (PROPER ? kTileBytes : 0);
+    constexpr uint32_t kTxBytes = kTileBytes + ((GAE || PROPER) ? kVBytes : 0) + kTileBytes + (PROPER ? kTileBytes : 0);
+    const int S = a.stages;
+    const int T = a.T, N = a.N, nblk = a.nblk, nseg = a.nseg;
+    const int items = nblk * nseg;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned epoch = *reinterpret_cast<volatile unsigned*>(&a.hdr->epoch) + 1u;
+
+    auto issue = [&](int k_local) {
+        const int item = blockIdx.x + k_local * gridDim.x;
+        if (item >= items) return;
+        const int seg = item / nblk, blk = item - seg * nblk;
+        const int t_lo = T - (seg + 1) * kTSeg;           // may be negative: those rows are zero-filled
+        const int st = k_local % S;
+        uint8_t* base = smem + (size_t)st * kStageBytes;
+        tma::mbar_expect_tx(&full_bar[st], kTxBytes);
+        tma::load_2d(&tmR, &full_bar[st], base, blk * 32, t_lo);
+        if (GAE || PROPER) tma::load_2d(&tmV, &full_bar[st], base + kTileBytes, blk * 32, t_lo);
+        tma::load_2d(&tmM, &full_bar[st], base + kTileBytes + kVBytesPad, blk * 32, t_lo + 1);     // m_{t+1}
+        if (PROPER) tma::load_2d(&tmB, &full_bar[st], base + 2 * kTileBytes + kVBytesPad, blk * 32, t_lo + 1);
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) tma::mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmM) : "memory");
+        for (int k = 0; k < S; ++k) issue(k);
+    }
+    __syncthreads();
+
+    for (int k = 0;; ++k) {
+        const int item = blockIdx.x + k * gridDim.x;
+        if (item >= items) break;
+        const int seg = item / nblk, blk = item - seg * nblk;
+        const int n = blk * 32 + lane;
+        const bool live = n < N;
+        const float nv = live ? __ldg(a.next_value + n) : 0.f;
+        const int t_hi = T - seg * kTSeg;
+        const int t_lo = t_hi - kTSeg;
+        if (seg == 0 && w == 0 && live) {
+            if (GAE) a.value_preds[(size_t)T * N + n] = nv;
+            else     a.returns[(size_t)T * N + n] = nv;
+        }
+        // ---- look-back first: it does not need this item's data (which is still landing)
+        {
+            const int per = (seg + kTW - 1) / kTW;
+            const int s_begin = min(seg, w * per), s_end = min(seg, s_begin + per);
+            float Pw = 1.f, Qw = 0.f;
+            for (int s = s_begin; s < s_end; ++s) {
+                float Pm, Qm;
+                wait_map(a.seg_pq + (((size_t)blk * nseg + s) * 32 + lane) * 2, epoch, Pm, Qm);
+                Qw = Pm * Qw + Qm;
+                Pw = Pm * Pw;
+            }
+            lP[w][lane] = Pw;
+            lQ[w][lane] = Qw;
+        }
+        // ---- this warp's 16 steps from the landed tiles
+        const int st = k % S;
+        tma::mbar_wait(&full_bar[st], (uint32_t)(k / S) & 1u);
+        const float* tR = reinterpret_cast<const float*>(smem + (size_t)st * kStageBytes);
+        const float* tV = tR + kTileRows * 32;
+        const float* tM = tV + kVRowsPad * 32;
+        const float* tB = tM + kTileRows * 32;
+        const int r0 = kTSeg - (w + 1) * kSteps;          // first local row of this warp's chunk
+        const int t0 = t_lo + r0;
+        float f0[kSteps], f1[kSteps], f2[kSteps], f3[kSteps];
+        float P = 1.f, Q = 0.f;
+        {
+            float r_[kSteps], v_[kSteps + 1], m_[kSteps], b_[kSteps];
+#pragma unroll
+            for (int i = 0; i < kSteps; ++i) {
+                r_[i] = tR[(r0 + i) * 32 + lane];
+                m_[i] = tM[(r0 + i) * 32 + lane];
+                if (PROPER) b_[i] = tB[(r0 + i) * 32 + lane];
+                if (GAE || PROPER) v_[i] = tV[(r0 + i) * 32 + lane];
+            }
+            if (GAE) v_[kSteps] = (t0 + kSteps >= T) ? nv : tV[(r0 + kSteps) * 32 + lane];
+#pragma unroll
+            for (int i = kSteps - 1; i >= 0; --i) {
+                const bool in = (t0 + i) >= 0;
+                if (GAE) {
+                    const float delta = (r_[i] + (a.g * v_[i + 1]) * m_[i]) - v_[i];
+                    const float coef = a.gl * m_[i];
+                    f0[i] = delta; f1[i] = coef; f2[i] = v_[i];
+                    if (PROPER) f3[i] = b_[i];
+                    if (in) {
+                        Q = delta + coef * Q;
+                        P = coef * P;
+                        if (PROPER) { Q = Q * b_[i]; P = P * b_[i]; }
+                    }
+                } else {
+                    f0[i] = r_[i]; f1[i] = m_[i];
+                    if (PROPER) { f2[i] = v_[i]; f3[i] = b_[i]; }
+                    if (in) {
+                        Q = (Q * a.g) * m_[i] + r_[i];
+                        P = (P * a.g) * m_[i];
+                        if (PROPER) { Q = Q * b_[i] + (1.f - b_[i]) * v_[i]; P = P * b_[i]; }
+                    }
+                }
+            }
+        }
+        sP[w][lane] = P;
+        sQ[w][lane] = Q;
+        __syncthreads();       // every warp has copied its rows out of the stage; sP/sQ/lP/lQ are complete
+        if (threadIdx.x == 0) issue(k + S);                // refill this ring slot
+        if (w == 0 && seg + 1 < nseg) {
+            float Ps = 1.f, Qs = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < kTW; ++ww) {
+                Qs = sP[ww][lane] * Qs + sQ[ww][lane];
+                Ps = sP[ww][lane] * Ps;
+            }
+            publish(a.seg_pq + (((size_t)blk * nseg + seg) * 32 + lane) * 2, Ps, Qs, epoch);
+        }
+        float x = GAE ? 0.f : nv;
+#pragma unroll
+        for (int ww = 0; ww < kTW; ++ww) x = lP[ww][lane] * x + lQ[ww][lane];
+        for (int ww = 0; ww < w; ++ww) x = sP[ww][lane] * x + sQ[ww][lane];
+        replay_and_store<GAE, PROPER, false>(a.returns, N, n, t0, a.g, live, f0, f1, f2, f3, x);
+        __syncthreads();       // sP/sQ/lP/lQ are free for the next item
+    }
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(&a.hdr->done, 1u);
+        if (prev == gridDim.x - 1) {
+            a.hdr->done = 0;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned*>(&a.hdr->epoch) = epoch;
+        }
+    }
+}
+
 struct Plan { int nblk, nseg; size_t total; };
-Plan plan(int T, int N) {
+Plan plan(int T, int N, int warps) {
     Plan p;
+    const int kSeg = kSteps * warps;
     p.nblk = (N + 31) / 32;
     p.nseg = (T + kSeg - 1) / kSeg;
     p.total = kHeaderBytes + (size_t)p.nblk * p.nseg * 32 * 2 * sizeof(uint2);
@@ -245,8 +410,28 @@ Plan plan(int T, int N) {
 
 extern "C" size_t ppd_compute_returns_workspace(int T, int N) {
     if (T <= 0 || N <= 0) return 0;
-    return plan(T, N).total;
+    return plan(T, N, 4).total;          // the smallest segment size needs the most carry slots
 }
+
+extern "C" void ppd_compute_returns_set_tuning(int warps, int min_blocks) {
+    if (warps == 4 || warps == 8 || warps == 16) g_warps = warps;
+    if (min_blocks == 3 || min_blocks == 4) g_min_blocks = min_blocks;
+    if (warps >= 100) g_tma_mode = warps - 100;      // 100 = never TMA, 101 = auto, 102 = always
+}
+
+namespace {
+template <bool GAE, bool PROPER>
+int launch_tma(const CUtensorMap& mR, const CUtensorMap& mV, const CUtensorMap& mM, const CUtensorMap& mB, const TmaArgs& a,
+               int grid, cudaStream_t s) {
+    constexpr size_t tile = kTileRows * 32 * 4, vpad = kVRowsPad * 32 * 4;
+    constexpr size_t stage = tile + vpad + tile + (PROPER ? tile : 0);
+    const size_t smem = (size_t)a.stages * stage + 128;
+    cudaError_t e = cudaFuncSetAttribute(returns_scan_tma_kernel<GAE, PROPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ppd::set_error("ppd_compute_returns: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
+    returns_scan_tma_kernel<GAE, PROPER><<<grid, kTW * 32, smem, s>>>(mR, mV, mM, mB, a);
+    return ppd::launch_status("returns_scan_tma_kernel");
+}
+}  // namespace
 
 extern "C" int ppd_compute_returns(const float* rewards, float* value_preds, const float* masks,
                                    const float* bad_masks, float* returns, const float* next_value,
@@ -256,7 +441,7 @@ extern "C" int ppd_compute_returns(const float* rewards, float* value_preds, con
     PPD_REQUIRE(rewards && value_preds && masks && returns && next_value && workspace, "null pointer");
     PPD_REQUIRE(!use_proper_time_limits || bad_masks, "bad_masks required with use_proper_time_limits");
     PPD_REQUIRE(T > 0 && N > 0, "T and N must be positive");
-    const Plan p = plan(T, N);
+    const Plan p = plan(T, N, g_warps);
     if (workspace_bytes < p.total) {
         ppd::set_error("ppd_compute_returns: workspace too small");
         return PPD_EWORKSPACE;
@@ -269,12 +454,40 @@ extern "C" int ppd_compute_returns(const float* rewards, float* value_preds, con
     char* ws = reinterpret_cast<char*>(workspace);
     Header* hdr = reinterpret_cast<Header*>(ws);
     uint2* pq = reinterpret_cast<uint2*>(ws + kHeaderBytes);
-    dim3 grid((unsigned)(p.nblk * p.nseg)), block(kWarps * 32);
-#define PPD_LAUNCH(G, P) \
-    returns_scan_kernel<G, P><<<grid, block, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, \
-                                                     T, N, g, gl, p.nblk, p.nseg, hdr, pq)
+    // ---- persistent TMA kernel for large rollouts (row stride must be a multiple of 16 bytes)
+    const bool tma_ok = (N % 4 == 0) && (((uintptr_t)rewards | (uintptr_t)value_preds | (uintptr_t)masks |
+                                           (uintptr_t)(use_proper_time_limits ? bad_masks : masks)) % 16 == 0);
+    if (tma_ok && (g_tma_mode == 2 || (g_tma_mode == 1 && (int64_t)T * N >= (1 << 20)))) {
+        const Plan pt = plan(T, N, kTW);
+        CUtensorMap mR, mV, mM, mB;
+        const float* bm = use_proper_time_limits ? bad_masks : masks;
+        if (ppd::tma::make_map_2d(&mR, rewards, T, N, N, 32, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+            ppd::tma::make_map_2d(&mV, value_preds, T + 1, N, N, 32, kVRows, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+            ppd::tma::make_map_2d(&mM, masks, T + 1, N, N, 32, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+            ppd::tma::make_map_2d(&mB, bm, T + 1, N, N, 32, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE)) {
+            TmaArgs a{value_preds, returns, next_value, T, N, g, gl, pt.nblk, pt.nseg, hdr, pq, use_proper_time_limits ? 3 : 4};
+            int grid_t = pt.nblk * pt.nseg;
+            if (grid_t > ppd::kNumSMs) grid_t = ppd::kNumSMs;
+            if (use_gae) return use_proper_time_limits ? launch_tma<true, true>(mR, mV, mM, mB, a, grid_t, s)
+                                                       : launch_tma<true, false>(mR, mV, mM, mB, a, grid_t, s);
+            return use_proper_time_limits ? launch_tma<false, true>(mR, mV, mM, mB, a, grid_t, s)
+                                          : launch_tma<false, false>(mR, mV, mM, mB, a, grid_t, s);
+        }
+    }
+    dim3 grid((unsigned)(p.nblk * p.nseg)), block(g_warps * 32);
+#define PPD_LAUNCH2(G, P, W, MB) \
+    returns_scan_kernel<G, P, W, MB><<<grid, block, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, \
+                                                            T, N, g, gl, p.nblk, p.nseg, hdr, pq)
+#define PPD_LAUNCH(G, P)                                          \
+    do {                                                          \
+        if (g_warps == 4) PPD_LAUNCH2(G, P, 4, 6);                \
+        else if (g_warps == 16) PPD_LAUNCH2(G, P, 16, 1);         \
+        else if (g_min_blocks == 4) PPD_LAUNCH2(G, P, 8, 4);      \
+        else PPD_LAUNCH2(G, P, 8, 3);                             \
+    } while (0)
     if (use_gae) { if (use_proper_time_limits) PPD_LAUNCH(true, true); else PPD_LAUNCH(true, false); }
     else         { if (use_proper_time_limits) PPD_LAUNCH(false, true); else PPD_LAUNCH(false, false); }
 #undef PPD_LAUNCH
+#undef PPD_LAUNCH2
     return ppd::launch_status("ppd_compute_returns");
 }

@@ -84,6 +84,29 @@ def test_returns_vs_oracle_shapes(T, N, use_gae, proper):
         assert np.array_equal(ret.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("T,N", [(16, 32), (130, 36), (300, 72), (512, 32), (1000, 256), (2048, 128)])
+@pytest.mark.parametrize("use_gae,proper", [(True, False), (True, True), (False, True), (False, False)])
+def test_returns_persistent_tma_kernel(T, N, use_gae, proper):
+    """Force the persistent TMA variant (auto-selected only for >= 1M steps) on small shapes, ragged in T and N."""
+    L = _lib.lib()
+    L.ppd_compute_returns_set_tuning(102, 3)
+    try:
+        gen = torch.Generator().manual_seed(T * 7 + N)
+        f = synthetic.scalar_fields(gen, T, N, 4, reset_prob=0.02, bad_prob=0.01 if proper else 0.0)
+        want, want_v = o_ret.returns_recurrence(f["rewards"].numpy(), f["value_preds"].numpy(), f["masks"].numpy(),
+                                                f["bad_masks"].numpy(), f["next_value"].numpy(), use_gae, 0.99, 0.95, proper)
+        d = {k: f[k].to(DEV).contiguous() for k in ("rewards", "value_preds", "masks", "bad_masks", "next_value")}
+        ret = torch.zeros(T + 1, N, 1, device=DEV)
+        for _ in range(2):      # twice: the workspace re-arms itself between launches
+            _lib.check(L.ppd_compute_returns(d["rewards"].data_ptr(), d["value_preds"].data_ptr(), d["masks"].data_ptr(),
+                                             d["bad_masks"].data_ptr(), ret.data_ptr(), d["next_value"].data_ptr(), T, N,
+                                             0.99, 0.95, int(use_gae), int(proper), *_ws(T, N), _lib.stream_ptr()))
+        np.testing.assert_allclose(ret.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+        assert np.array_equal(d["value_preds"].cpu().numpy(), want_v)
+    finally:
+        L.ppd_compute_returns_set_tuning(101, 3)
+
+
 def test_returns_edge_masks():
     """all-ones, zero at t=1, zero at t=T, every env zero on the same step, a full zero column."""
     T, N = 64, 40
