@@ -139,6 +139,9 @@ int ppd_categorical_eval(const float* z, int ldz, int A, const int64_t* actions,
  * read once per update instead of three .item() syncs per minibatch, ppo.py:86-88).
  */
 size_t ppd_clip_adam_workspace(int64_t n);
+/* 1 (default): parameter sets of up to 4 Mi floats run as ONE cooperative launch (norm -> grid barrier ->
+ * Adam, gradient re-read from L2); 0: always the three-kernel path. */
+void ppd_clip_adam_set_fused(int fused);
 int ppd_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                        int64_t n, int64_t step, double lr, double beta1, double beta2, double eps,
                        double max_norm, float* grad_norm_out, const float* loss_in, float* loss_acc,

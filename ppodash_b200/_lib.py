@@ -73,6 +73,7 @@ _PROTOTYPES = {
                                      c_float, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "ppd_categorical_eval": (c_int, [_P, c_int, c_int, _P, c_int64, _P, _P, _P, _P, _P]),
     "ppd_clip_adam_workspace": (c_size_t, [c_int64]),
+    "ppd_clip_adam_set_fused": (None, [c_int]),
     "ppd_clip_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_double, c_double, c_double, c_double,
                                    c_double, _P, _P, _P, _P, c_size_t, _P]),
     "ppd_obs_rms_update_normalize": (c_int, [_P, c_int, c_int64, _P, _P, c_double, c_int, c_double, c_double,

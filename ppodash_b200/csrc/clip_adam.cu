@@ -4,7 +4,11 @@
 //   pass 1  per-block sum of squares (fp32 per thread, fp64 across the block)       reads g
 //   pass 2  fixed-order reduction of the partials -> total_norm, clip coefficient (1 CTA)
 //   pass 3  Adam: reads g, p, m, v; writes p, m, v                                   28 B/param
+#include <cooperative_groups.h>
+
 #include "ppd_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -99,11 +103,76 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
 }
 
-size_t ws_bytes(int64_t n) { return 256 + (size_t)norm_blocks(n) * sizeof(double); }
+// Single cooperative launch for parameter sets that fit in L2 (the policy has 2.5 M parameters = 10 MB per
+// array): pass 1 (sum of squares) -> grid barrier -> every CTA folds the per-CTA partials in the same fixed
+// order -> clip coefficient -> Adam.  One launch instead of three; the gradient is re-read from L2.
+__global__ void __launch_bounds__(kThreads)
+clip_adam_fused_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       int64_t n, double* __restrict__ partial, Scalars* __restrict__ sc, float max_norm,
+                       float* __restrict__ grad_norm_out, const float* __restrict__ loss_in, float* __restrict__ loss_acc,
+                       AdamConst c) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double scratch[32];
+    __shared__ float s_coef;
+    const int64_t nvec = n / kVec;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float acc = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * kThreads) {
+        const float4 x = __ldg(g4 + i);
+        acc += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = nvec * kVec + threadIdx.x; i < n; i += kThreads) acc += g[i] * g[i];
+    double s = ppd::block_sum((double)acc, scratch);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    grid.sync();
+    s = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) s += __ldcg(partial + i);
+    s = ppd::block_sum(s, scratch);
+    if (threadIdx.x == 0) {
+        const float total = (float)sqrt(s);
+        float coef = 1.f;
+        if (max_norm > 0.f) coef = fminf(__fdiv_rn(max_norm, total + 1e-6f), 1.0f);
+        s_coef = coef;
+        if (blockIdx.x == 0) {
+            sc->clip_coef = coef;
+            sc->total_norm = total;
+            if (grad_norm_out) *grad_norm_out = total;
+            if (loss_in && loss_acc) {
+                loss_acc[0] += loss_in[0];
+                loss_acc[1] += loss_in[1];
+                loss_acc[2] += loss_in[2];
+            }
+        }
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * kThreads) {
+        float4 pp = p4[i], mm = m4[i], vv = v4[i];
+        const float4 gg = __ldg(g4 + i);
+        adam_one(pp.x, gg.x, mm.x, vv.x, coef, c);
+        adam_one(pp.y, gg.y, mm.y, vv.y, coef, c);
+        adam_one(pp.z, gg.z, mm.z, vv.z, coef, c);
+        adam_one(pp.w, gg.w, mm.w, vv.w, coef, c);
+        p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = nvec * kVec + threadIdx.x; i < n; i += kThreads) adam_one(p[i], g[i], m[i], v[i], coef, c);
+}
+
+constexpr int64_t kFusedMaxParams = 4 << 20;     // 4 arrays x 16 MB stay L2-resident
+int g_fused = 1;
+
+size_t ws_bytes(int64_t n) { (void)n; return 256 + (size_t)kMaxBlocks * sizeof(double); }
 
 }  // namespace
 
 extern "C" size_t ppd_clip_adam_workspace(int64_t n) { return ws_bytes(n > 0 ? n : 1); }
+
+extern "C" void ppd_clip_adam_set_fused(int fused) { g_fused = fused; }
 
 extern "C" int ppd_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                   int64_t n, int64_t step, double lr, double beta1, double beta2, double eps,
@@ -120,13 +189,6 @@ extern "C" int ppd_clip_adam_step(float* params, const float* grads, float* exp_
     cudaStream_t s = ppd::as_stream(stream);
     Scalars* sc = reinterpret_cast<Scalars*>(workspace);
     double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
-    const int nb = norm_blocks(n);
-    sqnorm_partial<<<nb, kThreads, 0, s>>>(grads, n, partial);
-    int rc = ppd::launch_status("sqnorm_partial");
-    if (rc) return rc;
-    norm_final<<<1, kThreads, 0, s>>>(partial, nb, (float)max_norm, sc, grad_norm_out, loss_in, loss_acc);
-    rc = ppd::launch_status("norm_final");
-    if (rc) return rc;
     // scalar prefactors in double, as torch's python-side Adam does (_single_tensor_adam)
     const double bc1 = 1.0 - pow(beta1, (double)step);
     const double bc2 = 1.0 - pow(beta2, (double)step);
@@ -137,6 +199,37 @@ extern "C" int ppd_clip_adam_step(float* params, const float* grads, float* exp_
     c.neg_step_size = (float)(-(lr / bc1));
     c.bc2_sqrt = (float)sqrt(bc2);
     c.eps = (float)eps;
+    float mn = (float)max_norm;
+    if (g_fused && n <= kFusedMaxParams) {
+        static int capacity = 0;
+        if (!capacity) {
+            int per_sm = 0, dev = 0, sms = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clip_adam_fused_kernel, kThreads, 0) == cudaSuccess)
+                capacity = per_sm * sms;
+            cudaGetLastError();
+        }
+        int64_t want = (n / kVec + kThreads - 1) / kThreads;
+        int grid = (int)(want < 1 ? 1 : want);
+        int cap = capacity < 4 * ppd::kNumSMs ? capacity : 4 * ppd::kNumSMs;
+        if (cap > kMaxBlocks) cap = kMaxBlocks;
+        if (grid > cap) grid = cap;
+        if (grid >= 1) {
+            void* kargs[] = {&params, &grads, &exp_avg, &exp_avg_sq, &n, &partial, &sc, &mn,
+                             &grad_norm_out, &loss_in, &loss_acc, &c};
+            cudaError_t e = cudaLaunchCooperativeKernel((void*)clip_adam_fused_kernel, dim3(grid), dim3(kThreads), kargs, 0, s);
+            if (e == cudaSuccess) return ppd::launch_status("clip_adam_fused_kernel");
+            cudaGetLastError();        // fall through to the three-kernel path
+        }
+    }
+    const int nb = norm_blocks(n);
+    sqnorm_partial<<<nb, kThreads, 0, s>>>(grads, n, partial);
+    int rc = ppd::launch_status("sqnorm_partial");
+    if (rc) return rc;
+    norm_final<<<1, kThreads, 0, s>>>(partial, nb, mn, sc, grad_norm_out, loss_in, loss_acc);
+    rc = ppd::launch_status("norm_final");
+    if (rc) return rc;
     int64_t blocks = (n / kVec + kThreads - 1) / kThreads;
     if (blocks < 1) blocks = 1;
     if (blocks > 8 * ppd::kNumSMs) blocks = 8 * ppd::kNumSMs;

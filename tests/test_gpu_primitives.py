@@ -374,8 +374,17 @@ def test_categorical_eval():
 
 
 # --------------------------------------------------------------------------- clip + Adam
+@pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("n,max_norm", [(1000, 0.5), (2464393, 0.5), (4097, 1e9), (33, 0.0)])
-def test_clip_adam_vs_torch(n, max_norm):
+def test_clip_adam_vs_torch(n, max_norm, fused):
+    _lib.lib().ppd_clip_adam_set_fused(fused)
+    try:
+        _clip_adam_case(n, max_norm)
+    finally:
+        _lib.lib().ppd_clip_adam_set_fused(1)
+
+
+def _clip_adam_case(n, max_norm):
     g = torch.Generator().manual_seed(n)
     p0 = torch.randn(n, generator=g) * 0.05
     ref_p = p0.clone().requires_grad_(True)
