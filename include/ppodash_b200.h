@@ -49,7 +49,9 @@ void ppd_reset_launch_count(void);
  * gamma*gae_lambda is formed in double and rounded once, as Python does in the reference.
  */
 size_t ppd_compute_returns_workspace(int T, int N);
-/* Tuning: warps per CTA (4, 8 or 16; 16 steps each) and, for 8 warps, resident CTAs per SM (3 or 4). */
+/* Tuning: warps per CTA (4, 8 or 16; 16 steps each) and, for 8 warps, resident CTAs per SM (3 or 4).
+ * warps = 100 / 101 / 102 selects never / auto / always for the persistent TMA-staged variant (default never:
+ * it measured slower than the register kernel); warps = 200 + 10*S + C sets its ring depth S and CTAs/SM C. */
 void ppd_compute_returns_set_tuning(int warps, int min_blocks);
 int ppd_compute_returns(const float* rewards, float* value_preds, const float* masks,
                         const float* bad_masks, float* returns, const float* next_value,

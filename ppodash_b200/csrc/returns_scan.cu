@@ -31,7 +31,12 @@ constexpr int kSteps = 16;                // steps per warp chunk (held in regis
 constexpr int kHeaderBytes = 128;
 int g_warps = 8;                          // warps per CTA: 4, 8 or 16 (ppd_compute_returns_set_tuning)
 int g_min_blocks = 3;                     // __launch_bounds__ min blocks per SM for the 8-warp variant: 3 or 4
-int g_tma_mode = 1;                       // 1 = auto (persistent TMA kernel for large rollouts), 0 = never, 2 = always
+// The persistent TMA variant is kept selectable but is NOT the default: measured on B200 at 4096 x 2048 it
+// reaches 40 us (2 CTAs/SM, 2-deep ring) against 36.9 us for the register kernel below -- per-item latency
+// (look-back + dependent fold + replay), not memory-level parallelism, is what bounds both.
+int g_tma_mode = 0;                       // 0 = never (default), 1 = auto for >= 1M steps, 2 = always
+int g_tma_stages = 2;                     // ring depth per CTA
+int g_tma_ctas = 2;                       // persistent CTAs per SM
 
 // Workspace header.  The workspace must be zero-filled once when it is allocated; every launch
 // leaves it ready for the next one (the last CTA to finish bumps the epoch that tags published maps),
@@ -254,7 +259,7 @@ struct TmaArgs {
 };
 
 template <bool GAE, bool PROPER>
-__global__ void __launch_bounds__(kTW * 32, 1)
+__global__ void __launch_bounds__(kTW * 32, 2)
 returns_scan_tma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmB, const TmaArgs a) {
     namespace tma = ppd::tma;
@@ -294,13 +299,25 @@ returns_scan_tma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_co
     }
     __syncthreads();
 
+    float nv_next = 0.f;
+    if ((int)blockIdx.x < items) {
+        const int n0 = ((int)blockIdx.x % nblk) * 32 + lane;
+        nv_next = (n0 < N) ? __ldg(a.next_value + n0) : 0.f;
+    }
     for (int k = 0;; ++k) {
         const int item = blockIdx.x + k * gridDim.x;
         if (item >= items) break;
         const int seg = item / nblk, blk = item - seg * nblk;
         const int n = blk * 32 + lane;
         const bool live = n < N;
-        const float nv = live ? __ldg(a.next_value + n) : 0.f;
+        const float nv = nv_next;
+        {   // next item's bootstrap value: its latency hides behind this item
+            const int item2 = item + gridDim.x;
+            if (item2 < items) {
+                const int n2 = (item2 % nblk) * 32 + lane;
+                nv_next = (n2 < N) ? __ldg(a.next_value + n2) : 0.f;
+            }
+        }
         const int t_hi = T - seg * kTSeg;
         const int t_lo = t_hi - kTSeg;
         if (seg == 0 && w == 0 && live) {
@@ -416,7 +433,8 @@ extern "C" size_t ppd_compute_returns_workspace(int T, int N) {
 extern "C" void ppd_compute_returns_set_tuning(int warps, int min_blocks) {
     if (warps == 4 || warps == 8 || warps == 16) g_warps = warps;
     if (min_blocks == 3 || min_blocks == 4) g_min_blocks = min_blocks;
-    if (warps >= 100) g_tma_mode = warps - 100;      // 100 = never TMA, 101 = auto, 102 = always
+    if (warps >= 100 && warps < 200) g_tma_mode = warps - 100;      // 100 = never TMA, 101 = auto, 102 = always
+    if (warps >= 200) { g_tma_stages = (warps - 200) / 10; g_tma_ctas = (warps - 200) % 10; }   // 2SC: stages S, CTAs/SM C
 }
 
 namespace {
@@ -465,9 +483,15 @@ extern "C" int ppd_compute_returns(const float* rewards, float* value_preds, con
             ppd::tma::make_map_2d(&mV, value_preds, T + 1, N, N, 32, kVRows, CU_TENSOR_MAP_SWIZZLE_NONE) &&
             ppd::tma::make_map_2d(&mM, masks, T + 1, N, N, 32, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE) &&
             ppd::tma::make_map_2d(&mB, bm, T + 1, N, N, 32, kTileRows, CU_TENSOR_MAP_SWIZZLE_NONE)) {
-            TmaArgs a{value_preds, returns, next_value, T, N, g, gl, pt.nblk, pt.nseg, hdr, pq, use_proper_time_limits ? 3 : 4};
+            const size_t tile = kTileRows * 32 * 4, vpad = kVRowsPad * 32 * 4;
+            const size_t stage = tile + vpad + tile + (use_proper_time_limits ? tile : 0);
+            int ctas = g_tma_ctas < 1 ? 1 : (g_tma_ctas > 2 ? 2 : g_tma_ctas);
+            int stages = g_tma_stages < 1 ? 1 : (g_tma_stages > kMaxTmaStages ? kMaxTmaStages : g_tma_stages);
+            while (stages > 1 && (size_t)ctas * (stages * stage + 2048) > 226 * 1024) --stages;
+            while (ctas > 1 && (size_t)ctas * (stages * stage + 2048) > 226 * 1024) --ctas;
+            TmaArgs a{value_preds, returns, next_value, T, N, g, gl, pt.nblk, pt.nseg, hdr, pq, stages};
             int grid_t = pt.nblk * pt.nseg;
-            if (grid_t > ppd::kNumSMs) grid_t = ppd::kNumSMs;
+            if (grid_t > ctas * ppd::kNumSMs) grid_t = ctas * ppd::kNumSMs;
             if (use_gae) return use_proper_time_limits ? launch_tma<true, true>(mR, mV, mM, mB, a, grid_t, s)
                                                        : launch_tma<true, false>(mR, mV, mM, mB, a, grid_t, s);
             return use_proper_time_limits ? launch_tma<false, true>(mR, mV, mM, mB, a, grid_t, s)

@@ -115,8 +115,9 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else "all"
     res = []
     if os.environ.get("PPD_RET_TUNE"):
-        w, mb = (int(x) for x in os.environ["PPD_RET_TUNE"].split(","))
-        _lib.lib().ppd_compute_returns_set_tuning(w, mb)
+        for part in os.environ["PPD_RET_TUNE"].split(";"):
+            w, mb = (int(x) for x in part.split(","))
+            _lib.lib().ppd_compute_returns_set_tuning(w, mb)
     if only in ("all", "returns"):
         for T, N in ((512, 32), (512, 1024), (2048, 4096)):
             res.append(bench_gae(T, N))
