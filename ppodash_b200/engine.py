@@ -85,6 +85,8 @@ class PolicyEngine:
         self.flat = None
         self._buffers = {}
         self._cols_valid = False
+        self.overlap_wgrad = True         # weight-gradient GEMMs / bias sums on a second stream, concurrent with the dgrad chain
+        self._side = None
 
     # ------------------------------------------------------------------ parameters
     PRECISIONS = ("fp32", "tf32x3", "tf32")
@@ -185,6 +187,47 @@ class PolicyEngine:
         buf = self.flat_grad if grad else self.flat
         return buf[s.off:s.off + s.numel]
 
+    # ------------------------------------------------------------------ streams
+    @property
+    def stream(self):
+        """cudaStream_t of torch's current stream on this device (kernels are enqueued where torch ops go)."""
+        return _lib.stream_ptr(self.device)
+
+    def _ws(self, nbytes, tag):
+        # one scratch buffer per (kind, stream): GEMMs running concurrently on two streams must not share split-K partials
+        return _lib.workspace(nbytes, self.device, f"{tag}@{self.stream}")
+
+    class _Side:
+        """Context manager: run the enclosed launches on the side stream after everything enqueued so far on the
+        main stream (fork); PolicyEngine._join() makes the main stream wait for the side stream."""
+
+        def __init__(self, eng):
+            self.eng = eng
+
+        def __enter__(self):
+            eng = self.eng
+            if not eng.overlap_wgrad:
+                return self
+            if eng._side is None:
+                eng._side = torch.cuda.Stream(device=eng.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(eng.device))
+            eng._side.wait_event(ev)
+            self.ctx = torch.cuda.stream(eng._side)
+            self.ctx.__enter__()
+            return self
+
+        def __exit__(self, *exc):
+            if self.eng.overlap_wgrad:
+                self.ctx.__exit__(*exc)
+            return False
+
+    def _join(self):
+        if self.overlap_wgrad and self._side is not None:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
     # ------------------------------------------------------------------ scratch
     def buf(self, name, *shape, dtype=torch.float32):
         n = 1
@@ -216,10 +259,10 @@ class PolicyEngine:
                 g.A, g.lda, g.B, g.ldb = g.B, g.ldb, g.A, g.lda
                 g.I, g.J = J, I
                 flags |= 1
-            ws = _lib.workspace(L.ppd_tc_gemm_workspace(g.I, g.J, KK), self.device, "tcgemm")
+            ws = self._ws(L.ppd_tc_gemm_workspace(g.I, g.J, KK), "tcgemm")
             check(L.ppd_tc_gemm(ctypes.byref(g), flags, ws.data_ptr(), ws.numel(), self.stream), "tc_gemm")
             return
-        ws = _lib.workspace(L.ppd_sgemm_workspace(I, J, KK), self.device, "gemm")
+        ws = self._ws(L.ppd_sgemm_workspace(I, J, KK), "gemm")
         check(L.ppd_sgemm(ctypes.byref(g), ws.data_ptr(), ws.numel(), self.stream), "sgemm")
 
     def _dgrad_col2im(self, dY, N, W, K, n, Hin, Cin, k, stride, act, dx):
@@ -248,7 +291,7 @@ class PolicyEngine:
 
     def _colsum(self, X, ld, I, J, out, acc=0):
         L = lib()
-        ws = _lib.workspace(L.ppd_colsum_workspace(I, J), self.device, "colsum")
+        ws = self._ws(L.ppd_colsum_workspace(I, J), "colsum")
         check(L.ppd_colsum(X.data_ptr(), ld, I, J, out.data_ptr(), acc, ws.data_ptr(), ws.numel(), self.stream), "colsum")
 
     # ------------------------------------------------------------------ trunk
@@ -291,18 +334,18 @@ class PolicyEngine:
         C, H, hw = self.C, self.H, self.hw
         s1, s2, s3 = self.sp
         K1, K2, K3 = C * 64, 512, 576
-        st = self.stream
         a1 = self.buf("a1", B, s1 * s1 * 32)
         a2 = self.buf("a2", B, s2 * s2 * 64)
         a3t = self.buf("a3t", B, self.flat_dim)
         fd = self.flat_dim
-        # FC
-        self._gemm(dfeat, ldd, 0, a3t, fd, 0, self.seg("fc.w", True), fd, H, fd, B)
-        self._colsum(dfeat, ldd, B, H, self.seg("fc.b", True))
+        # FC: weight / bias gradients go to the side stream, the dgrad chain stays on the main stream
+        with self._Side(self):
+            self._gemm(dfeat, ldd, 0, a3t, fd, 0, self.seg("fc.w", True), fd, H, fd, B)
+            self._colsum(dfeat, ldd, B, H, self.seg("fc.b", True))
         da3t = self.buf("da3t", B, fd)
         self._gemm(dfeat, ldd, 1, self.seg("fc.w"), fd, 0, da3t, fd, B, fd, H, mask=a3t, ldm=fd)
         dy3 = self.buf("dy3", B, s3 * s3 * 32)                   # NHWC = [B*49, 32]
-        check(L.ppd_batched_transpose(da3t.data_ptr(), B, 32, s3 * s3, dy3.data_ptr(), st), "transpose")
+        check(L.ppd_batched_transpose(da3t.data_ptr(), B, 32, s3 * s3, dy3.data_ptr(), self.stream), "transpose")
         ch = min(self.chunk_rows, B)
         cols1 = self.buf("cols1", ch * s1 * s1, K1)
         cols2 = self.buf("cols2", ch * s2 * s2, K2)
@@ -315,30 +358,34 @@ class PolicyEngine:
             n = min(ch, B - r0)
             acc = 0 if first else 1
             M3, M2, M1 = n * s3 * s3, n * s2 * s2, n * s1 * s1
+            if not first:
+                self._join()          # the side stream still reads dy2 / dy1 / cols* of the previous chunk
             # conv3
             if not self._cols_valid:
-                check(L.ppd_im2col_nhwc(a2[r0:].data_ptr(), n, s2, s2, 64, 3, 3, 1, cols3.data_ptr(), K3, st), "im2col3")
-            self._gemm(dy3[r0:], 32, 0, cols3, K3, 0, self.seg("conv3.w", True), K3, 32, K3, M3, acc=acc)
-            self._colsum(dy3[r0:], 32, M3, 32, self.seg("conv3.b", True), acc)
+                check(L.ppd_im2col_nhwc(a2[r0:].data_ptr(), n, s2, s2, 64, 3, 3, 1, cols3.data_ptr(), K3, self.stream), "im2col3")
+            with self._Side(self):
+                self._gemm(dy3[r0:], 32, 0, cols3, K3, 0, self.seg("conv3.w", True), K3, 32, K3, M3, acc=acc)
+                self._colsum(dy3[r0:], 32, M3, 32, self.seg("conv3.b", True), acc)
             self._dgrad_col2im(dy3[r0:], 32, w3, K3, n, s2, 64, 3, 1, a2[r0:], dy2)
             # conv2
             if not self._cols_valid:
-                check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, cols2.data_ptr(), K2, st), "im2col2")
-            self._gemm(dy2, 64, 0, cols2, K2, 0, self.seg("conv2.w", True), K2, 64, K2, M2, acc=acc)
-            self._colsum(dy2, 64, M2, 64, self.seg("conv2.b", True), acc)
+                check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, cols2.data_ptr(), K2, self.stream), "im2col2")
+            with self._Side(self):
+                self._gemm(dy2, 64, 0, cols2, K2, 0, self.seg("conv2.w", True), K2, 64, K2, M2, acc=acc)
+                self._colsum(dy2, 64, M2, 64, self.seg("conv2.b", True), acc)
             self._dgrad_col2im(dy2, 64, w2, K2, n, s1, 32, 4, 2, a1[r0:], dy1)
             # conv1 (no input gradient needed)
             if not self._cols_valid:
-                check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, cols1.data_ptr(), K1, st), "im2col1")
+                check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, cols1.data_ptr(), K1, self.stream), "im2col1")
             self._gemm(dy1, 32, 0, cols1, K1, 0, self.seg("conv1.w", True), K1, 32, K1, M1, acc=acc)
             self._colsum(dy1, 32, M1, 32, self.seg("conv1.b", True), acc)
             first = False
+        self._join()
 
     # ------------------------------------------------------------------ forward
     def _prep(self, visual, vector, rnn_hxs, masks):
         self.bind()
         dev = self.device
-        self.stream = _lib.stream_ptr(dev)
         obs = visual.to(device=dev, dtype=torch.float32).contiguous()
         B = obs.shape[0]
         if tuple(obs.shape[1:]) != (self.C, self.hw, self.hw):
@@ -421,10 +468,11 @@ class PolicyEngine:
                                      float(clip_param), float(value_coef), float(entropy_coef),
                                      int(bool(use_clipped_value_loss)), dz.data_ptr(), None, None, loss_out.data_ptr(),
                                      ws.data_ptr(), ws.numel(), st), "ppo_loss")
-        # ---- heads backward
+        # ---- heads backward (weight / bias gradients on the side stream)
         feats = sv["hs"] if self.recurrent else sv["feat"]
-        self._gemm(dz, A + 1, 0, feats, H, 0, self.seg("heads.w", True), H, A + 1, H, B)
-        self._colsum(dz, A + 1, B, A + 1, self.seg("heads.b", True))
+        with self._Side(self):
+            self._gemm(dz, A + 1, 0, feats, H, 0, self.seg("heads.w", True), H, A + 1, H, B)
+            self._colsum(dz, A + 1, B, A + 1, self.seg("heads.b", True))
         if self.recurrent:
             T, E, Ipad = sv["T"], sv["E"], self.Ipad
             dhs = self.buf("t_dhs", B, H)
@@ -435,19 +483,20 @@ class PolicyEngine:
             w_hh = self.seg("gru.w_hh")
             check(L.ppd_gru_backward(dhs.data_ptr(), sv["m"].data_ptr(), w_hh.data_ptr(), sv["h0"].data_ptr(),
                                      sv["hs"].data_ptr(), s0.data_ptr(), s1.data_ptr(), s2.data_ptr(), s3.data_ptr(),
-                                     T, E, H, dgi.data_ptr(), dghn.data_ptr(), None, st), "gru_backward")
-            hm = self.buf("t_hm", B, H)
-            check(L.ppd_gru_masked_prev(sv["hs"].data_ptr(), sv["h0"].data_ptr(), sv["m"].data_ptr(), T, E, H,
-                                        hm.data_ptr(), st), "masked_prev")
+                                     T, E, H, dgi.data_ptr(), dghn.data_ptr(), None, self.stream), "gru_backward")
             xcat = sv["xcat"]
-            gw_hh = self.seg("gru.w_hh", True)
-            self._gemm(dgi, 3 * H, 0, xcat, Ipad, 0, self.seg("gru.w_ih", True), Ipad, 3 * H, Ipad, B)
-            self._colsum(dgi, 3 * H, B, 3 * H, self.seg("gru.b_ih", True))
-            self._gemm(dgi, 3 * H, 0, hm, H, 0, gw_hh, H, 2 * H, H, B)                    # r, z rows of dW_hh
-            self._gemm(dghn, H, 0, hm, H, 0, gw_hh[2 * H * H:], H, H, H, B)                # n rows
-            gb_hh = self.seg("gru.b_hh", True)
-            gb_hh[:2 * H].copy_(self.seg("gru.b_ih", True)[:2 * H])                      # same sums for r, z
-            self._colsum(dghn, H, B, H, gb_hh[2 * H:])
+            with self._Side(self):
+                hm = self.buf("t_hm", B, H)
+                check(L.ppd_gru_masked_prev(sv["hs"].data_ptr(), sv["h0"].data_ptr(), sv["m"].data_ptr(), T, E, H,
+                                            hm.data_ptr(), self.stream), "masked_prev")
+                gw_hh = self.seg("gru.w_hh", True)
+                self._gemm(dgi, 3 * H, 0, xcat, Ipad, 0, self.seg("gru.w_ih", True), Ipad, 3 * H, Ipad, B)
+                self._colsum(dgi, 3 * H, B, 3 * H, self.seg("gru.b_ih", True))
+                self._gemm(dgi, 3 * H, 0, hm, H, 0, gw_hh, H, 2 * H, H, B)                    # r, z rows of dW_hh
+                self._gemm(dghn, H, 0, hm, H, 0, gw_hh[2 * H * H:], H, H, H, B)                # n rows
+                gb_hh = self.seg("gru.b_hh", True)
+                gb_hh[:2 * H].copy_(self.seg("gru.b_ih", True)[:2 * H])                      # same sums for r, z
+                self._colsum(dghn, H, B, H, gb_hh[2 * H:])
             # d(feat) = dgi W_ih[:, :H], masked by feat > 0 (ReLU of the FC layer)
             dfeat = self.buf("t_dfeat", B, H)
             self._gemm(dgi, 3 * H, 1, self.seg("gru.w_ih"), Ipad, 0, dfeat, H, B, H, 3 * H, mask=xcat, ldm=Ipad)
