@@ -64,6 +64,41 @@ im2col_nhwc_kernel(const float* __restrict__ x, int B, int H, int W, int C, int 
     }
 }
 
+// Row-structured im2col: blockIdx.x = (b, oy) output row, threadIdx.x = float4 index inside a patch (so the patch
+// decomposition is done once per thread, no divisions in the loop), threadIdx.y strides over ox.  For one ox the
+// threads of a row write one contiguous patch (K*4 bytes) -> coalesced 16-byte stores; 32-bit index arithmetic.
+__global__ void __launch_bounds__(256)
+im2col_nchw_rows_kernel(const float* __restrict__ x, int C, int H, int W, int kh, int kw, int stride,
+                        int OH, int OW, float* __restrict__ cols, int64_t ld) {
+    const int k = threadIdx.x << 2;                       // first of 4 consecutive taps (same c, ky)
+    const int kx = k % kw, ky = (k / kw) % kh, c = k / (kw * kh);
+    const int b = blockIdx.x / OH, oy = blockIdx.x - b * OH;
+    const float* src = x + (((size_t)b * C + c) * H + (oy * stride + ky)) * (size_t)W + kx;
+    float* dst = cols + ((size_t)blockIdx.x * OW) * ld + k;
+    for (int ox = threadIdx.y; ox < OW; ox += blockDim.y) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + ox * stride));
+        __stcs(reinterpret_cast<float4*>(dst + (size_t)ox * ld), v);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+im2col_nhwc_rows_kernel(const float* __restrict__ x, int H, int W, int C, int kh, int kw, int stride,
+                        int OH, int OW, float* __restrict__ cols, int64_t ld) {
+    const int seg = kw * C;                               // contiguous floats per (pixel, ky)
+    const int K4 = (kh * seg) >> 2;
+    const int b = blockIdx.x / OH, oy = blockIdx.x - b * OH;
+    for (int k4 = threadIdx.x; k4 < K4; k4 += blockDim.x) {
+        const int k = k4 << 2;
+        const int ky = k / seg, r = k - ky * seg;
+        const float* src = x + (((size_t)b * H + (oy * stride + ky)) * W) * (size_t)C + r;
+        float* dst = cols + ((size_t)blockIdx.x * OW) * ld + k;
+        for (int ox = threadIdx.y; ox < OW; ox += blockDim.y) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)ox * stride * C));
+            __stcs(reinterpret_cast<float4*>(dst + (size_t)ox * ld), v);
+        }
+    }
+}
+
 // dx[b,y,x,c] = sum over patches containing the pixel of dcols[(b,oy,ox), (ky,kx,c)], times (act > 0).
 __global__ void __launch_bounds__(kThreads)
 col2im_nhwc_kernel(const float* __restrict__ dcols, int64_t ld, int B, int H, int W, int C, int kh, int kw,
@@ -149,6 +184,15 @@ extern "C" int ppd_im2col_nchw(const float* x, int B, int C, int H, int W, int k
     const int OH = (H - kh) / stride + 1, OW = (W - kw) / stride + 1;
     const int vec = (kw % 4 == 0) && (stride % 4 == 0) && (W % 4 == 0) && ((uintptr_t)x % 16 == 0);
     const int64_t total = (int64_t)B * OH * OW * (K / 4);
+    if (vec && K / 4 <= 256 && (int64_t)B * OH <= 0x7fffffffLL) {
+        const int tx = K / 4;
+        int ty = 256 / tx;
+        if (ty > OW) ty = OW;
+        if (ty < 1) ty = 1;
+        im2col_nchw_rows_kernel<<<(unsigned)(B * OH), dim3(tx, ty), 0, ppd::as_stream(stream)>>>(x, C, H, W, kh, kw, stride,
+                                                                                                 OH, OW, cols, ld);
+        return ppd::launch_status("im2col_nchw_rows_kernel");
+    }
     im2col_nchw_kernel<<<grid_for(total), kThreads, 0, ppd::as_stream(stream)>>>(x, B, C, H, W, kh, kw, stride, OH, OW,
                                                                                cols, ld, vec);
     return ppd::launch_status("im2col_nchw_kernel");
@@ -162,6 +206,16 @@ extern "C" int ppd_im2col_nhwc(const float* x, int B, int H, int W, int C, int k
     PPD_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)cols % 16 == 0, "buffers must be 16-byte aligned");
     const int OH = (H - kh) / stride + 1, OW = (W - kw) / stride + 1;
     const int64_t total = (int64_t)B * OH * OW * (kh * kw * C / 4);
+    if ((int64_t)B * OH <= 0x7fffffffLL) {
+        const int K4 = kh * kw * C / 4;
+        const int tx = K4 < 128 ? K4 : 128;
+        int ty = 256 / tx;
+        if (ty > OW) ty = OW;
+        if (ty < 1) ty = 1;
+        im2col_nhwc_rows_kernel<<<(unsigned)(B * OH), dim3(tx, ty), 0, ppd::as_stream(stream)>>>(x, H, W, C, kh, kw, stride,
+                                                                                                 OH, OW, cols, ld);
+        return ppd::launch_status("im2col_nhwc_rows_kernel");
+    }
     im2col_nhwc_kernel<<<grid_for(total), kThreads, 0, ppd::as_stream(stream)>>>(x, B, H, W, C, kh, kw, stride, OH, OW,
                                                                                cols, ld);
     return ppd::launch_status("im2col_nhwc_kernel");
