@@ -84,9 +84,12 @@ class PolicyEngine:
         self.device = None
         self.flat = None
         self._buffers = {}
-        self._cols_valid = False
         self.overlap_wgrad = True         # weight-gradient GEMMs / bias sums on a second stream, concurrent with the dgrad chain
+        self.overlap_gru = True           # GRU time chunks on their own stream, concurrent with the trunk of other chunks
+        self.time_chunks = 4
+        self.cols_budget = 6 << 30        # bytes of im2col matrices kept from forward for backward
         self._side = None
+        self._gru_stream = None
 
     # ------------------------------------------------------------------ parameters
     PRECISIONS = ("fp32", "tf32x3", "tf32")
@@ -180,7 +183,6 @@ class PolicyEngine:
         if old_state is None or old_state["exp_avg"].numel() != total or old_state["exp_avg"].device != dev:
             self.adam_state = dict(exp_avg=torch.zeros(total, device=dev), exp_avg_sq=torch.zeros(total, device=dev), step=0)
         self._buffers = {}
-        self._cols_valid = False
 
     def seg(self, name, grad=False):
         s = self.segs[name]
@@ -294,93 +296,104 @@ class PolicyEngine:
         ws = self._ws(L.ppd_colsum_workspace(I, J), "colsum")
         check(L.ppd_colsum(X.data_ptr(), ld, I, J, out.data_ptr(), acc, ws.data_ptr(), ws.numel(), self.stream), "colsum")
 
+    # ------------------------------------------------------------------ row chunks
+    def _chunks(self, B, E=None):
+        """Row ranges [r0, r1) processed one after the other.  Recurrent minibatches are cut along TIME (rows are
+        time-major), so that the GRU of one time chunk runs on its own stream concurrently with the conv trunk
+        of the next one (forward) / the previous one (backward); every chunk is also at most chunk_rows rows so
+        that the im2col scratch stays bounded."""
+        if E:
+            T = B // E
+            nc = self.time_chunks if (self.overlap_gru and T >= 8 * self.time_chunks) else 1
+            nc = max(nc, -(-B // self.chunk_rows))
+            nc = min(nc, T)
+            tl = -(-T // nc)
+            return [(t0 * E, min(T, t0 + tl) * E) for t0 in range(0, T, tl)]
+        ch = min(self.chunk_rows, B)
+        return [(r0, min(B, r0 + ch)) for r0 in range(0, B, ch)]
+
+    def _cols(self, B, chunks, keep):
+        """im2col scratch.  If the matrices of the whole minibatch fit the budget they are kept for backward
+        (row offset = chunk start); otherwise one chunk-sized set is reused and backward recomputes them."""
+        C = self.C
+        s1, s2, s3 = self.sp
+        K1, K2, K3 = C * 64, 512, 576
+        per_row = 4 * (s1 * s1 * K1 + s2 * s2 * K2 + s3 * s3 * K3)
+        full = keep and B * per_row <= self.cols_budget
+        rows = B if full else max(r1 - r0 for r0, r1 in chunks)
+        return (self.buf("cols1", rows * s1 * s1, K1), self.buf("cols2", rows * s2 * s2, K2),
+                self.buf("cols3", rows * s3 * s3, K3), full)
+
     # ------------------------------------------------------------------ trunk
-    def _trunk_forward(self, obs, B, feat, ldf, keep):
-        """obs [B,C,hw,hw] -> feat[:, :H] (row stride ldf) = ReLU(FC(flatten(conv stack))).
-        keep=True stores the activations needed by backward."""
+    def _trunk_forward_rows(self, obs, r0, r1, cols, off, feat, ldf):
+        """rows [r0, r1): obs -> conv stack -> flatten -> feat[r0:r1, :H] = ReLU(FC(.)) (model.py:176-180,194)."""
         L = lib()
         C, H, hw = self.C, self.H, self.hw
         s1, s2, s3 = self.sp
         K1, K2, K3 = C * 64, 512, 576
+        n = r1 - r0
+        B = obs.shape[0]
         a1 = self.buf("a1", B, s1 * s1 * 32)
         a2 = self.buf("a2", B, s2 * s2 * 64)
         a3 = self.buf("a3", B, s3 * s3 * 32)
         a3t = self.buf("a3t", B, self.flat_dim)
-        ch = min(self.chunk_rows, B)
-        cols1 = self.buf("cols1", ch * s1 * s1, K1)
-        cols2 = self.buf("cols2", ch * s2 * s2, K2)
-        cols3 = self.buf("cols3", ch * s3 * s3, K3)
+        c1, c2, c3 = cols[0][off * s1 * s1:], cols[1][off * s2 * s2:], cols[2][off * s3 * s3:]
         st = self.stream
-        w1, b1 = self.seg("conv1.w"), self.seg("conv1.b")
-        w2, b2 = self.seg("conv2.w"), self.seg("conv2.b")
-        w3, b3 = self.seg("conv3.w"), self.seg("conv3.b")
-        for r0 in range(0, B, ch):
-            n = min(ch, B - r0)
-            check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, cols1.data_ptr(), K1, st), "im2col1")
-            self._gemm(cols1, K1, 1, w1, K1, 1, a1[r0:], 32, n * s1 * s1, 32, K1, bias=b1, relu=1)
-            check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, cols2.data_ptr(), K2, st), "im2col2")
-            self._gemm(cols2, K2, 1, w2, K2, 1, a2[r0:], 64, n * s2 * s2, 64, K2, bias=b2, relu=1)
-            check(L.ppd_im2col_nhwc(a2[r0:].data_ptr(), n, s2, s2, 64, 3, 3, 1, cols3.data_ptr(), K3, st), "im2col3")
-            self._gemm(cols3, K3, 1, w3, K3, 1, a3[r0:], 32, n * s3 * s3, 32, K3, bias=b3, relu=1)
-        self._cols_valid = keep and ch >= B      # single chunk: backward can reuse the im2col matrices
-        check(L.ppd_batched_transpose(a3.data_ptr(), B, s3 * s3, 32, a3t.data_ptr(), st), "transpose")
-        self._gemm(a3t, self.flat_dim, 1, self.seg("fc.w"), self.flat_dim, 1, feat, ldf, B, H, self.flat_dim,
+        check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, c1.data_ptr(), K1, st), "im2col1")
+        self._gemm(c1, K1, 1, self.seg("conv1.w"), K1, 1, a1[r0:], 32, n * s1 * s1, 32, K1, bias=self.seg("conv1.b"), relu=1)
+        check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, c2.data_ptr(), K2, st), "im2col2")
+        self._gemm(c2, K2, 1, self.seg("conv2.w"), K2, 1, a2[r0:], 64, n * s2 * s2, 64, K2, bias=self.seg("conv2.b"), relu=1)
+        check(L.ppd_im2col_nhwc(a2[r0:].data_ptr(), n, s2, s2, 64, 3, 3, 1, c3.data_ptr(), K3, st), "im2col3")
+        self._gemm(c3, K3, 1, self.seg("conv3.w"), K3, 1, a3[r0:], 32, n * s3 * s3, 32, K3, bias=self.seg("conv3.b"), relu=1)
+        check(L.ppd_batched_transpose(a3[r0:].data_ptr(), n, s3 * s3, 32, a3t[r0:].data_ptr(), st), "transpose")
+        self._gemm(a3t[r0:], self.flat_dim, 1, self.seg("fc.w"), self.flat_dim, 1, feat[r0:], ldf, n, H, self.flat_dim,
                    bias=self.seg("fc.b"), relu=1)
 
-    def _trunk_backward(self, obs, B, dfeat, ldd):
-        """dfeat [B, H] (row stride ldd; already masked by feat > 0) -> conv/FC gradients (accumulated
-        into the zeroed flat gradient buffer)."""
+    def _trunk_backward_rows(self, obs, r0, r1, cols, off, cols_valid, dfeat, ldd):
+        """rows [r0, r1): dfeat (already masked by feat > 0) -> FC / conv gradients, ADDED to the flat gradient buffer
+        (zeroed at the start of the minibatch).  Weight / bias gradients run on the side stream."""
         L = lib()
         C, H, hw = self.C, self.H, self.hw
         s1, s2, s3 = self.sp
         K1, K2, K3 = C * 64, 512, 576
+        n = r1 - r0
+        B = obs.shape[0]
+        fd = self.flat_dim
         a1 = self.buf("a1", B, s1 * s1 * 32)
         a2 = self.buf("a2", B, s2 * s2 * 64)
-        a3t = self.buf("a3t", B, self.flat_dim)
-        fd = self.flat_dim
-        # FC: weight / bias gradients go to the side stream, the dgrad chain stays on the main stream
-        with self._Side(self):
-            self._gemm(dfeat, ldd, 0, a3t, fd, 0, self.seg("fc.w", True), fd, H, fd, B)
-            self._colsum(dfeat, ldd, B, H, self.seg("fc.b", True))
+        a3t = self.buf("a3t", B, fd)
         da3t = self.buf("da3t", B, fd)
-        self._gemm(dfeat, ldd, 1, self.seg("fc.w"), fd, 0, da3t, fd, B, fd, H, mask=a3t, ldm=fd)
         dy3 = self.buf("dy3", B, s3 * s3 * 32)                   # NHWC = [B*49, 32]
-        check(L.ppd_batched_transpose(da3t.data_ptr(), B, 32, s3 * s3, dy3.data_ptr(), self.stream), "transpose")
-        ch = min(self.chunk_rows, B)
-        cols1 = self.buf("cols1", ch * s1 * s1, K1)
-        cols2 = self.buf("cols2", ch * s2 * s2, K2)
-        cols3 = self.buf("cols3", ch * s3 * s3, K3)
-        dy2 = self.buf("dy2", ch, s2 * s2 * 64)
-        dy1 = self.buf("dy1", ch, s1 * s1 * 32)
-        w2, w3 = self.seg("conv2.w"), self.seg("conv3.w")
-        first = True
-        for r0 in range(0, B, ch):
-            n = min(ch, B - r0)
-            acc = 0 if first else 1
-            M3, M2, M1 = n * s3 * s3, n * s2 * s2, n * s1 * s1
-            if not first:
-                self._join()          # the side stream still reads dy2 / dy1 / cols* of the previous chunk
-            # conv3
-            if not self._cols_valid:
-                check(L.ppd_im2col_nhwc(a2[r0:].data_ptr(), n, s2, s2, 64, 3, 3, 1, cols3.data_ptr(), K3, self.stream), "im2col3")
-            with self._Side(self):
-                self._gemm(dy3[r0:], 32, 0, cols3, K3, 0, self.seg("conv3.w", True), K3, 32, K3, M3, acc=acc)
-                self._colsum(dy3[r0:], 32, M3, 32, self.seg("conv3.b", True), acc)
-            self._dgrad_col2im(dy3[r0:], 32, w3, K3, n, s2, 64, 3, 1, a2[r0:], dy2)
-            # conv2
-            if not self._cols_valid:
-                check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, cols2.data_ptr(), K2, self.stream), "im2col2")
-            with self._Side(self):
-                self._gemm(dy2, 64, 0, cols2, K2, 0, self.seg("conv2.w", True), K2, 64, K2, M2, acc=acc)
-                self._colsum(dy2, 64, M2, 64, self.seg("conv2.b", True), acc)
-            self._dgrad_col2im(dy2, 64, w2, K2, n, s1, 32, 4, 2, a1[r0:], dy1)
-            # conv1 (no input gradient needed)
-            if not self._cols_valid:
-                check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, cols1.data_ptr(), K1, self.stream), "im2col1")
-            self._gemm(dy1, 32, 0, cols1, K1, 0, self.seg("conv1.w", True), K1, 32, K1, M1, acc=acc)
-            self._colsum(dy1, 32, M1, 32, self.seg("conv1.b", True), acc)
-            first = False
-        self._join()
+        dy2 = self.buf("dy2", B, s2 * s2 * 64)
+        dy1 = self.buf("dy1", B, s1 * s1 * 32)
+        c1, c2, c3 = cols[0][off * s1 * s1:], cols[1][off * s2 * s2:], cols[2][off * s3 * s3:]
+        M3, M2, M1 = n * s3 * s3, n * s2 * s2, n * s1 * s1
+        with self._Side(self):
+            self._gemm(dfeat[r0:], ldd, 0, a3t[r0:], fd, 0, self.seg("fc.w", True), fd, H, fd, n, acc=1)
+            self._colsum(dfeat[r0:], ldd, n, H, self.seg("fc.b", True), 1)
+        self._gemm(dfeat[r0:], ldd, 1, self.seg("fc.w"), fd, 0, da3t[r0:], fd, n, fd, H, mask=a3t[r0:], ldm=fd)
+        check(L.ppd_batched_transpose(da3t[r0:].data_ptr(), n, 32, s3 * s3, dy3[r0:].data_ptr(), self.stream), "transpose")
+        # conv3
+        if not cols_valid:
+            check(L.ppd_im2col_nhwc(a2[r0:].data_ptr(), n, s2, s2, 64, 3, 3, 1, c3.data_ptr(), K3, self.stream), "im2col3")
+        with self._Side(self):
+            self._gemm(dy3[r0:], 32, 0, c3, K3, 0, self.seg("conv3.w", True), K3, 32, K3, M3, acc=1)
+            self._colsum(dy3[r0:], 32, M3, 32, self.seg("conv3.b", True), 1)
+        self._dgrad_col2im(dy3[r0:], 32, self.seg("conv3.w"), K3, n, s2, 64, 3, 1, a2[r0:], dy2[r0:])
+        # conv2
+        if not cols_valid:
+            check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, c2.data_ptr(), K2, self.stream), "im2col2")
+        with self._Side(self):
+            self._gemm(dy2[r0:], 64, 0, c2, K2, 0, self.seg("conv2.w", True), K2, 64, K2, M2, acc=1)
+            self._colsum(dy2[r0:], 64, M2, 64, self.seg("conv2.b", True), 1)
+        self._dgrad_col2im(dy2[r0:], 64, self.seg("conv2.w"), K2, n, s1, 32, 4, 2, a1[r0:], dy1[r0:])
+        # conv1 (no input gradient needed)
+        if not cols_valid:
+            check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, c1.data_ptr(), K1, self.stream), "im2col1")
+        self._gemm(dy1[r0:], 32, 0, c1, K1, 0, self.seg("conv1.w", True), K1, 32, K1, M1, acc=1)
+        self._colsum(dy1[r0:], 32, M1, 32, self.seg("conv1.b", True), 1)
+        if not cols_valid:
+            self._join()              # the side stream still reads the chunk-sized im2col scratch
 
     # ------------------------------------------------------------------ forward
     def _prep(self, visual, vector, rnn_hxs, masks):
@@ -397,47 +410,77 @@ class PolicyEngine:
         m = masks.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
         return obs, vobs, h0, m, B
 
+    def _gru_stream_ctx(self, nchunks):
+        """Stream the GRU chunks run on: a dedicated stream when the minibatch is cut along time, else the current one."""
+        if nchunks > 1 and self.overlap_gru:
+            if self._gru_stream is None:
+                self._gru_stream = torch.cuda.Stream(device=self.device)
+            return self._gru_stream
+        return None
+
     def forward(self, visual, vector, rnn_hxs, masks, keep=False, xcat_prefilled=None):
         """CNNBase.forward + both heads (model.py:192-199, distributions.py:66-68).
         Returns dict(value [B,1], z [B,A+1] (logits | value), rnn_hxs, feats)."""
         obs, vobs, h0, m, B = self._prep(visual, vector, rnn_hxs, masks)
         L = lib()
         H, A = self.H, self.A
-        st = self.stream
         tag = "t_" if keep else "i_"
         z = self.buf(tag + "z", B, A + 1) if keep else torch.empty(B, A + 1, device=self.device)
+        main = torch.cuda.current_stream(self.device)
         if self.recurrent:
             E = h0.shape[0]
             if B % E != 0:
                 raise ValueError("rows must be a multiple of the number of hidden-state rows (T*E, E)")
             T = B // E
             Ipad = self.Ipad
+            chunks = self._chunks(B, E)
+            cols = self._cols(B, chunks, keep)
             xcat = xcat_prefilled if xcat_prefilled is not None else self.buf(tag + "xcat", B, Ipad)
-            if xcat_prefilled is None:
-                if Ipad != H:
-                    xcat[:, H:].zero_()
-                    if self.V:
-                        xcat[:, H:H + self.V].copy_(vobs)           # torch.cat((x, vector), 1), model.py:195
-            self._trunk_forward(obs, B, xcat, Ipad, keep)
+            if xcat_prefilled is None and Ipad != H:
+                xcat[:, H:].zero_()
+                if self.V:
+                    xcat[:, H:H + self.V].copy_(vobs)               # torch.cat((x, vector), 1), model.py:195
             gi = self.buf(tag + "gi", B, 3 * H)
-            self._gemm(xcat, Ipad, 1, self.seg("gru.w_ih"), Ipad, 1, gi, 3 * H, B, 3 * H, Ipad, bias=self.seg("gru.b_ih"))
             hs = self.buf(tag + "hs", B, H) if keep else torch.empty(B, H, device=self.device)
             hl = torch.empty(E, H, device=self.device)
-            if keep:
-                sv = [self.buf("t_s%d" % i, B, H) for i in range(4)]
-                svp = [s.data_ptr() for s in sv]
-            else:
-                svp = [None] * 4
-            check(L.ppd_gru_forward(gi.data_ptr(), h0.data_ptr(), m.data_ptr(), self.seg("gru.w_hh").data_ptr(),
-                                    self.seg("gru.b_hh").data_ptr(), T, E, H, hs.data_ptr(), hl.data_ptr(), *svp, st),
-                  "gru_forward")
+            sv = [self.buf("t_s%d" % i, B, H) for i in range(4)] if keep else None
+            gstream = self._gru_stream_ctx(len(chunks))
+            w_hh, b_hh = self.seg("gru.w_hh"), self.seg("gru.b_hh")
+            for ci, (r0, r1) in enumerate(chunks):
+                n = r1 - r0
+                self._trunk_forward_rows(obs, r0, r1, cols, r0 if cols[3] else 0, xcat, Ipad)
+                self._gemm(xcat[r0:], Ipad, 1, self.seg("gru.w_ih"), Ipad, 1, gi[r0:], 3 * H, n, 3 * H, Ipad,
+                           bias=self.seg("gru.b_ih"))
+                last = ci == len(chunks) - 1
+                h_in = h0 if ci == 0 else hs[r0 - E:r0]
+                svp = [s_[r0:].data_ptr() for s_ in sv] if keep else [None] * 4
+
+                def run_gru():
+                    check(L.ppd_gru_forward(gi[r0:].data_ptr(), h_in.data_ptr(), m[r0:].data_ptr(), w_hh.data_ptr(),
+                                            b_hh.data_ptr(), n // E, E, H, hs[r0:].data_ptr(),
+                                            hl.data_ptr() if last else None, *svp, self.stream), "gru_forward")
+                if gstream is None:
+                    run_gru()
+                else:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    gstream.wait_event(ev)
+                    with torch.cuda.stream(gstream):
+                        run_gru()
+            if gstream is not None:
+                ev = torch.cuda.Event()
+                ev.record(gstream)
+                main.wait_event(ev)
             feats, ldf, rnn_out = hs, H, hl
-            self._saved = dict(obs=obs, xcat=xcat, gi=gi, hs=hs, h0=h0, m=m, T=T, E=E, B=B) if keep else None
+            self._saved = dict(obs=obs, xcat=xcat, gi=gi, hs=hs, h0=h0, m=m, T=T, E=E, B=B, chunks=chunks, cols=cols) if keep else None
         else:
+            chunks = self._chunks(B)
+            cols = self._cols(B, chunks, keep)
             feat = self.buf(tag + "feat", B, H) if keep else torch.empty(B, H, device=self.device)
-            self._trunk_forward(obs, B, feat, H, keep)
+            for r0, r1 in chunks:
+                self._trunk_forward_rows(obs, r0, r1, cols, r0 if cols[3] else 0, feat, H)
             feats, ldf, rnn_out = feat, H, rnn_hxs
-            self._saved = dict(obs=obs, feat=feat, B=B) if keep else None
+            self._saved = dict(obs=obs, feat=feat, B=B, chunks=chunks, cols=cols) if keep else None
         self._gemm(feats, ldf, 1, self.seg("heads.w"), H, 1, z, A + 1, B, A + 1, H, bias=self.seg("heads.b"))
         if keep:
             self._saved["z"] = z
@@ -448,14 +491,14 @@ class PolicyEngine:
                         global_rows=None, xcat_prefilled=None):
         """Forward, fused PPO loss forward+backward, full backward for one minibatch
         (PKG/algo/ppo.py:57-81).  Leaves d(loss)/d(params) in the flat gradient buffer and the three
-        loss partial sums at its tail; nothing is synchronised."""
+        loss partial sums at its tail; nothing is synchronised with the host."""
         obs, vobs, h0, actions, old_v, ret, masks, old_logp, adv = sample
         out = self.forward(obs, vobs, h0, masks, keep=True, xcat_prefilled=xcat_prefilled)
         L = lib()
         sv = self._saved
         B, H, A = sv["B"], self.H, self.A
-        st = self.stream
         dev = self.device
+        main = torch.cuda.current_stream(dev)
         z = sv["z"]
         dz = self.buf("t_dz", B, A + 1)
         self.flat_grad.zero_()                                              # optimizer.zero_grad(), ppo.py:79
@@ -467,27 +510,58 @@ class PolicyEngine:
                                      f32(old_v).data_ptr(), f32(ret).data_ptr(), B, int(global_rows or B),
                                      float(clip_param), float(value_coef), float(entropy_coef),
                                      int(bool(use_clipped_value_loss)), dz.data_ptr(), None, None, loss_out.data_ptr(),
-                                     ws.data_ptr(), ws.numel(), st), "ppo_loss")
+                                     ws.data_ptr(), ws.numel(), self.stream), "ppo_loss")
         # ---- heads backward (weight / bias gradients on the side stream)
         feats = sv["hs"] if self.recurrent else sv["feat"]
         with self._Side(self):
             self._gemm(dz, A + 1, 0, feats, H, 0, self.seg("heads.w", True), H, A + 1, H, B)
             self._colsum(dz, A + 1, B, A + 1, self.seg("heads.b", True))
+        chunks, cols = sv["chunks"], sv["cols"]
+        dfeat = self.buf("t_dfeat", B, H)
         if self.recurrent:
             T, E, Ipad = sv["T"], sv["E"], self.Ipad
             dhs = self.buf("t_dhs", B, H)
             self._gemm(dz, A + 1, 1, self.seg("heads.w"), H, 0, dhs, H, B, H, A + 1)
             dgi = self.buf("t_dgi", B, 3 * H)
             dghn = self.buf("t_dghn", B, H)
-            s0, s1, s2, s3 = (self.buf("t_s%d" % i, B, H) for i in range(4))
-            w_hh = self.seg("gru.w_hh")
-            check(L.ppd_gru_backward(dhs.data_ptr(), sv["m"].data_ptr(), w_hh.data_ptr(), sv["h0"].data_ptr(),
-                                     sv["hs"].data_ptr(), s0.data_ptr(), s1.data_ptr(), s2.data_ptr(), s3.data_ptr(),
-                                     T, E, H, dgi.data_ptr(), dghn.data_ptr(), None, self.stream), "gru_backward")
-            xcat = sv["xcat"]
+            saves = [self.buf("t_s%d" % i, B, H) for i in range(4)]
+            dh0 = self.buf("t_dh0", E, H)
+            w_hh, w_ih = self.seg("gru.w_hh"), self.seg("gru.w_ih")
+            xcat, hs, m = sv["xcat"], sv["hs"], sv["m"]
+            gstream = self._gru_stream_ctx(len(chunks))
+            if gstream is not None:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                gstream.wait_event(ev)
+            # BPTT runs over the time chunks from the last to the first on the GRU stream; as soon as a chunk's dgi is
+            # there, the main stream back-propagates that chunk through the FC / conv trunk while the GRU continues
+            for ci in range(len(chunks) - 1, -1, -1):
+                r0, r1 = chunks[ci]
+                n = r1 - r0
+                h_in = sv["h0"] if ci == 0 else hs[r0 - E:r0]
+
+                def run_gru():
+                    if ci != len(chunks) - 1:
+                        dhs[r1 - E:r1].add_(dh0)                      # gradient flowing back from the next chunk
+                    check(L.ppd_gru_backward(dhs[r0:].data_ptr(), m[r0:].data_ptr(), w_hh.data_ptr(), h_in.data_ptr(),
+                                             hs[r0:].data_ptr(), *[s_[r0:].data_ptr() for s_ in saves], n // E, E, H,
+                                             dgi[r0:].data_ptr(), dghn[r0:].data_ptr(), dh0.data_ptr() if ci > 0 else None,
+                                             self.stream), "gru_backward")
+                if gstream is None:
+                    run_gru()
+                else:
+                    with torch.cuda.stream(gstream):
+                        run_gru()
+                        ev = torch.cuda.Event()
+                        ev.record(gstream)
+                    main.wait_event(ev)
+                # d(feat) = dgi W_ih[:, :H], masked by feat > 0 (ReLU of the FC layer)
+                self._gemm(dgi[r0:], 3 * H, 1, w_ih, Ipad, 0, dfeat[r0:], H, n, H, 3 * H, mask=xcat[r0:], ldm=Ipad)
+                self._trunk_backward_rows(sv["obs"], r0, r1, cols, r0 if cols[3] else 0, cols[3], dfeat, H)
+            # ---- GRU parameter gradients over all T*E rows (side stream; dgi complete because main waited for it)
             with self._Side(self):
                 hm = self.buf("t_hm", B, H)
-                check(L.ppd_gru_masked_prev(sv["hs"].data_ptr(), sv["h0"].data_ptr(), sv["m"].data_ptr(), T, E, H,
+                check(L.ppd_gru_masked_prev(hs.data_ptr(), sv["h0"].data_ptr(), m.data_ptr(), T, E, H,
                                             hm.data_ptr(), self.stream), "masked_prev")
                 gw_hh = self.seg("gru.w_hh", True)
                 self._gemm(dgi, 3 * H, 0, xcat, Ipad, 0, self.seg("gru.w_ih", True), Ipad, 3 * H, Ipad, B)
@@ -497,13 +571,11 @@ class PolicyEngine:
                 gb_hh = self.seg("gru.b_hh", True)
                 gb_hh[:2 * H].copy_(self.seg("gru.b_ih", True)[:2 * H])                      # same sums for r, z
                 self._colsum(dghn, H, B, H, gb_hh[2 * H:])
-            # d(feat) = dgi W_ih[:, :H], masked by feat > 0 (ReLU of the FC layer)
-            dfeat = self.buf("t_dfeat", B, H)
-            self._gemm(dgi, 3 * H, 1, self.seg("gru.w_ih"), Ipad, 0, dfeat, H, B, H, 3 * H, mask=xcat, ldm=Ipad)
         else:
-            dfeat = self.buf("t_dfeat", B, H)
             self._gemm(dz, A + 1, 1, self.seg("heads.w"), H, 0, dfeat, H, B, H, A + 1, mask=feats, ldm=H)
-        self._trunk_backward(sv["obs"], B, dfeat, H)
+            for r0, r1 in chunks:
+                self._trunk_backward_rows(sv["obs"], r0, r1, cols, r0 if cols[3] else 0, cols[3], dfeat, H)
+        self._join()
         return out
 
     # ------------------------------------------------------------------ optimiser

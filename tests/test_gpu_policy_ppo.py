@@ -172,13 +172,17 @@ def test_c2_shaped_minibatch_vs_oracle(precision):
                 err = np.abs(got - ref)
                 ok = err <= (1e-4 * np.abs(ref) + 2e-5 * scale)
                 assert ok.mean() >= 0.95 and float(err.max()) <= 5e-4 * scale, (name, ok.mean(), err.max() / scale)
-    # chunked trunk (rows processed 40 at a time) gives the same gradients
+    # the same minibatch cut into time chunks (GRU chunks on their own stream, pipelined against the trunk),
+    # with and without keeping the im2col matrices for backward, gives the same gradients
     g1 = eng.flat_grad.clone()
-    eng.chunk_rows = 40
-    eng.train_minibatch((dd(obs), dd(vobs), dd(h0), dd(actions), dd(old_v), dd(ret), dd(masks), dd(old_logp), dd(adv)),
-                        0.1, 0.5, 0.001)
-    np.testing.assert_allclose(eng.flat_grad.cpu().numpy(), g1.cpu().numpy(), rtol=1e-3 if loose else 1e-4,
-                               atol=1e-5 if loose else 1e-7)
+    sample = (dd(obs), dd(vobs), dd(h0), dd(actions), dd(old_v), dd(ret), dd(masks), dd(old_logp), dd(adv))
+    for chunk_rows, time_chunks, budget in ((40, 4, 6 << 30), (2048, 3, 6 << 30), (32, 4, 0)):
+        eng.chunk_rows, eng.time_chunks, eng.cols_budget = chunk_rows, time_chunks, budget
+        assert len(eng._chunks(B, E)) >= 3
+        eng.train_minibatch(sample, 0.1, 0.5, 0.001)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(eng.flat_grad.cpu().numpy(), g1.cpu().numpy(), rtol=1e-3 if loose else 1e-4,
+                                   atol=1e-5 if loose else 2e-7)
 
 
 def test_state_dict_roundtrip_and_rebind():
