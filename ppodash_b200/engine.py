@@ -85,7 +85,12 @@ class PolicyEngine:
         self.flat = None
         self._buffers = {}
         self.overlap_wgrad = True         # weight-gradient GEMMs / bias sums on a second stream, concurrent with the dgrad chain
-        self.overlap_gru = True           # GRU time chunks on their own stream, concurrent with the trunk of other chunks
+        # GRU time chunks on their own stream, concurrent with the trunk of other chunks.  Off by default: measured on
+        # B200 at the PPO-Dash shape (T=512, E=4) it is SLOWER (265.6 vs 248.6 ms per update): a 16-CTA cluster with the
+        # full register file per CTA cannot be co-scheduled while trunk kernels occupy the SMs, so the chunks serialise
+        # anyway and only pay for smaller GEMMs and repeated W_hh loads.  The chunking itself is what bounds the im2col
+        # scratch for large minibatches (E=128: 65 536 rows).
+        self.overlap_gru = False
         self.time_chunks = 4
         self.cols_budget = 6 << 30        # bytes of im2col matrices kept from forward for backward
         self._side = None
