@@ -189,11 +189,26 @@ def run_b200(args, cfg):
 
     T, N = cfg.num_steps, cfg.num_envs
     Hs = cfg.hidden_size if cfg.recurrent else 1
-    roll = synthetic.make_rollout(cfg, seed=1234 + rank)
-    host = {k: roll[k].pin_memory() for k in ppd.RolloutStorage._FIELDS}
-    nv_host = roll["next_value"].pin_memory()
     st = ppd.RolloutStorage(T, N, (cfg.channels, cfg.obs_hw, cfg.obs_hw), [cfg.vector_obs_len], Discrete(cfg.num_actions), Hs)
-    st.to(dev)
+    obs_bytes = (T + 1) * N * cfg.channels * cfg.obs_hw * cfg.obs_hw * 4
+    big = obs_bytes > (8 << 30)        # e.g. c5 (42.5 GiB per GPU): generate on the device, no host copy, no e2e leg
+    if big:
+        st.obs = torch.empty(0)
+        st.to(dev)
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        st.obs = torch.empty(T + 1, N, cfg.channels, cfg.obs_hw, cfg.obs_hw, device=dev)
+        for t0 in range(0, T + 1, 32):
+            st.obs[t0:t0 + 32].normal_(generator=gen)
+        small = synthetic.make_rollout(cfg, seed=1234 + rank, with_obs=False)
+        for k in ppd.RolloutStorage._FIELDS:
+            if k != "obs":
+                getattr(st, k).copy_(small[k])
+        host, nv_host = {}, small["next_value"].pin_memory()
+    else:
+        roll = synthetic.make_rollout(cfg, seed=1234 + rank)
+        host = {k: roll[k].pin_memory() for k in ppd.RolloutStorage._FIELDS}
+        nv_host = roll["next_value"].pin_memory()
+        st.to(dev)
     torch.manual_seed(0)                      # identical initial weights on every rank
     pol = ppd.Policy((cfg.channels, cfg.obs_hw, cfg.obs_hw), Discrete(cfg.num_actions),
                      base_kwargs={"recurrent": cfg.recurrent, "hidden_size": cfg.hidden_size},
@@ -235,7 +250,10 @@ def run_b200(args, cfg):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), out
 
-    upload()
+    if not big:
+        upload()
+    else:
+        nv_dev.copy_(nv_host)
     for _ in range(args.warmup):
         step(False)
     sampler = ClockSampler(local)
@@ -244,7 +262,7 @@ def run_b200(args, cfg):
     _lib.reset_launch_count()
     ms_total, losses = timed(args.steps, False)
     launches = _lib.launch_count()
-    ms_e2e, _ = timed(args.steps, True)
+    ms_e2e = ms_total if big else timed(args.steps, True)[0]
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- attribute the step to kernels (one extra, untimed-for-the-metric step with per-call CUDA events)
@@ -304,8 +322,11 @@ def run_b200(args, cfg):
                             num_mini_batch=cfg.num_mini_batch, precision=pol.engine().precision,
                             parallelism=f"env-sharded dp{world}",
                             l2="rollout (%.2f GiB) larger than L2; no flush needed" % (h2d_bytes / 2**30)),
-                e2e=dict(value=e2e_value, unit="env-steps/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12,
-                         ms_per_step=ms_e2e / args.steps),
+                e2e=(dict(value=None, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=12,
+                          note="rollout generated on the device (too large for a pinned host copy): no end-to-end leg")
+                     if big else
+                     dict(value=e2e_value, unit="env-steps/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=12,
+                          ms_per_step=ms_e2e / args.steps)),
                 gpu_launches=launches, roofline=roof, clocks=clocks, losses=list(losses),
                 sample_passes_per_sec=value * cfg.ppo_epoch,
                 kernel_ms_per_step={k: round(ms, 3) for ms, k, _ in shares})
@@ -326,7 +347,7 @@ def run_b200(args, cfg):
                        peak=pk["hbm"], unit="GB/s", frac=ad["gbs"] / pk["hbm"], ms=ad["ms"]))
         line["kernels"] = ks
 
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not big:
         line["cpu_baseline"] = cpu_reference(cfg, minibatches=2, warm=1)
     else:
         line["cpu_baseline"] = None

@@ -354,9 +354,9 @@ class PolicyEngine:
         self._gemm(a3t[r0:], self.flat_dim, 1, self.seg("fc.w"), self.flat_dim, 1, feat[r0:], ldf, n, H, self.flat_dim,
                    bias=self.seg("fc.b"), relu=1)
 
-    def _trunk_backward_rows(self, obs, r0, r1, cols, off, cols_valid, dfeat, ldd):
-        """rows [r0, r1): dfeat (already masked by feat > 0) -> FC / conv gradients, ADDED to the flat gradient buffer
-        (zeroed at the start of the minibatch).  Weight / bias gradients run on the side stream."""
+    def _trunk_backward_rows(self, obs, r0, r1, cols, off, cols_valid, dfeat, ldd, acc):
+        """rows [r0, r1): dfeat (already masked by feat > 0) -> FC / conv gradients, written to (acc=0, first chunk) or
+        added to (acc=1) the flat gradient buffer.  Weight / bias gradients run on the side stream."""
         L = lib()
         C, H, hw = self.C, self.H, self.hw
         s1, s2, s3 = self.sp
@@ -374,29 +374,29 @@ class PolicyEngine:
         c1, c2, c3 = cols[0][off * s1 * s1:], cols[1][off * s2 * s2:], cols[2][off * s3 * s3:]
         M3, M2, M1 = n * s3 * s3, n * s2 * s2, n * s1 * s1
         with self._Side(self):
-            self._gemm(dfeat[r0:], ldd, 0, a3t[r0:], fd, 0, self.seg("fc.w", True), fd, H, fd, n, acc=1)
-            self._colsum(dfeat[r0:], ldd, n, H, self.seg("fc.b", True), 1)
+            self._gemm(dfeat[r0:], ldd, 0, a3t[r0:], fd, 0, self.seg("fc.w", True), fd, H, fd, n, acc=acc)
+            self._colsum(dfeat[r0:], ldd, n, H, self.seg("fc.b", True), acc)
         self._gemm(dfeat[r0:], ldd, 1, self.seg("fc.w"), fd, 0, da3t[r0:], fd, n, fd, H, mask=a3t[r0:], ldm=fd)
         check(L.ppd_batched_transpose(da3t[r0:].data_ptr(), n, 32, s3 * s3, dy3[r0:].data_ptr(), self.stream), "transpose")
         # conv3
         if not cols_valid:
             check(L.ppd_im2col_nhwc(a2[r0:].data_ptr(), n, s2, s2, 64, 3, 3, 1, c3.data_ptr(), K3, self.stream), "im2col3")
         with self._Side(self):
-            self._gemm(dy3[r0:], 32, 0, c3, K3, 0, self.seg("conv3.w", True), K3, 32, K3, M3, acc=1)
-            self._colsum(dy3[r0:], 32, M3, 32, self.seg("conv3.b", True), 1)
+            self._gemm(dy3[r0:], 32, 0, c3, K3, 0, self.seg("conv3.w", True), K3, 32, K3, M3, acc=acc)
+            self._colsum(dy3[r0:], 32, M3, 32, self.seg("conv3.b", True), acc)
         self._dgrad_col2im(dy3[r0:], 32, self.seg("conv3.w"), K3, n, s2, 64, 3, 1, a2[r0:], dy2[r0:])
         # conv2
         if not cols_valid:
             check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, c2.data_ptr(), K2, self.stream), "im2col2")
         with self._Side(self):
-            self._gemm(dy2[r0:], 64, 0, c2, K2, 0, self.seg("conv2.w", True), K2, 64, K2, M2, acc=1)
-            self._colsum(dy2[r0:], 64, M2, 64, self.seg("conv2.b", True), 1)
+            self._gemm(dy2[r0:], 64, 0, c2, K2, 0, self.seg("conv2.w", True), K2, 64, K2, M2, acc=acc)
+            self._colsum(dy2[r0:], 64, M2, 64, self.seg("conv2.b", True), acc)
         self._dgrad_col2im(dy2[r0:], 64, self.seg("conv2.w"), K2, n, s1, 32, 4, 2, a1[r0:], dy1[r0:])
         # conv1 (no input gradient needed)
         if not cols_valid:
             check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, c1.data_ptr(), K1, self.stream), "im2col1")
-        self._gemm(dy1[r0:], 32, 0, c1, K1, 0, self.seg("conv1.w", True), K1, 32, K1, M1, acc=1)
-        self._colsum(dy1[r0:], 32, M1, 32, self.seg("conv1.b", True), 1)
+        self._gemm(dy1[r0:], 32, 0, c1, K1, 0, self.seg("conv1.w", True), K1, 32, K1, M1, acc=acc)
+        self._colsum(dy1[r0:], 32, M1, 32, self.seg("conv1.b", True), acc)
         if not cols_valid:
             self._join()              # the side stream still reads the chunk-sized im2col scratch
 
@@ -562,7 +562,8 @@ class PolicyEngine:
                     main.wait_event(ev)
                 # d(feat) = dgi W_ih[:, :H], masked by feat > 0 (ReLU of the FC layer)
                 self._gemm(dgi[r0:], 3 * H, 1, w_ih, Ipad, 0, dfeat[r0:], H, n, H, 3 * H, mask=xcat[r0:], ldm=Ipad)
-                self._trunk_backward_rows(sv["obs"], r0, r1, cols, r0 if cols[3] else 0, cols[3], dfeat, H)
+                self._trunk_backward_rows(sv["obs"], r0, r1, cols, r0 if cols[3] else 0, cols[3], dfeat, H,
+                                          0 if ci == len(chunks) - 1 else 1)
             # ---- GRU parameter gradients over all T*E rows (side stream; dgi complete because main waited for it)
             with self._Side(self):
                 hm = self.buf("t_hm", B, H)
@@ -578,8 +579,8 @@ class PolicyEngine:
                 self._colsum(dghn, H, B, H, gb_hh[2 * H:])
         else:
             self._gemm(dz, A + 1, 1, self.seg("heads.w"), H, 0, dfeat, H, B, H, A + 1, mask=feats, ldm=H)
-            for r0, r1 in chunks:
-                self._trunk_backward_rows(sv["obs"], r0, r1, cols, r0 if cols[3] else 0, cols[3], dfeat, H)
+            for ci, (r0, r1) in enumerate(chunks):
+                self._trunk_backward_rows(sv["obs"], r0, r1, cols, r0 if cols[3] else 0, cols[3], dfeat, H, 0 if ci == 0 else 1)
         self._join()
         return out
 
