@@ -56,6 +56,8 @@ def run(name, I, J, KK, ak, bk, mode):
 if __name__ == "__main__":
     if os.environ.get("PPD_TWO_CTAS") is not None:
         _lib.lib().ppd_tc_gemm_set_option(int(os.environ["PPD_TWO_CTAS"]))
+    if os.environ.get("PPD_BN") is not None:
+        _lib.lib().ppd_tc_gemm_set_option(int(os.environ["PPD_BN"]))
     modes = sys.argv[1:] or ["fp32", "tf32", "tf32x3"]
     tot = {m: 0.0 for m in modes}
     for sh in SHAPES:
