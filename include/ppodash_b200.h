@@ -215,6 +215,10 @@ void ppd_tc_gemm_set_option(int two_ctas);
 size_t ppd_colsum_workspace(int64_t I, int64_t J);
 int ppd_colsum(const float* X, int64_t ld, int64_t I, int64_t J, float* out, int accumulate,
                void* workspace, size_t workspace_bytes, void* stream);
+/* Up to 8 column sums in two launches: all bias gradients of a minibatch at once. */
+typedef struct ppd_colsum_seg { const float* X; int64_t ld, I, J; float* out; int accumulate; } ppd_colsum_seg;
+size_t ppd_colsum_multi_workspace(const ppd_colsum_seg* segs, int n);
+int ppd_colsum_multi(const ppd_colsum_seg* segs, int n, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Convolution lowering (conv = im2col + GEMM; activations NHWC between the convolutions).

@@ -47,6 +47,11 @@ class GemmArgs(Structure):
     ]
 
 
+class ColsumSeg(Structure):
+    """Mirror of ``ppd_colsum_seg``."""
+    _fields_ = [("X", c_void_p), ("ld", c_int64), ("I", c_int64), ("J", c_int64), ("out", c_void_p), ("accumulate", c_int)]
+
+
 class ConvGeom(Structure):
     """Mirror of ``ppd_conv_geom``."""
     _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("C", c_int), ("kh", c_int), ("kw", c_int), ("stride", c_int)]
@@ -88,6 +93,8 @@ _PROTOTYPES = {
     "ppd_relu_mask": (c_int, [_P, _P, c_int64, _P]),
     "ppd_colsum_workspace": (c_size_t, [c_int64, c_int64]),
     "ppd_colsum": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, _P, c_size_t, _P]),
+    "ppd_colsum_multi_workspace": (c_size_t, [POINTER(ColsumSeg), c_int]),
+    "ppd_colsum_multi": (c_int, [POINTER(ColsumSeg), c_int, _P, c_size_t, _P]),
     "ppd_im2col_nchw": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P]),
     "ppd_im2col_nhwc": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P]),
     "ppd_col2im_nhwc": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),

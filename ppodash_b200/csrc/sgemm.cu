@@ -269,6 +269,68 @@ int64_t colsum_parts(int64_t ld, int64_t I, int64_t J) {
     return colsum_narrow(ld, J) ? (I * J + kNarrowElems - 1) / kNarrowElems : (I + kColRows - 1) / kColRows;
 }
 
+// ---- several column sums in two launches (all bias gradients of a minibatch at once)
+constexpr int kMaxSegs = 8;
+struct MultiSegs {
+    const float* X[kMaxSegs]; float* out[kMaxSegs];
+    int64_t ld[kMaxSegs], I[kMaxSegs], J[kMaxSegs], parts[kMaxSegs], part_off[kMaxSegs];   // part_off: floats into the workspace
+    int block_off[kMaxSegs + 1], final_off[kMaxSegs + 1];
+    int narrow[kMaxSegs], accumulate[kMaxSegs], gx[kMaxSegs];
+    int n;
+};
+
+__global__ void __launch_bounds__(kThreads) colsum_multi_partial_kernel(const MultiSegs m, float* __restrict__ ws) {
+    __shared__ float sm[kThreads];
+    int s = 0;
+    while (s + 1 < m.n && (int)blockIdx.x >= m.block_off[s + 1]) ++s;
+    const int lb = blockIdx.x - m.block_off[s];
+    const float* __restrict__ X = m.X[s];
+    const int64_t J = m.J[s];
+    float* partial = ws + m.part_off[s];
+    if (m.narrow[s]) {
+        const int64_t n = m.I[s] * J;
+        const int64_t e0 = (int64_t)lb * kNarrowElems, e1 = min(n, e0 + kNarrowElems);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int64_t e = e0 + threadIdx.x;
+        for (; e + 3 * kThreads < e1; e += 4 * kThreads) {
+            s0 += __ldg(X + e); s1 += __ldg(X + e + kThreads); s2 += __ldg(X + e + 2 * kThreads); s3 += __ldg(X + e + 3 * kThreads);
+        }
+        for (; e < e1; e += kThreads) s0 += __ldg(X + e);
+        sm[threadIdx.x] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        if (threadIdx.x < J) {
+            float t = 0.f;
+            for (int q = threadIdx.x; q < kThreads; q += (int)J) t += sm[q];
+            partial[(int64_t)lb * J + threadIdx.x] = t;
+        }
+    } else {
+        const int bx = lb % m.gx[s], by = lb / m.gx[s];
+        const int64_t j = (int64_t)bx * kThreads + threadIdx.x;
+        if (j >= J) return;
+        const int64_t r0 = (int64_t)by * kColRows, r1 = min(m.I[s], r0 + kColRows);
+        float t = 0.f;
+        for (int64_t i = r0; i < r1; ++i) t += __ldg(X + i * m.ld[s] + j);
+        partial[(int64_t)by * J + j] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) colsum_multi_final_kernel(const MultiSegs m, const float* __restrict__ ws) {
+    int s = 0;
+    while (s + 1 < m.n && (int)blockIdx.x >= m.final_off[s + 1]) ++s;
+    const int64_t j = (int64_t)(blockIdx.x - m.final_off[s]) * kThreads + threadIdx.x;
+    const int64_t J = m.J[s];
+    if (j >= J) return;
+    const float* partial = ws + m.part_off[s];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int64_t p = 0;
+    for (; p + 3 < m.parts[s]; p += 4) {
+        s0 += partial[p * J + j]; s1 += partial[(p + 1) * J + j]; s2 += partial[(p + 2) * J + j]; s3 += partial[(p + 3) * J + j];
+    }
+    for (; p < m.parts[s]; ++p) s0 += partial[p * J + j];
+    const float t = (s0 + s1) + (s2 + s3);
+    m.out[s][j] = m.accumulate[s] ? (m.out[s][j] + t) : t;
+}
+
 struct Plan { int bi, bj; int64_t gx, gy; int splits; int64_t kk_per_split; size_t ws; };
 
 Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_bytes_avail, bool have_ws_limit) {
@@ -374,4 +436,44 @@ extern "C" int ppd_colsum(const float* X, int64_t ld, int64_t I, int64_t J, floa
     if (rc) return rc;
     colsum_final_kernel<<<gx, kThreads, 0, s>>>((const float*)workspace, parts, J, out, accumulate);
     return ppd::launch_status("colsum_final_kernel");
+}
+
+extern "C" size_t ppd_colsum_multi_workspace(const ppd_colsum_seg* segs, int n) {
+    size_t tot = 0;
+    for (int s = 0; segs && s < n; ++s) tot += ppd_colsum_workspace(segs[s].I, segs[s].J);
+    return tot;
+}
+
+extern "C" int ppd_colsum_multi(const ppd_colsum_seg* segs, int n, void* workspace, size_t workspace_bytes, void* stream) {
+    PPD_REQUIRE(segs && workspace, "null pointer");
+    PPD_REQUIRE(n >= 1 && n <= kMaxSegs, "between 1 and 8 segments");
+    MultiSegs m;
+    m.n = n;
+    int64_t off = 0;
+    m.block_off[0] = 0;
+    m.final_off[0] = 0;
+    for (int s = 0; s < n; ++s) {
+        const ppd_colsum_seg& g = segs[s];
+        PPD_REQUIRE(g.X && g.out && g.I > 0 && g.J > 0 && g.ld >= g.J, "bad segment");
+        m.X[s] = g.X; m.out[s] = g.out; m.ld[s] = g.ld; m.I[s] = g.I; m.J[s] = g.J; m.accumulate[s] = g.accumulate;
+        m.narrow[s] = colsum_narrow(g.ld, g.J) ? 1 : 0;
+        m.parts[s] = colsum_parts(g.ld, g.I, g.J);
+        m.gx[s] = (int)((g.J + kThreads - 1) / kThreads);
+        m.part_off[s] = off;
+        off += m.parts[s] * g.J;
+        const int64_t blocks = m.narrow[s] ? m.parts[s] : m.parts[s] * m.gx[s];
+        PPD_REQUIRE(m.block_off[s] + blocks <= 0x7fffffffLL, "too many blocks");
+        m.block_off[s + 1] = m.block_off[s] + (int)blocks;
+        m.final_off[s + 1] = m.final_off[s] + m.gx[s];
+    }
+    if (workspace_bytes < (size_t)off * sizeof(float)) {
+        ppd::set_error("ppd_colsum_multi: workspace too small");
+        return PPD_EWORKSPACE;
+    }
+    cudaStream_t st = ppd::as_stream(stream);
+    colsum_multi_partial_kernel<<<m.block_off[n], kThreads, 0, st>>>(m, (float*)workspace);
+    int rc = ppd::launch_status("colsum_multi_partial_kernel");
+    if (rc) return rc;
+    colsum_multi_final_kernel<<<m.final_off[n], kThreads, 0, st>>>(m, (const float*)workspace);
+    return ppd::launch_status("colsum_multi_final_kernel");
 }

@@ -22,7 +22,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import ConvGeom, GemmArgs, check, lib
+from ._lib import ColsumSeg, ConvGeom, GemmArgs, check, lib
 
 ALIGN = 64  # floats (256 B)
 
@@ -95,6 +95,7 @@ class PolicyEngine:
         self.cols_budget = 6 << 30        # bytes of im2col matrices kept from forward for backward
         self._side = None
         self._gru_stream = None
+        self._deferred = None
 
     # ------------------------------------------------------------------ parameters
     PRECISIONS = ("fp32", "tf32x3", "tf32")
@@ -229,6 +230,20 @@ class PolicyEngine:
                 self.ctx.__exit__(*exc)
             return False
 
+    def _flush_colsums(self):
+        """All bias gradients of the minibatch in two launches (ppd_colsum_multi)."""
+        todo, self._deferred = self._deferred, None
+        if not todo:
+            return
+        L = lib()
+        for i in range(0, len(todo), 8):
+            part = todo[i:i + 8]
+            segs = (ColsumSeg * len(part))()
+            for sg, (X, ld, I, J, out, acc) in zip(segs, part):
+                sg.X, sg.ld, sg.I, sg.J, sg.out, sg.accumulate = X.data_ptr(), ld, I, J, out.data_ptr(), acc
+            ws = self._ws(L.ppd_colsum_multi_workspace(segs, len(part)), "colsum_multi")
+            check(L.ppd_colsum_multi(segs, len(part), ws.data_ptr(), ws.numel(), self.stream), "colsum_multi")
+
     def _join(self):
         if self.overlap_wgrad and self._side is not None:
             ev = torch.cuda.Event()
@@ -297,6 +312,9 @@ class PolicyEngine:
         check(L.ppd_relu_mask(dx.data_ptr(), act.data_ptr(), cnt, self.stream), "relu_mask")
 
     def _colsum(self, X, ld, I, J, out, acc=0):
+        if self._deferred is not None:          # collected and reduced together at the end of the minibatch
+            self._deferred.append((X, ld, I, J, out, acc))
+            return
         L = lib()
         ws = self._ws(L.ppd_colsum_workspace(I, J), "colsum")
         check(L.ppd_colsum(X.data_ptr(), ld, I, J, out.data_ptr(), acc, ws.data_ptr(), ws.numel(), self.stream), "colsum")
@@ -516,6 +534,8 @@ class PolicyEngine:
                                      float(clip_param), float(value_coef), float(entropy_coef),
                                      int(bool(use_clipped_value_loss)), dz.data_ptr(), None, None, loss_out.data_ptr(),
                                      ws.data_ptr(), ws.numel(), self.stream), "ppo_loss")
+        # single chunk: every dY buffer stays valid until the end, so all bias gradients are reduced together then
+        self._deferred = [] if len(sv["chunks"]) == 1 else None
         # ---- heads backward (weight / bias gradients on the side stream)
         feats = sv["hs"] if self.recurrent else sv["feat"]
         with self._Side(self):
@@ -575,12 +595,21 @@ class PolicyEngine:
                 self._gemm(dgi, 3 * H, 0, hm, H, 0, gw_hh, H, 2 * H, H, B)                    # r, z rows of dW_hh
                 self._gemm(dghn, H, 0, hm, H, 0, gw_hh[2 * H * H:], H, H, H, B)                # n rows
                 gb_hh = self.seg("gru.b_hh", True)
-                gb_hh[:2 * H].copy_(self.seg("gru.b_ih", True)[:2 * H])                      # same sums for r, z
+                if self._deferred is None:
+                    gb_hh[:2 * H].copy_(self.seg("gru.b_ih", True)[:2 * H])                  # same sums for r, z
                 self._colsum(dghn, H, B, H, gb_hh[2 * H:])
         else:
             self._gemm(dz, A + 1, 1, self.seg("heads.w"), H, 0, dfeat, H, B, H, A + 1, mask=feats, ldm=H)
             for ci, (r0, r1) in enumerate(chunks):
                 self._trunk_backward_rows(sv["obs"], r0, r1, cols, r0 if cols[3] else 0, cols[3], dfeat, H, 0 if ci == 0 else 1)
+        if self._deferred is not None:
+            gb = None
+            if self.recurrent:      # b_hh's r,z sums equal b_ih's: drop that copy from the deferred list's dependencies
+                gb = (self.seg("gru.b_hh", True), self.seg("gru.b_ih", True))
+            with self._Side(self):
+                self._flush_colsums()
+                if gb is not None:
+                    gb[0][:2 * H].copy_(gb[1][:2 * H])
         self._join()
         return out
 

@@ -296,3 +296,19 @@ def test_tc_gemm_fused_col2im(B, H, C, k, s, N, split3):
     _lib.check(L.ppd_relu_mask(dx.data_ptr(), actd.data_ptr(), dx.numel(), _lib.stream_ptr()))
     scale = float(want.abs().max())
     assert float((dx.cpu() - want).abs().max()) <= (2e-5 if split3 else 4e-3) * scale
+
+
+def test_colsum_multi():
+    from ppodash_b200._lib import ColsumSeg
+    L = _lib.lib()
+    shapes = [(2048, 9, 9), (2048, 1536, 1536), (2048, 512, 512), (100352, 32, 32), (165888, 64, 64), (819200, 32, 32), (300, 64, 70)]
+    xs = [torch.randn(I, ld, device=DEV) for I, J, ld in shapes]
+    outs = [torch.randn(J, device=DEV) for I, J, ld in shapes]
+    want = [o.cpu() * (i % 2) + x[:, :J].double().sum(0).float().cpu() for i, (x, o, (I, J, ld)) in enumerate(zip(xs, outs, shapes))]
+    segs = (ColsumSeg * len(shapes))()
+    for i, (sg, x, o, (I, J, ld)) in enumerate(zip(segs, xs, outs, shapes)):
+        sg.X, sg.ld, sg.I, sg.J, sg.out, sg.accumulate = x.data_ptr(), ld, I, J, o.data_ptr(), i % 2
+    ws = torch.empty(L.ppd_colsum_multi_workspace(segs, len(shapes)), dtype=torch.uint8, device=DEV)
+    _lib.check(L.ppd_colsum_multi(segs, len(shapes), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    for o, w, (I, J, ld) in zip(outs, want, shapes):
+        np.testing.assert_allclose(o.cpu().numpy(), w.numpy(), rtol=1e-4, atol=2e-3 * np.sqrt(I) / 30)
