@@ -177,7 +177,7 @@ def test_c2_shaped_minibatch_vs_oracle(precision):
     g1 = eng.flat_grad.clone()
     sample = (dd(obs), dd(vobs), dd(h0), dd(actions), dd(old_v), dd(ret), dd(masks), dd(old_logp), dd(adv))
     for chunk_rows, time_chunks, budget in ((40, 4, 6 << 30), (2048, 3, 6 << 30), (32, 4, 0)):
-        eng.chunk_rows, eng.time_chunks, eng.cols_budget = chunk_rows, time_chunks, budget
+        eng.chunk_rows, eng.time_chunks, eng.cols_budget, eng.overlap_gru = chunk_rows, time_chunks, budget, True
         assert len(eng._chunks(B, E)) >= 3
         eng.train_minibatch(sample, 0.1, 0.5, 0.001)
         torch.cuda.synchronize()
