@@ -300,12 +300,31 @@ def run_b200(args, cfg):
                          f"barrier per timestep), the tensor roofline is not reachable at this E (SURVEY.md 7); "
                          f"peak = bf16 burst {pk['how']}")
     elif top_name in ("ppd_sgemm", "ppd_tc_gemm"):
-        fwd = 2.0 * (819200 * C + 2654208 + 903168 + 802816) / (84 * 84 / (cfg.obs_hw * cfg.obs_hw))
-        flops_step = 3.0 * fwd * rows_mb * cfg.ppo_epoch * cfg.num_mini_batch
-        ach = flops_step / (top_ms * 1e-3) / 1e12
-        roof.update(bound="tensor", achieved=ach, peak=pk["bf16"], unit="TFLOP/s", frac=ach / pk["bf16"],
-                    note=f"GEMM family ({args.precision}), all launches of one step pooled against the network's 3x-forward "
-                         f"training FLOPs; peak = bf16 burst {pk['how']}")
+        # The network's GEMMs are skinny (N = 32 / 64 output channels, or a 2048-row minibatch): ~15-60 FLOP per byte,
+        # far left of the tensor ridge (~170 FLOP/B for TF32), i.e. HBM-bound.  Algorithmic bytes = every operand read
+        # once and every result written once, fp32, summed over the GEMMs of one minibatch.
+        Bm = rows_mb
+        s1, s2, s3 = 20, 9, 7
+        M1, M2, M3 = Bm * s1 * s1, Bm * s2 * s2, Bm * s3 * s3
+        K1, K2, K3, FD = C * 64, 512, 576, 1568
+        Ip = (H + V + 3) // 4 * 4
+        w = dict(c1=32 * K1, c2=64 * K2, c3=32 * K3, fc=H * FD, ih=3 * H * Ip, hh=3 * H * H)
+        fwd_b = (M1 * K1 + w["c1"] + M1 * 32) + (M2 * K2 + w["c2"] + M2 * 64) + (M3 * K3 + w["c3"] + M3 * 32) + \
+                (Bm * FD + w["fc"] + Bm * H) + ((Bm * Ip + w["ih"] + Bm * 3 * H) if cfg.recurrent else 0)
+        dgrad_b = (Bm * H + w["fc"] + Bm * FD) + (M3 * 32 + w["c3"] + M2 * 64) + (M2 * 64 + w["c2"] + M1 * 32) + \
+                  ((Bm * 3 * H + w["ih"] + Bm * H) if cfg.recurrent else 0)
+        wgrad_b = (M1 * 32 + M1 * K1 + w["c1"]) + (M2 * 64 + M2 * K2 + w["c2"]) + (M3 * 32 + M3 * K3 + w["c3"]) + \
+                  (Bm * H + Bm * FD + w["fc"]) + ((Bm * 3 * H + Bm * Ip + w["ih"] + Bm * 3 * H + 2 * Bm * H + w["hh"])
+                                                  if cfg.recurrent else 0)
+        bytes_step = 4.0 * (fwd_b + dgrad_b + wgrad_b) * cfg.ppo_epoch * cfg.num_mini_batch
+        ach = bytes_step / (top_ms * 1e-3) / 1e9
+        fwd = 2.0 * (819200 * C + 2654208 + 903168 + 802816 + ((3 * H * (H + V)) if cfg.recurrent else 0))
+        tf = 3.0 * fwd * Bm * cfg.ppo_epoch * cfg.num_mini_batch / (top_ms * 1e-3) / 1e12
+        roof.update(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], tflops=tf,
+                    note=f"GEMM family ({args.precision}; tcgen05 kind::tf32), all launches of one step pooled: skinny GEMMs "
+                         f"(N=32/64, or 2048-row minibatch) are HBM-bound; achieved = algorithmic operand+result bytes / summed "
+                         f"launch time (side-stream launches overlap, so the sum over-counts time); peak = copy bandwidth "
+                         f"{pk['how']}; tensor-side: {tf:.1f} TFLOP/s useful")
     else:
         row_bytes = C * cfg.obs_hw ** 2 * 4 + V * 4 + 8 + 5 * 4
         bytes_launch = 2.0 * row_bytes * rows_mb
