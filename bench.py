@@ -103,9 +103,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
-def cpu_reference(cfg, minibatches, warm, reps=1, threads=None):
-    """Times the oracle port (torch-CPU restatement of PKG/algo/ppo.py + PKG/storage.py) on the box's
-    host cores.  One sample = `minibatches` minibatches of the update (of epochs*num_mini_batch) plus
+def cpu_reference(cfg, minibatches, warm, reps=1, threads=None, device="cpu"):
+    """Times the oracle port (torch restatement of PKG/algo/ppo.py + PKG/storage.py) on the box's
+    host cores (device="cpu"), or -- as a second comparison row, BASELINE.md section 2 item 5 -- the same
+    reference algorithm through STOCK PyTorch CUDA ops (cuDNN conv / GRU, cuBLAS, autograd) on the B200
+    (device="cuda").  One sample = `minibatches` minibatches of the update (of epochs*num_mini_batch) plus
     the full compute_returns; the update time is extrapolated linearly to the full update."""
     import numpy as np
     import torch
@@ -119,6 +121,10 @@ def cpu_reference(cfg, minibatches, warm, reps=1, threads=None):
     torch.manual_seed(0)
     p = o_pol.init_params(cfg.channels, cfg.num_actions, cfg.vector_obs_len, cfg.recurrent, cfg.hidden_size,
                           concat_vector=cfg.recurrent)
+    on_gpu = device != "cpu"
+    if on_gpu:
+        p = {k: v.to(device) for k, v in p.items()}
+        roll_dev = {k: v.to(device) for k, v in roll.items()}
     state = o_upd.UpdateState(p, lr=cfg.lr, eps=cfg.eps)
     times_gae, times_mb = [], []
     total_mb = cfg.ppo_epoch * cfg.num_mini_batch
@@ -128,14 +134,19 @@ def cpu_reference(cfg, minibatches, warm, reps=1, threads=None):
                                           roll["bad_masks"].numpy(), roll["next_value"].numpy(), True, cfg.gamma,
                                           cfg.gae_lambda, False)
         t1 = time.perf_counter()
-        r2 = dict(roll)
-        r2["returns"] = torch.from_numpy(ret)
-        r2["value_preds"] = torch.from_numpy(v)
+        r2 = dict(roll_dev if on_gpu else roll)
+        r2["returns"] = torch.from_numpy(ret).to(device)
+        r2["value_preds"] = torch.from_numpy(v).to(device)
+        if on_gpu:
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
         torch.manual_seed(99)
         o_upd.ppo_update(state, r2, recurrent=cfg.recurrent, clip_param=cfg.clip_param, ppo_epoch=cfg.ppo_epoch,
                          num_mini_batch=cfg.num_mini_batch, value_loss_coef=cfg.value_loss_coef,
                          entropy_coef=cfg.entropy_coef, max_grad_norm=cfg.max_grad_norm,
                          concat_vector=cfg.recurrent, max_minibatches=minibatches)
+        if on_gpu:
+            torch.cuda.synchronize()
         t2 = time.perf_counter()
         times_gae.append(t1 - t0)
         times_mb.append((t2 - t1) / minibatches)
@@ -145,7 +156,9 @@ def cpu_reference(cfg, minibatches, warm, reps=1, threads=None):
     steps = cfg.num_envs * cfg.num_steps
     return dict(value=steps / t_step, unit="env-steps/s", cores=cores, kind="port",
                 sample=f"{minibatches} of {total_mb} minibatches of one {cfg.name} update (+ full compute_returns), "
-                       f"best of {len(times_mb) - warm} after {warm} warm-up, extrapolated linearly; torch-CPU oracle port",
+                       f"best of {len(times_mb) - warm} after {warm} warm-up, extrapolated linearly; "
+                       + ("reference algorithm on stock PyTorch CUDA ops (cuDNN/cuBLAS/autograd), compute_returns on host"
+                          if on_gpu else "torch-CPU oracle port"),
                 gae_steps_per_sec=steps / t_gae, sec_per_minibatch=t_mb, sec_per_step_extrapolated=t_step)
 
 
@@ -368,6 +381,13 @@ def run_b200(args, cfg):
 
     if not args.no_cpu_baseline and world == 1 and not big:
         line["cpu_baseline"] = cpu_reference(cfg, minibatches=2, warm=1)
+        # second comparison row: the reference algorithm on the SAME GPU through stock PyTorch (not an optimisation
+        # target either; it separates "GPU vs CPU" from "hand-written sm_100a kernels vs stock PyTorch")
+        del st, host
+        torch.cuda.empty_cache()
+        sc = cpu_reference(cfg, minibatches=4, warm=1, device=str(dev))
+        line["stock_torch_cuda_baseline"] = dict(value=sc["value"], unit="env-steps/s", sample=sc["sample"],
+                                                 sec_per_minibatch=sc["sec_per_minibatch"])
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)

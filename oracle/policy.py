@@ -93,7 +93,7 @@ def gru_with_resets(p, x, hxs, masks):
     T = x.shape[0] // E
     xs = x.reshape(T, E, x.shape[1])
     mk = masks.reshape(T, E)
-    resets = (np.flatnonzero((mk[1:] == 0.0).any(dim=-1).numpy()) + 1).tolist()
+    resets = (np.flatnonzero((mk[1:] == 0.0).any(dim=-1).cpu().numpy()) + 1).tolist()   # host sync, as model.py:129-133
     cuts = [0] + resets + [T]
     h = hxs
     outs = []
