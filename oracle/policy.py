@@ -78,7 +78,7 @@ def _gru_run(p, x_seq, h):
     """x_seq [L,E,I], h [E,H] -> (out [L,E,H], h_last [E,H]) via torch's GRU (gate order r,z,n)."""
     flat = [p["base.gru.weight_ih_l0"], p["base.gru.weight_hh_l0"],
             p["base.gru.bias_ih_l0"], p["base.gru.bias_hh_l0"]]
-    out, hn = torch._VF.gru(x_seq, h.unsqueeze(0), flat, True, 1, 0.0, False, False, False)
+    out, hn = torch._VF.gru(x_seq, h.unsqueeze(0), flat, True, 1, 0.0, True, False, False)   # train=True (dropout 0): nn.GRU in .train() mode, and cuDNN needs it for backward
     return out, hn.squeeze(0)
 
 
