@@ -24,6 +24,7 @@
 #include <cuda.h>
 
 #include "ppd_common.cuh"
+#include "tca_gemm.cuh"
 
 namespace {
 
@@ -41,6 +42,7 @@ struct Args {
     int relu, accumulate, transpose_out;
     int block_n, a_mn, b_mn;
     int split3;                // 3xTF32: also multiply the low-order residuals (fp32-level accuracy)
+    int a_tmem;                // split3 only: A tiles go smem -> registers (hi/lo split) -> tensor memory; the MMAs read A from TMEM
     int stages;
     int64_t kk_per_split;
     float* partial;
@@ -90,6 +92,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand in tensor memory (lane = row, one 32-bit column per contraction element), B from a shared-memory descriptor
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
     asm volatile(
@@ -148,6 +173,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
     __shared__ __align__(8) uint64_t ready_bar[kMaxStages];     // split3: residual tiles written
+    __shared__ __align__(8) uint64_t ta_empty_bar[2];           // a_tmem: TMEM A stage consumed by its MMAs
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
 
@@ -157,7 +183,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int kStages = a.stages;
     const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)bn * BK * 4;
     const uint32_t tx_bytes = a_bytes + b_bytes;
-    const uint32_t stage_bytes = a.split3 ? 2 * tx_bytes : tx_bytes;
+    // a_tmem: [A raw | B hi | B lo]; split3 in shared memory: [A hi | B hi | A lo | B lo]; else [A | B]
+    const uint32_t stage_bytes = a.a_tmem ? a_bytes + 2 * b_bytes : (a.split3 ? 2 * tx_bytes : tx_bytes);
+    const uint32_t b_lo_off = a.a_tmem ? b_bytes : tx_bytes;     // B residual tile relative to the B tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i0 = (int64_t)blockIdx.y * BM;
@@ -172,6 +200,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&empty_bar[s], 1);
             mbar_init(&ready_bar[s], kEpiThreads);
         }
+        mbar_init(&ta_empty_bar[0], 1);
+        mbar_init(&ta_empty_bar[1], 1);
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -201,6 +231,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int kk = (int)(kk_begin + (int64_t)kb * BK);
                 if (!a.a_mn) {
                     tma_load_2d(&tmA, &full_bar[s], sa, kk, (int)i0);                         // box {32 k, 128 rows}
+                } else if (a.a_tmem) {
+                    tma_load_2d(&tmA, &full_bar[s], sa, (int)i0, kk);                         // box {128 rows(i), 32 k}, no swizzle
                 } else {
                     for (int q = 0; q < BM / 32; ++q)                                          // box {32 rows(i), 32 k}
                         tma_load_2d(&tmA, &full_bar[s], sa + q * 4096, (int)i0 + 32 * q, kk);
@@ -217,6 +249,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             // ================= MMA issuer
             const uint32_t idesc = make_idesc(bn, a.a_mn, a.b_mn);
+            const uint32_t idesc_ts = make_idesc(bn, 0, a.b_mn);      // A from tensor memory is always k-major
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
@@ -231,7 +264,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                : make_desc(sa + oa, 0, 1024, kLayoutSw128);
                     const uint64_t db = a.b_mn ? make_desc(sb + ob, 4096, 512, kLayoutSw128Base32)
                                                : make_desc(sb + ob, 0, 1024, kLayoutSw128);
-                    if (a.split3) {
+                    if (a.a_tmem) {
+                        // A hi / lo of this k-block sit in TMEM columns [ta, ta+32) / [ta+32, ta+64), 8 per MMA
+                        const uint32_t ta = tmem_base + 128u + (uint32_t)(kb & 1) * 64u + (uint32_t)k * 8u;
+                        const uint64_t dbl = a.b_mn ? make_desc(sb + b_lo_off + ob, 4096, 512, kLayoutSw128Base32)
+                                                    : make_desc(sb + b_lo_off + ob, 0, 1024, kLayoutSw128);
+                        umma_tf32_ts(tmem_base, ta + 32u, db, idesc_ts, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32_ts(tmem_base, ta, dbl, idesc_ts, 1u);
+                        umma_tf32_ts(tmem_base, ta, db, idesc_ts, 1u);
+                    } else if (a.split3) {
                         // x = hi + lo with hi = the 19 bits the tensor core reads; add the small terms first
                         const uint64_t dal = a.a_mn ? make_desc(sa + tx_bytes + oa, 4096, 512, kLayoutSw128Base32)
                                                     : make_desc(sa + tx_bytes + oa, 0, 1024, kLayoutSw128);
@@ -245,6 +286,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 umma_commit(&empty_bar[s]);          // ring slot free once these MMAs have read it
+                if (a.a_tmem) umma_commit(&ta_empty_bar[kb & 1]);
             }
             umma_commit(&tmem_full_bar);             // accumulator complete
         }
@@ -254,7 +296,56 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // Rounding (instead of the tensor core's truncation of the raw fp32 bits) keeps the neglected
         // lo*lo term and the rounding of lo zero-mean, so long sums with cancellation (weight gradients)
         // do not pick up a bias.
-        if (a.split3) {
+        if (a.a_tmem) {
+            // A: each thread owns one tile row (TMEM lane) and half of the 32 k columns; warps 2-5 take k 0..15,
+            // warps 6-9 k 16..31 (a warp may only touch TMEM lanes [32*(warp%4), +32)).  B is split in place.
+            const int et = threadIdx.x - 64;
+            const int r = (warp & 3) * 32 + lane, h = (warp - 2) >> 2;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                const uint8_t* sa = smem + (size_t)s * stage_bytes;
+                float x[16], hi[16], lo[16];
+                if (!a.a_mn) {
+                    // 128B-swizzled rows of 32 floats: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
+                    const float4* rowp = reinterpret_cast<const float4*>(sa + r * 128);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 v = rowp[(4 * h + c) ^ (r & 7)];
+                        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+                    }
+                } else {
+                    const float* colp = reinterpret_cast<const float*>(sa) + (16 * h) * BM + r;   // [k][128 rows]
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) x[c] = colp[c * BM];
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) split_tf32(x[c], hi[c], lo[c]);
+                mbar_wait(&ta_empty_bar[kb & 1], ((uint32_t)(kb >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 128u + (uint32_t)(kb & 1) * 64u + 16u * h;
+                tmem_st16(ta, hi);
+                tmem_st16(ta + 32u, lo);
+                float4* src = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes);
+                float4* dst = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes + b_bytes);
+                const int nvec = (int)(b_bytes >> 4);
+                for (int v = et; v < nvec; v += kEpiThreads) {
+                    const float4 xb = src[v];
+                    float4 hb, rb;
+                    split_tf32(xb.x, hb.x, rb.x);
+                    split_tf32(xb.y, hb.y, rb.y);
+                    split_tf32(xb.z, hb.z, rb.z);
+                    split_tf32(xb.w, hb.w, rb.w);
+                    src[v] = hb;
+                    dst[v] = rb;
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
+            }
+        } else if (a.split3) {
             const int et = threadIdx.x - 64;                         // 0..255
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % kStages;
@@ -426,6 +517,8 @@ int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int6
 }
 
 int g_two_ctas = 1;
+int g_persistent = 1;     // 3xTF32 products run on the persistent TMEM-A kernel (tca_gemm.cu); 0 = the kernel in this file
+int g_a_tmem = 1;         // 3xTF32: stage the A operand through registers into tensor memory (0 = split it in shared memory)
 int g_force_bn = 0;       // tuning: 0 = heuristic, else 32/64/128/256 where it divides the problem sensibly
 struct Plan { int bn; int64_t gx, gy; int splits; int64_t kk_per_split; size_t ws; };
 
@@ -473,6 +566,8 @@ Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_avail, bool limit, bo
 
 extern "C" void ppd_tc_gemm_set_option(int v) {
     if (v == 0 || v == 1) g_two_ctas = v;
+    else if (v == 2 || v == 3) g_a_tmem = v - 2;
+    else if (v == 4 || v == 5) g_persistent = v - 4;
     else if (v == 32 || v == 64 || v == 128 || v == 256) g_force_bn = v;
     else if (v == -1) g_force_bn = 0;
 }
@@ -480,7 +575,8 @@ extern "C" void ppd_tc_gemm_set_option(int v) {
 extern "C" size_t ppd_tc_gemm_workspace(int64_t I, int64_t J, int64_t KK) {
     if (I <= 0 || J <= 0 || KK <= 0) return 0;
     const size_t a = make_plan(I, J, KK, 0, false, false, false).ws, b = make_plan(I, J, KK, 0, false, true, true).ws;
-    return a > b ? a : b;                        // upper bound over the tile choices
+    const size_t c = ppd::tca::make_plan(I, J, KK, 0, false).ws;
+    return a > b ? (a > c ? a : c) : (b > c ? b : c);      // upper bound over the kernels' tile choices
 }
 
 // 1 if ppd_tc_gemm can run this problem (alignment of the operands for TMA), else 0.
@@ -519,6 +615,17 @@ int tc_gemm_impl(const ppd_gemm_args* g, int flags, const ppd_conv_geom* geom, v
     const int split3 = (flags & PPD_TC_SPLIT3) ? 1 : 0;
     PPD_REQUIRE(ppd_tc_gemm_supported(g), "operands must be 16-byte aligned with leading dimensions that are multiples of 4");
     PPD_REQUIRE(geom || (transpose_out ? g->ldc >= g->I : g->ldc >= g->J), "bad ldc");
+    if (split3 && g_persistent && !geom) {
+        ppd::tca::Plan tp;
+        cudaStream_t ts = ppd::as_stream(stream);
+        int trc = ppd::tca::launch(g, transpose_out, nullptr, workspace, workspace_bytes, ts, &tp);
+        if (trc || tp.splits == 1) return trc;
+        int64_t nb = (g->I * g->J + 255) / 256;
+        if (nb > 4 * ppd::kNumSMs) nb = 4 * ppd::kNumSMs;
+        tc_splitk_reduce_kernel<<<(unsigned)nb, 256, 0, ts>>>(reinterpret_cast<float*>(workspace), tp.splits, g->I, g->J, g->C,
+                                                              g->ldc, g->bias, g->mask, g->ldm, g->relu, g->accumulate, transpose_out);
+        return ppd::launch_status("tc_splitk_reduce_kernel");
+    }
     Plan p = make_plan(g->I, g->J, g->KK, workspace ? workspace_bytes : 0, true, split3, g->a_kmajor != 0);
     if (geom && p.splits > 1) {           // the scatter epilogue adds complete products only
         p.splits = 1;
@@ -528,7 +635,9 @@ int tc_gemm_impl(const ppd_gemm_args* g, int flags, const ppd_conv_geom* geom, v
     CUtensorMap tmA, tmB;
     int rc;
     // k-major operand: matrix [rows = I or J, cols = KK]; mn-major: matrix [rows = KK, cols = I or J]
+    const int a_tmem = (split3 && g_a_tmem && p.bn <= 128) ? 1 : 0;
     if (g->a_kmajor) rc = make_map(&tmA, g->A, g->I, g->KK, g->lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    else if (a_tmem) rc = make_map(&tmA, g->A, g->KK, g->I, g->lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE);
     else             rc = make_map(&tmA, g->A, g->KK, g->I, g->lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
     if (g->b_kmajor) rc = make_map(&tmB, g->B, g->J, g->KK, g->ldb, BK, p.bn, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -542,6 +651,7 @@ int tc_gemm_impl(const ppd_gemm_args* g, int flags, const ppd_conv_geom* geom, v
     a.kk_per_split = p.kk_per_split;
     a.partial = p.splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
     a.split3 = split3;
+    a.a_tmem = a_tmem;
     a.scatter = geom ? 1 : 0;
     if (geom) {
         a.OH = (geom->H - geom->kh) / geom->stride + 1; a.OW = (geom->W - geom->kw) / geom->stride + 1;
@@ -549,7 +659,8 @@ int tc_gemm_impl(const ppd_gemm_args* g, int flags, const ppd_conv_geom* geom, v
     } else {
         a.OH = a.OW = a.kw = a.cstride = a.Cin = a.Hin = a.Win = 0;
     }
-    const size_t stage = (size_t)(split3 ? 2 : 1) * (BM * BK * 4 + (size_t)p.bn * BK * 4);
+    const size_t stage = a_tmem ? (size_t)BM * BK * 4 + 2 * (size_t)p.bn * BK * 4
+                                : (size_t)(split3 ? 2 : 1) * (BM * BK * 4 + (size_t)p.bn * BK * 4);
     // Ring depth: if two CTAs (2 x 256 TMEM columns) can be co-resident with at least a 2-deep ring each, size
     // the ring for that -- one CTA's prologue / epilogue then hides behind the other's main loop (the kernel
     // is not persistent); otherwise give the single CTA as deep a ring as fits.

@@ -1,0 +1,582 @@
+// Persistent 3xTF32 tcgen05 GEMM with the A operand staged through tensor memory.
+//
+//   C[i,j] (+)= sum_kk OpA(i,kk) * OpB(j,kk)   (problem statement of sgemm.cu / tc_gemm.cu)
+//
+// fp32-level accuracy on the tensor cores needs every operand split into hi = TF32(x) and lo = TF32(x - hi)
+// and three products (A_lo B_hi + A_hi B_lo + A_hi B_hi).  Doing that split in shared memory (tc_gemm.cu)
+// costs 7 shared-memory passes over every A tile (TMA write, split read, two split writes, three MMA
+// reads).  Here the A tile makes two: TMA writes it, the transform warps read it into registers, split it
+// there and store hi / lo into TENSOR MEMORY (tcgen05.st); the MMAs take A from TMEM
+// (tcgen05.mma ... [d], [a], b-desc) and only the (small) B tile from shared memory.  Because the tile
+// passes through registers, row-major and transposed A tiles, and the patch tiles of an implicit-GEMM
+// convolution, all land in the same TMEM layout (lane = output row, one 32-bit column per contraction
+// element); no operand-layout constraints reach the TMA side.
+//
+// One CTA per SM, persistent over (m tile, n tile, k split) work items; 16 warps:
+//   warp 0      TMA producer of A (ring of kSA x 16 KB: deep enough to cover the HBM latency at full bandwidth)
+//   warp 1      MMA issuer; owns the TMEM allocation (512 columns: 2 tiles x [main | correction] accumulators, 4 A stages x 64)
+//   warp 2      TMA producer of B (ring of [hi | lo] tiles), independent of the A ring
+//   warps 4-11  transform: smem A tile -> registers -> hi/lo -> TMEM A stage (and the split of B in shared
+//               memory when the caller has no pre-split copy of it)
+//   warps 12-15 epilogue: tcgen05.ld of the finished accumulator while the next tile's MMAs fill the other
+// Every hand-off is an mbarrier; tcgen05.commit releases B stages, TMEM A stages and accumulators.
+#include <cuda.h>
+
+#include "ppd_common.cuh"
+#include "tca_gemm.cuh"
+
+namespace ppd {
+namespace tca {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// hi = x rounded to TF32 (10 mantissa bits, round half away in magnitude), lo = (x - hi) rounded likewise.
+// Integer rounding on the bit pattern: 5 instructions per element (cvt.rna.tf32.f32 expands to ~8 on sm_100a).
+// x - hi is exact; Inf stays Inf, the largest finite values round to Inf as round-to-nearest does.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    const float r = x - __uint_as_float(hi);
+    lo = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+constexpr uint32_t kLayoutSw128 = 2;        // k-major tiles
+constexpr uint32_t kLayoutSw128Base32 = 1;  // mn-major 32-bit tiles
+
+// c_format F32 @4, a/b_format TF32 @7/@10, a_major @15 (0: A from TMEM is k-major), b_major @16, N>>3 @17, M>>4 @24
+__device__ __forceinline__ uint32_t make_idesc(int n, int b_mn) {
+    uint32_t d = 0;
+    d |= 1u << 4;
+    d |= 2u << 7;
+    d |= 2u << 10;
+    d |= (uint32_t)(b_mn ? 1 : 0) << 16;
+    d |= (uint32_t)(n >> 3) << 17;
+    d |= (uint32_t)(BM >> 4) << 24;
+    return d;
+}
+
+struct Item { int64_t i0, j0, kk_begin; int nkb; int z; };
+
+// Pipeline timeline of CTA 0 (debug builds only: -DPPD_TCA_TRACE): trace[(it * 16 + slot)] = clock64()
+#ifdef PPD_TCA_TRACE
+__device__ long long* g_trace = nullptr;
+#define TCA_TRACE(it_, slot_) do { if (g_trace && blockIdx.x == 0 && (it_) < 256 && lane == 0) g_trace[(it_) * 16 + (slot_)] = clock64(); } while (0)
+#else
+#define TCA_TRACE(it_, slot_) do { } while (0)
+#endif
+
+__device__ __forceinline__ Item decode(const Args& a, int w) {
+    Item it;
+    const int n = w % a.num_n;
+    const int r = w / a.num_n;
+    const int m = r % a.num_m;
+    it.z = r / a.num_m;
+    it.i0 = (int64_t)m * BM;
+    it.j0 = (int64_t)n * a.bn;
+    it.kk_begin = (int64_t)it.z * a.kk_per_split;
+    const int64_t kk_end = min(a.KK, it.kk_begin + a.kk_per_split);
+    it.nkb = (int)((kk_end - it.kk_begin + BK - 1) / BK);
+    return it;
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Roles branch on a warp index the compiler can prove warp-uniform (shfl), and every role loop is executed by the
+// whole warp with one ELECTED lane issuing the TMA / MMA / commit instructions.  That keeps tensor-map coordinates,
+// descriptors and barrier addresses in uniform registers: issued from a divergent `lane == 0` branch, each
+// tcgen05.mma cost ~185 clocks (seven R2UR moves per instruction) instead of ~33 (measured, tools/probes/mma_probe.cu).
+__global__ void __launch_bounds__(kThreads, 1)
+tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmBlo, const Args a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_a[kSA], empty_a[kSA], full_b[kMaxSB], empty_b[kMaxSB];
+    __shared__ __align__(8) uint64_t ta_full[kTA], ta_empty[kTA], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int bn = a.bn;
+    const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)bn * BK * 4;
+    uint8_t* smemA = smem;                               // kSA stages of one 128 x 32 fp32 tile
+    uint8_t* smemB = smem + kSA * a_bytes;               // kSB stages of [B hi | B lo]
+    const uint32_t kSB = (uint32_t)a.sb_stages;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 4); }
+        for (int s = 0; s < kMaxSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < kTA; ++s) { mbar_init(&ta_full[s], 4); mbar_init(&ta_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (a.b_presplit) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer, A tiles
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
+            const Item t = decode(a, w);
+            for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+                const int kk = (int)(t.kk_begin + (int64_t)kb * BK);
+                const uint32_t s = it % kSA;
+                mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
+                if (elect_one()) {
+                    mbar_expect_tx(&full_a[s], a_bytes);
+                    uint8_t* sa = smemA + s * a_bytes;
+                    if (!a.a_mn) tma_load_2d(&tmA, &full_a[s], sa, kk, (int)t.i0);     // box {32 k, 128 rows}, 128B swizzle
+                    else         tma_load_2d(&tmA, &full_a[s], sa, (int)t.i0, kk);     // box {128 rows, 32 k}, no swizzle
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 2) {
+        // ================= TMA producer, B tiles
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
+            const Item t = decode(a, w);
+            for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+                const int kk = (int)(t.kk_begin + (int64_t)kb * BK);
+                const uint32_t s = it % kSB;
+                mbar_wait(&empty_b[s], ((it / kSB) & 1u) ^ 1u);
+                if (elect_one()) {
+                    mbar_expect_tx(&full_b[s], a.b_presplit ? 2 * b_bytes : b_bytes);
+                    uint8_t* sb = smemB + s * 2 * b_bytes;
+                    if (!a.b_mn) {
+                        tma_load_2d(&tmB, &full_b[s], sb, kk, (int)t.j0);               // box {32 k, bn rows}
+                        if (a.b_presplit) tma_load_2d(&tmBlo, &full_b[s], sb + b_bytes, kk, (int)t.j0);
+                    } else {
+                        for (int q = 0; q < bn / 32; ++q) {                             // box {32 cols(j), 32 k}
+                            tma_load_2d(&tmB, &full_b[s], sb + q * 4096, (int)t.j0 + 32 * q, kk);
+                            if (a.b_presplit) tma_load_2d(&tmBlo, &full_b[s], sb + b_bytes + q * 4096, (int)t.j0 + 32 * q, kk);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer.  Two accumulators per tile: main = A_hi B_hi in columns [0, bn) and the
+        // corrections A_hi B_lo + A_lo B_hi in columns [bn, 2bn).  The B stage holds [hi rows | lo rows] back to back,
+        // so ONE N = 2bn MMA multiplies A_hi with both; a second N = bn MMA adds A_lo B_hi: two instructions per
+        // k-step instead of three, and the truncating tcgen05 accumulation sees a third of the steps per accumulator.
+        const uint32_t idesc2 = make_idesc(2 * bn, a.b_mn), idesc1 = make_idesc(bn, a.b_mn);
+        const uint64_t bdesc0 = a.b_mn ? make_desc(smem_u32(smemB), 4096, 512, kLayoutSw128Base32)
+                                       : make_desc(smem_u32(smemB), 0, 1024, kLayoutSw128);
+        const uint32_t kstep = a.b_mn ? (1024u >> 4) : (32u >> 4);          // descriptor start-address step per 8 k
+        uint32_t it = 0, tile_it = 0;
+        for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
+            const Item t = decode(a, w);
+            const uint32_t acc = tile_it & 1u;
+            mbar_wait(&acc_empty[acc], ((tile_it >> 1) & 1u) ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d = tmem_base + kAccCol0 + acc * kAccStride;
+            for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+                const uint32_t ts = it % kTA, s = it % kSB;
+                mbar_wait(&ta_full[ts], (it / kTA) & 1u);
+                if (a.b_presplit) mbar_wait(&full_b[s], (it / kSB) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t db = bdesc0 + (uint64_t)((s * 2u * b_bytes) >> 4);
+                    const uint32_t ta = tmem_base + kTaCol0 + ts * 64u;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        umma_tf32_ts(d, ta + k * 8u, db + (uint64_t)(k * kstep), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32_ts(d + (uint32_t)bn, ta + 32u + k * 8u, db + (uint64_t)(k * kstep), idesc1, 1u);
+                    }
+                    umma_commit(&ta_empty[ts]);
+                    umma_commit(&empty_b[s]);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(&acc_full[acc]);
+            __syncwarp();
+        }
+    } else if (warp == 3) {
+        // spare
+    } else if (warp < 4 + kXformWarps) {
+        // ================= transform: two groups of four warps take alternate k-blocks (two k-blocks in flight hide
+        // the shared-memory / TMEM / barrier latencies of one another); thread = one tile row, all 32 contraction columns
+        const int q = warp & 3;                       // TMEM lane quarter this warp may touch
+        const int grp = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
+        const int gt = (threadIdx.x - 128) & 127;     // thread index within the group
+        const uint32_t smemA_u = smem_u32(smemA), smemB_u = smem_u32(smemB);
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
+            const Item t = decode(a, w);
+            for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+                if ((int)(it & 1u) != grp) continue;
+                const uint32_t s = it % kSA;
+                if (q == 0) TCA_TRACE(it, 2);
+                mbar_wait(&full_a[s], (it / kSA) & 1u);
+                if (q == 0) TCA_TRACE(it, 3);
+                const uint32_t sa = smemA_u + s * a_bytes;
+                float x[32];
+                if (!a.a_mn) {
+                    // 128B-swizzled rows of 32 floats: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v = lds128(sa + r * 128 + ((c ^ (r & 7)) << 4));
+                        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) x[c] = lds32(sa + (c * BM + r) * 4);                // [k][128 rows]
+                }
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) split_tf32(x[c], hi[c], lo[c]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_a[s]);            // the tile is in registers: slot back to the producer
+                if (q == 0) TCA_TRACE(it, 4);
+                const uint32_t ts = it % kTA;
+                mbar_wait(&ta_empty[ts], ((it / kTA) & 1u) ^ 1u);
+                if (q == 0) TCA_TRACE(it, 5);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kTaCol0 + ts * 64u;
+                tmem_st16(ta, hi);
+                tmem_st16(ta + 16u, hi + 16);
+                tmem_st16(ta + 32u, lo);
+                tmem_st16(ta + 48u, lo + 16);
+                if (q == 0) TCA_TRACE(it, 6);
+                if (!a.b_presplit) {
+                    const uint32_t sbs = it % kSB;
+                    mbar_wait(&full_b[sbs], (it / kSB) & 1u);
+                    const uint32_t src = smemB_u + sbs * 2 * b_bytes;
+                    const int nvec = (int)(b_bytes >> 4);
+                    for (int v = gt; v < nvec; v += 128) {
+                        const float4 xb = lds128(src + (v << 4));
+                        uint4 hb, rb;
+                        split_tf32(xb.x, hb.x, rb.x);
+                        split_tf32(xb.y, hb.y, rb.y);
+                        split_tf32(xb.z, hb.z, rb.z);
+                        split_tf32(xb.w, hb.w, rb.w);
+                        sts128(src + (v << 4), hb);
+                        sts128(src + b_bytes + (v << 4), rb);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ta_full[ts]);
+                if (q == 0) TCA_TRACE(it, 7);
+            }
+        }
+    } else {
+        // ================= epilogue: warp w may touch TMEM lanes [32*(w%4), +32); result = main + correction accumulator
+        const int q = warp & 3;
+        uint32_t tile_it = 0;
+        for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
+            const Item t = decode(a, w);
+            const uint32_t acc = tile_it & 1u;
+            mbar_wait(&acc_full[acc], (tile_it >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t i = t.i0 + q * 32 + lane;
+            for (int c0 = 0; c0 < bn; c0 += 32) {
+                float v[32];
+                {
+                    float u[32];
+                    const uint32_t tad = tmem_base + ((uint32_t)(q * 32) << 16) + kAccCol0 + acc * kAccStride + (uint32_t)c0;
+                    tmem_ld32(tad + (uint32_t)bn, u);
+                    tmem_ld32(tad, v);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] += u[c];
+                }
+                if (c0 + 32 >= bn) {
+                    // last read of this accumulator: hand it back before the global stores
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                }
+                const int64_t jb = t.j0 + c0;
+                if (a.partial) {
+                    if (i < a.I) {
+                        float* P = a.partial + ((int64_t)t.z * a.I + i) * a.J;
+                        if (jb + 31 < a.J && (a.J & 3) == 0) {
+#pragma unroll
+                            for (int c = 0; c < 32; c += 4)
+                                *reinterpret_cast<float4*>(P + jb + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c)
+                                if (jb + c < a.J) P[jb + c] = v[c];
+                        }
+                    }
+                    continue;
+                }
+                if (a.bias) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] += (jb + c < a.J) ? __ldg(a.bias + jb + c) : 0.f;
+                }
+                if (a.relu) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+                }
+                if (a.transpose_out) {
+                    // C is [J, I] row-major: for a fixed column the 32 lanes write 32 consecutive floats
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if (i < a.I && jb + c < a.J) {
+                            float* p = a.C + (jb + c) * a.ldc + i;
+                            float x = v[c];
+                            if (a.mask) x = (__ldg(a.mask + (jb + c) * a.ldm + i) > 0.f) ? x : 0.f;
+                            *p = a.accumulate ? (*p + x) : x;
+                        }
+                    }
+                } else if (i < a.I) {
+                    float* crow = a.C + i * a.ldc + jb;
+                    const float* mrow = a.mask ? a.mask + i * a.ldm + jb : nullptr;
+                    const bool vec = (jb + 31 < a.J) && ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) &&
+                                     (!mrow || (((a.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)));
+                    if (vec) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            float4 x = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                            if (mrow) {
+                                const float4 m = __ldg(reinterpret_cast<const float4*>(mrow + c));
+                                x.x = m.x > 0.f ? x.x : 0.f; x.y = m.y > 0.f ? x.y : 0.f;
+                                x.z = m.z > 0.f ? x.z : 0.f; x.w = m.w > 0.f ? x.w : 0.f;
+                            }
+                            float4* p = reinterpret_cast<float4*>(crow + c);
+                            if (a.accumulate) { const float4 o = *p; x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w; }
+                            *p = x;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            if (jb + c < a.J) {
+                                float x = v[c];
+                                if (mrow) x = (__ldg(mrow + c) > 0.f) ? x : 0.f;
+                                crow[c] = a.accumulate ? (crow[c] + x) : x;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+#ifdef PPD_TCA_TRACE
+extern "C" int ppd_tca_set_trace(void* dev_ptr) {
+    return (int)cudaMemcpyToSymbol(g_trace, &dev_ptr, sizeof(void*));
+}
+#endif
+
+int make_map_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("tca_gemm: cuTensorMapEncodeTiled not available"); return PPD_EINVAL; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tca_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r); return PPD_EINVAL; }
+    return 0;
+}
+
+Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_avail, bool limit) {
+    Plan p;
+    p.bn = J <= 32 ? 32 : 64;          // the MMAs run at N = 2 bn ([hi | lo] of B side by side)
+    p.num_n = (int)((J + p.bn - 1) / p.bn);
+    p.num_m = (int)((I + BM - 1) / BM);
+    const int64_t tiles = (int64_t)p.num_n * p.num_m;
+    const int64_t nkb = (KK + BK - 1) / BK;
+    int64_t splits = 1;
+    if (tiles < kNumSMs) {
+        splits = kNumSMs / tiles;                   // fill the SMs once; every split keeps >= 4 k-blocks
+        if (splits > nkb / 4) splits = nkb / 4;
+        if (splits < 1) splits = 1;
+    }
+    // tcgen05 accumulates with truncation: a chain of KK/8 x 3 accumulate steps loses ~1e-5 (relative) at KK ~ 1500.
+    // Where the output is small enough for the partials to be cheap, keep every chain at <= 24 k-blocks (768).
+    if (KK > 1024 && tiles <= 2 * kNumSMs && splits < (nkb + 23) / 24) splits = (nkb + 23) / 24;
+    if (limit) {
+        while (splits > 1 && (size_t)splits * I * J * sizeof(float) > ws_avail) --splits;
+    }
+    int64_t per = (nkb + splits - 1) / splits * BK;
+    splits = (KK + per - 1) / per;
+    p.splits = (int)splits;
+    p.kk_per_split = per;
+    p.ws = splits > 1 ? (size_t)splits * I * J * sizeof(float) : 0;
+    return p;
+}
+
+int launch(const ppd_gemm_args* g, int transpose_out, const float* b_lo, void* workspace, size_t workspace_bytes,
+           cudaStream_t s, Plan* plan_out) {
+    Plan p = make_plan(g->I, g->J, g->KK, workspace ? workspace_bytes : 0, true);
+    CUtensorMap tmA, tmB, tmBlo;
+    int rc;
+    if (g->a_kmajor) rc = make_map_2d(&tmA, g->A, g->I, g->KK, g->lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    else             rc = make_map_2d(&tmA, g->A, g->KK, g->I, g->lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    for (int k = 0; k < (b_lo ? 2 : 1); ++k) {
+        const float* base = k ? b_lo : g->B;
+        CUtensorMap* m = k ? &tmBlo : &tmB;
+        if (g->b_kmajor) rc = make_map_2d(m, base, g->J, g->KK, g->ldb, BK, p.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+        else             rc = make_map_2d(m, base, g->KK, g->J, g->ldb, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+    }
+    if (!b_lo) tmBlo = tmB;
+    Args a;
+    a.C = g->C; a.ldc = g->ldc; a.I = g->I; a.J = g->J; a.KK = g->KK;
+    a.bias = g->bias; a.mask = g->mask; a.ldm = g->ldm; a.relu = g->relu; a.accumulate = g->accumulate;
+    a.transpose_out = transpose_out;
+    a.bn = p.bn; a.a_mn = g->a_kmajor ? 0 : 1; a.b_mn = g->b_kmajor ? 0 : 1; a.b_presplit = b_lo ? 1 : 0;
+    a.num_m = p.num_m; a.num_n = p.num_n; a.splits = p.splits; a.kk_per_split = p.kk_per_split;
+    a.partial = p.splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
+    a.total_items = p.num_m * p.num_n * p.splits;
+    int sb_stages = (int)((kSmemBudget - 1024 - (size_t)kSA * BM * BK * 4) / ((size_t)2 * p.bn * BK * 4));
+    if (sb_stages > kMaxSB) sb_stages = kMaxSB;
+    a.sb_stages = sb_stages;
+    const size_t smem = (size_t)kSA * BM * BK * 4 + (size_t)sb_stages * 2 * p.bn * BK * 4 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tca_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e != cudaSuccess) { set_error("tca_gemm: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
+        attr_set = true;
+    }
+    const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+    tca_gemm_kernel<<<grid, kThreads, smem, s>>>(tmA, tmB, tmBlo, a);
+    if (plan_out) *plan_out = p;
+    return launch_status("tca_gemm_kernel");
+}
+
+}  // namespace tca
+}  // namespace ppd

@@ -56,11 +56,18 @@ def run(name, I, J, KK, ak, bk, mode):
 if __name__ == "__main__":
     if os.environ.get("PPD_TWO_CTAS") is not None:
         _lib.lib().ppd_tc_gemm_set_option(int(os.environ["PPD_TWO_CTAS"]))
+    if os.environ.get("PPD_ATMEM") is not None:
+        _lib.lib().ppd_tc_gemm_set_option(2 + int(os.environ["PPD_ATMEM"]))
+    if os.environ.get("PPD_PERSIST") is not None:
+        _lib.lib().ppd_tc_gemm_set_option(4 + int(os.environ["PPD_PERSIST"]))
     if os.environ.get("PPD_BN") is not None:
         _lib.lib().ppd_tc_gemm_set_option(int(os.environ["PPD_BN"]))
     modes = sys.argv[1:] or ["fp32", "tf32", "tf32x3"]
     tot = {m: 0.0 for m in modes}
+    only = os.environ.get("PPD_SHAPES")
     for sh in SHAPES:
+        if only and sh[0] not in only.split(","):
+            continue
         for m in modes:
             r = run(*sh, m)
             tot[m] += r["ms"]
