@@ -200,6 +200,12 @@ int ppd_sgemm(const ppd_gemm_args* g, void* workspace, size_t workspace_bytes, v
 size_t ppd_tc_gemm_workspace(int64_t I, int64_t J, int64_t KK);
 int ppd_tc_gemm_supported(const ppd_gemm_args* g);
 int ppd_tc_gemm(const ppd_gemm_args* g, int flags, void* workspace, size_t workspace_bytes, void* stream);
+/* 3xTF32 with a PRE-SPLIT B operand (weights): g->B holds hi = TF32(B), b_lo the residuals TF32(B - hi), same layout
+ * and leading dimension; ppd_split_tf32 produces both (n a multiple of 4, 16-byte aligned).  The kernel then neither
+ * re-splits B per tile nor fences shared memory for it: the weights of a minibatch are split once, after the optimiser step. */
+int ppd_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+int ppd_tc_gemm_bsplit(const ppd_gemm_args* g, const float* b_lo, int flags, void* workspace, size_t workspace_bytes,
+                       void* stream);
 /* dgrad of an NHWC convolution with col2im fused into the epilogue: the product dY[M,N] W[N,(ky,kx,c)] is not
  * stored but scatter-added (red.global.add.v4.f32) into dx[B,H,W,C], which the caller has zeroed; follow with
  * ppd_relu_mask.  Replaces the dcols round trip through HBM (write + col2im read).  g->C = dx, g->ldc ignored.

@@ -591,7 +591,20 @@ extern "C" int ppd_tc_gemm_supported(const ppd_gemm_args* g) {
 
 namespace {
 int tc_gemm_impl(const ppd_gemm_args* g, int flags, const ppd_conv_geom* geom, void* workspace, size_t workspace_bytes,
-                 void* stream);
+                 void* stream, const float* b_lo = nullptr);
+}
+
+extern "C" int ppd_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+    PPD_REQUIRE(x && hi && lo && n >= 0 && (n & 3) == 0, "n must be a multiple of 4");
+    PPD_REQUIRE(!(((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15), "pointers must be 16-byte aligned");
+    return ppd::tca::split_operand(x, hi, lo, n, ppd::as_stream(stream));
+}
+
+extern "C" int ppd_tc_gemm_bsplit(const ppd_gemm_args* g, const float* b_lo, int flags, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+    PPD_REQUIRE(g && b_lo && (flags & PPD_TC_SPLIT3), "pre-split B operands are a 3xTF32 feature");
+    PPD_REQUIRE(!((uintptr_t)b_lo & 15), "b_lo must be 16-byte aligned");
+    return tc_gemm_impl(g, flags, nullptr, workspace, workspace_bytes, stream, b_lo);
 }
 
 extern "C" int ppd_tc_gemm(const ppd_gemm_args* g, int flags, void* workspace, size_t workspace_bytes, void* stream) {
@@ -610,15 +623,16 @@ extern "C" int ppd_tc_gemm_col2im(const ppd_gemm_args* g, const ppd_conv_geom* g
 
 namespace {
 int tc_gemm_impl(const ppd_gemm_args* g, int flags, const ppd_conv_geom* geom, void* workspace, size_t workspace_bytes,
-                 void* stream) {
+                 void* stream, const float* b_lo) {
     const int transpose_out = flags & PPD_TC_TRANSPOSE_OUT;
     const int split3 = (flags & PPD_TC_SPLIT3) ? 1 : 0;
     PPD_REQUIRE(ppd_tc_gemm_supported(g), "operands must be 16-byte aligned with leading dimensions that are multiples of 4");
     PPD_REQUIRE(geom || (transpose_out ? g->ldc >= g->I : g->ldc >= g->J), "bad ldc");
-    if (split3 && g_persistent && !geom) {
+    PPD_REQUIRE(!b_lo || (split3 && !geom), "pre-split B needs the persistent 3xTF32 kernel");
+    if (split3 && (g_persistent || b_lo) && !geom) {
         ppd::tca::Plan tp;
         cudaStream_t ts = ppd::as_stream(stream);
-        int trc = ppd::tca::launch(g, transpose_out, nullptr, workspace, workspace_bytes, ts, &tp);
+        int trc = ppd::tca::launch(g, transpose_out, b_lo, workspace, workspace_bytes, ts, &tp);
         if (trc || tp.splits == 1) return trc;
         int64_t nb = (g->I * g->J + 255) / 256;
         if (nb > 4 * ppd::kNumSMs) nb = 4 * ppd::kNumSMs;

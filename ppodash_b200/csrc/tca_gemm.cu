@@ -137,8 +137,10 @@ struct Item { int64_t i0, j0, kk_begin; int nkb; int z; };
 #ifdef PPD_TCA_TRACE
 __device__ long long* g_trace = nullptr;
 #define TCA_TRACE(it_, slot_) do { if (g_trace && blockIdx.x == 0 && (it_) < 256 && lane == 0) g_trace[(it_) * 16 + (slot_)] = clock64(); } while (0)
+#define TCA_TRACE1(it_, slot_) do { if (g_trace && blockIdx.x == 0 && (it_) < 256) g_trace[(it_) * 16 + (slot_)] = clock64(); } while (0)
 #else
 #define TCA_TRACE(it_, slot_) do { } while (0)
+#define TCA_TRACE1(it_, slot_) do { } while (0)
 #endif
 
 __device__ __forceinline__ Item decode(const Args& a, int w) {
@@ -232,6 +234,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const uint32_t s = it % kSA;
                 mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
                 if (elect_one()) {
+                    TCA_TRACE1(it, 0);
                     mbar_expect_tx(&full_a[s], a_bytes);
                     uint8_t* sa = smemA + s * a_bytes;
                     if (!a.a_mn) tma_load_2d(&tmA, &full_a[s], sa, kk, (int)t.i0);     // box {32 k, 128 rows}, 128B swizzle
@@ -250,6 +253,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const uint32_t s = it % kSB;
                 mbar_wait(&empty_b[s], ((it / kSB) & 1u) ^ 1u);
                 if (elect_one()) {
+                    TCA_TRACE1(it, 1);
                     mbar_expect_tx(&full_b[s], a.b_presplit ? 2 * b_bytes : b_bytes);
                     uint8_t* sb = smemB + s * 2 * b_bytes;
                     if (!a.b_mn) {
@@ -287,6 +291,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (a.b_presplit) mbar_wait(&full_b[s], (it / kSB) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
+                    TCA_TRACE1(it, 8);
                     const uint64_t db = bdesc0 + (uint64_t)((s * 2u * b_bytes) >> 4);
                     const uint32_t ta = tmem_base + kTaCol0 + ts * 64u;
 #pragma unroll
@@ -296,6 +301,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     umma_commit(&ta_empty[ts]);
                     umma_commit(&empty_b[s]);
+                    TCA_TRACE1(it, 9);
                 }
                 __syncwarp();
             }
@@ -496,6 +502,31 @@ extern "C" int ppd_tca_set_trace(void* dev_ptr) {
     return (int)cudaMemcpyToSymbol(g_trace, &dev_ptr, sizeof(void*));
 }
 #endif
+
+namespace {
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, uint4* __restrict__ hi, uint4* __restrict__ lo, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        const float4 v = x[i];
+        uint4 h, l;
+        split_tf32(v.x, h.x, l.x);
+        split_tf32(v.y, h.y, l.y);
+        split_tf32(v.z, h.z, l.z);
+        split_tf32(v.w, h.w, l.w);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+}  // namespace
+
+int split_operand(const float* x, float* hi, float* lo, int64_t n, cudaStream_t s) {
+    const int64_t n4 = n / 4;
+    int64_t nb = (n4 + 255) / 256;
+    if (nb > 8 * kNumSMs) nb = 8 * kNumSMs;
+    if (nb < 1) nb = 1;
+    split_tf32_kernel<<<(unsigned)nb, 256, 0, s>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint4*>(hi),
+                                                   reinterpret_cast<uint4*>(lo), n4);
+    return launch_status("split_tf32_kernel");
+}
 
 int make_map_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
                 CUtensorMapSwizzle swz) {

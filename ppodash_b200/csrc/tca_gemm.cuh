@@ -43,5 +43,8 @@ int make_map_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, i
 int launch(const ppd_gemm_args* g, int transpose_out, const float* b_lo, void* workspace, size_t workspace_bytes,
            cudaStream_t s, Plan* plan_out);
 
+// hi = TF32(x), lo = TF32(x - hi) with the kernel's rounding; n a multiple of 4, pointers 16-byte aligned.
+int split_operand(const float* x, float* hi, float* lo, int64_t n, cudaStream_t s);
+
 }  // namespace tca
 }  // namespace ppd

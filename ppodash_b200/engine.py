@@ -186,6 +186,9 @@ class PolicyEngine:
                     param.grad = gview
                 self.segs[name] = _Seg(name, o, numel, None, view)
         self.flat, self.flat_grad, self.device = flat, grad, dev
+        # TF32 hi / residual copies of the parameters (ppd_split_tf32): weight operands of the 3xTF32 GEMMs are split
+        # once per forward pass instead of once per tile inside the kernel
+        self.flat_hi, self.flat_lo = torch.empty_like(flat), torch.empty_like(flat)
         if old_state is None or old_state["exp_avg"].numel() != total or old_state["exp_avg"].device != dev:
             self.adam_state = dict(exp_avg=torch.zeros(total, device=dev), exp_avg_sq=torch.zeros(total, device=dev), step=0)
         self._buffers = {}
@@ -262,7 +265,16 @@ class PolicyEngine:
         return t[:n].view(*shape)
 
     # ------------------------------------------------------------------ kernel wrappers
-    def _gemm(self, A, lda, a_k, B, ldb, b_k, C, ldc, I, J, KK, bias=None, mask=None, ldm=0, relu=0, acc=0):
+    def split_params(self):
+        """hi = TF32(w), lo = TF32(w - hi) for every parameter, in one launch over the flat buffer."""
+        if self.precision != "tf32x3":
+            return
+        n = self.n_params
+        check(lib().ppd_split_tf32(self.flat.data_ptr(), self.flat_hi.data_ptr(), self.flat_lo.data_ptr(), n, self.stream),
+              "split_tf32")
+
+    def _gemm(self, A, lda, a_k, B, ldb, b_k, C, ldc, I, J, KK, bias=None, mask=None, ldm=0, relu=0, acc=0, b_param=False):
+        """b_param: B is a view of the flat parameter buffer (its pre-split hi / lo copies are used in tf32x3 mode)."""
         g = GemmArgs()
         g.A, g.lda, g.a_kmajor = A.data_ptr(), lda, a_k
         g.B, g.ldb, g.b_kmajor = B.data_ptr(), ldb, b_k
@@ -282,6 +294,12 @@ class PolicyEngine:
                 g.I, g.J = J, I
                 flags |= 1
             ws = self._ws(L.ppd_tc_gemm_workspace(g.I, g.J, KK), "tcgemm")
+            if b_param and self.precision == "tf32x3" and not (flags & 1):
+                off = B.data_ptr() - self.flat.data_ptr()
+                g.B = self.flat_hi.data_ptr() + off
+                check(L.ppd_tc_gemm_bsplit(ctypes.byref(g), self.flat_lo.data_ptr() + off, flags, ws.data_ptr(), ws.numel(),
+                                           self.stream), "tc_gemm_bsplit")
+                return
             check(L.ppd_tc_gemm(ctypes.byref(g), flags, ws.data_ptr(), ws.numel(), self.stream), "tc_gemm")
             return
         ws = self._ws(L.ppd_sgemm_workspace(I, J, KK), "gemm")
@@ -363,14 +381,14 @@ class PolicyEngine:
         c1, c2, c3 = cols[0][off * s1 * s1:], cols[1][off * s2 * s2:], cols[2][off * s3 * s3:]
         st = self.stream
         check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, c1.data_ptr(), K1, st), "im2col1")
-        self._gemm(c1, K1, 1, self.seg("conv1.w"), K1, 1, a1[r0:], 32, n * s1 * s1, 32, K1, bias=self.seg("conv1.b"), relu=1)
+        self._gemm(c1, K1, 1, self.seg("conv1.w"), K1, 1, a1[r0:], 32, n * s1 * s1, 32, K1, bias=self.seg("conv1.b"), relu=1, b_param=True)
         check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, c2.data_ptr(), K2, st), "im2col2")
-        self._gemm(c2, K2, 1, self.seg("conv2.w"), K2, 1, a2[r0:], 64, n * s2 * s2, 64, K2, bias=self.seg("conv2.b"), relu=1)
+        self._gemm(c2, K2, 1, self.seg("conv2.w"), K2, 1, a2[r0:], 64, n * s2 * s2, 64, K2, bias=self.seg("conv2.b"), relu=1, b_param=True)
         check(L.ppd_im2col_nhwc(a2[r0:].data_ptr(), n, s2, s2, 64, 3, 3, 1, c3.data_ptr(), K3, st), "im2col3")
-        self._gemm(c3, K3, 1, self.seg("conv3.w"), K3, 1, a3[r0:], 32, n * s3 * s3, 32, K3, bias=self.seg("conv3.b"), relu=1)
+        self._gemm(c3, K3, 1, self.seg("conv3.w"), K3, 1, a3[r0:], 32, n * s3 * s3, 32, K3, bias=self.seg("conv3.b"), relu=1, b_param=True)
         check(L.ppd_batched_transpose(a3[r0:].data_ptr(), n, s3 * s3, 32, a3t[r0:].data_ptr(), st), "transpose")
         self._gemm(a3t[r0:], self.flat_dim, 1, self.seg("fc.w"), self.flat_dim, 1, feat[r0:], ldf, n, H, self.flat_dim,
-                   bias=self.seg("fc.b"), relu=1)
+                   bias=self.seg("fc.b"), relu=1, b_param=True)
 
     def _trunk_backward_rows(self, obs, r0, r1, cols, off, cols_valid, dfeat, ldd, acc):
         """rows [r0, r1): dfeat (already masked by feat > 0) -> FC / conv gradients, written to (acc=0, first chunk) or
@@ -394,7 +412,7 @@ class PolicyEngine:
         with self._Side(self):
             self._gemm(dfeat[r0:], ldd, 0, a3t[r0:], fd, 0, self.seg("fc.w", True), fd, H, fd, n, acc=acc)
             self._colsum(dfeat[r0:], ldd, n, H, self.seg("fc.b", True), acc)
-        self._gemm(dfeat[r0:], ldd, 1, self.seg("fc.w"), fd, 0, da3t[r0:], fd, n, fd, H, mask=a3t[r0:], ldm=fd)
+        self._gemm(dfeat[r0:], ldd, 1, self.seg("fc.w"), fd, 0, da3t[r0:], fd, n, fd, H, mask=a3t[r0:], ldm=fd, b_param=True)
         check(L.ppd_batched_transpose(da3t[r0:].data_ptr(), n, 32, s3 * s3, dy3[r0:].data_ptr(), self.stream), "transpose")
         # conv3
         if not cols_valid:
@@ -445,6 +463,7 @@ class PolicyEngine:
         """CNNBase.forward + both heads (model.py:192-199, distributions.py:66-68).
         Returns dict(value [B,1], z [B,A+1] (logits | value), rnn_hxs, feats)."""
         obs, vobs, h0, m, B = self._prep(visual, vector, rnn_hxs, masks)
+        self.split_params()
         L = lib()
         H, A = self.H, self.A
         tag = "t_" if keep else "i_"
@@ -473,7 +492,7 @@ class PolicyEngine:
                 n = r1 - r0
                 self._trunk_forward_rows(obs, r0, r1, cols, r0 if cols[3] else 0, xcat, Ipad)
                 self._gemm(xcat[r0:], Ipad, 1, self.seg("gru.w_ih"), Ipad, 1, gi[r0:], 3 * H, n, 3 * H, Ipad,
-                           bias=self.seg("gru.b_ih"))
+                           bias=self.seg("gru.b_ih"), b_param=True)
                 last = ci == len(chunks) - 1
                 h_in = h0 if ci == 0 else hs[r0 - E:r0]
                 svp = [s_[r0:].data_ptr() for s_ in sv] if keep else [None] * 4
@@ -581,7 +600,7 @@ class PolicyEngine:
                         ev.record(gstream)
                     main.wait_event(ev)
                 # d(feat) = dgi W_ih[:, :H], masked by feat > 0 (ReLU of the FC layer)
-                self._gemm(dgi[r0:], 3 * H, 1, w_ih, Ipad, 0, dfeat[r0:], H, n, H, 3 * H, mask=xcat[r0:], ldm=Ipad)
+                self._gemm(dgi[r0:], 3 * H, 1, w_ih, Ipad, 0, dfeat[r0:], H, n, H, 3 * H, mask=xcat[r0:], ldm=Ipad, b_param=True)
                 self._trunk_backward_rows(sv["obs"], r0, r1, cols, r0 if cols[3] else 0, cols[3], dfeat, H,
                                           0 if ci == len(chunks) - 1 else 1)
             # ---- GRU parameter gradients over all T*E rows (side stream; dgi complete because main waited for it)

@@ -48,6 +48,13 @@ def run(name, I, J, KK, ak, bk, mode):
     else:
         ws = torch.empty(max(256, L.ppd_tc_gemm_workspace(g.I, g.J, KK)), dtype=torch.uint8, device=DEV)
         fn = lambda: _lib.check(L.ppd_tc_gemm(ctypes.byref(g), flags, ws.data_ptr(), ws.numel(), st))
+        if mode == "tf32x3" and os.environ.get("PPD_BSPLIT") == "1" and not (flags & 1) and ak:
+            # weights as B: pre-split once (forward / dgrad products)
+            Bhi, Blo = torch.empty_like(Bm), torch.empty_like(Bm)
+            _lib.check(L.ppd_split_tf32(Bm.data_ptr(), Bhi.data_ptr(), Blo.data_ptr(), Bm.numel(), st))
+            g.B = Bhi.data_ptr()
+            keep = (Bhi, Blo)
+            fn = lambda: _lib.check(L.ppd_tc_gemm_bsplit(ctypes.byref(g), keep[1].data_ptr(), flags, ws.data_ptr(), ws.numel(), st))
     med, best = time_kernel(fn, iters=8, warmup=2)
     bytes_ = 4.0 * (I * KK + J * KK + I * J)
     return dict(gemm=name, mode=mode, ms=round(med, 4), gbs=round(bytes_ / med / 1e6, 1), tflops=round(2.0 * I * J * KK / med / 1e9, 2))
