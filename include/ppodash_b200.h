@@ -200,18 +200,30 @@ int ppd_sgemm(const ppd_gemm_args* g, void* workspace, size_t workspace_bytes, v
 size_t ppd_tc_gemm_workspace(int64_t I, int64_t J, int64_t KK);
 int ppd_tc_gemm_supported(const ppd_gemm_args* g);
 int ppd_tc_gemm(const ppd_gemm_args* g, int flags, void* workspace, size_t workspace_bytes, void* stream);
+typedef struct ppd_conv_geom { int B, H, W, C, kh, kw, stride; } ppd_conv_geom;   /* input tensor [B,H,W,C] and the filter */
 /* 3xTF32 with a PRE-SPLIT B operand (weights): g->B holds hi = TF32(B), b_lo the residuals TF32(B - hi), same layout
  * and leading dimension; ppd_split_tf32 produces both (n a multiple of 4, 16-byte aligned).  The kernel then neither
  * re-splits B per tile nor fences shared memory for it: the weights of a minibatch are split once, after the optimiser step. */
 int ppd_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 int ppd_tc_gemm_bsplit(const ppd_gemm_args* g, const float* b_lo, int flags, void* workspace, size_t workspace_bytes,
                        void* stream);
+/* Implicit-GEMM NHWC convolution, 3xTF32 (fp32-level accuracy), no im2col / col2im matrices in HBM: the persistent tcgen05
+ * kernel loads the patch rows of a tile straight from the activation tensor with 4-D TMA boxes (an overlapping-stride
+ * im2col VIEW).  geom describes the INPUT tensor x / dx [B,H,W,C] and the filter; weights are [Cout, (ky,kx,c)] pre-split
+ * (ppd_split_tf32).  Requires kw*C % 32 == 0 (forward), kh == kw, kh | H | W multiples of the stride and Cout % 32 == 0
+ * (dgrad), C and Cout in {32, 64} on the output side.
+ *   fwd  : out[B*OH*OW, Cout] = (ReLU)(conv(x) + bias)                      replaces nn.Conv2d forward, PKG/model.py:177-178
+ *   dgrad: dx[B,H,W,C] = (act_mask > 0) * conv_transpose(dy[B,OH,OW,Cout])  gather form over the stride's parity classes:
+ *          every dx element is written once (no atomics, no memset, ReLU backward fused); deterministic. */
+int ppd_conv_fwd_nhwc(const float* x, const ppd_conv_geom* geom, int Cout, const float* w_hi, const float* w_lo,
+                      const float* bias, int relu, float* out, void* stream);
+int ppd_conv_dgrad_nhwc(const float* dy, const ppd_conv_geom* geom, int Cout, const float* w_hi, const float* w_lo,
+                        const float* act_mask, float* dx, void* stream);
 /* dgrad of an NHWC convolution with col2im fused into the epilogue: the product dY[M,N] W[N,(ky,kx,c)] is not
  * stored but scatter-added (red.global.add.v4.f32) into dx[B,H,W,C], which the caller has zeroed; follow with
  * ppd_relu_mask.  Replaces the dcols round trip through HBM (write + col2im read).  g->C = dx, g->ldc ignored.
  * Summation order of the overlapping taps is not fixed (fp32 atomics); the "fp32" mode keeps the deterministic
  * ppd_sgemm + ppd_col2im_nhwc pair. */
-typedef struct ppd_conv_geom { int B, H, W, C, kh, kw, stride; } ppd_conv_geom;   /* input tensor [B,H,W,C] and the filter */
 int ppd_tc_gemm_col2im(const ppd_gemm_args* g, const ppd_conv_geom* geom, int flags, void* stream);
 /* x[i] = act[i] > 0 ? x[i] : 0 */
 int ppd_relu_mask(float* x, const float* act, int64_t n, void* stream);

@@ -600,6 +600,18 @@ extern "C" int ppd_split_tf32(const float* x, float* hi, float* lo, int64_t n, v
     return ppd::tca::split_operand(x, hi, lo, n, ppd::as_stream(stream));
 }
 
+extern "C" int ppd_conv_fwd_nhwc(const float* x, const ppd_conv_geom* geom, int Cout, const float* w_hi, const float* w_lo,
+                                 const float* bias, int relu, float* out, void* stream) {
+    PPD_REQUIRE(x && geom && w_hi && w_lo && out, "null pointer");
+    return ppd::tca::conv_forward(x, geom, Cout, w_hi, w_lo, bias, relu, out, ppd::as_stream(stream));
+}
+
+extern "C" int ppd_conv_dgrad_nhwc(const float* dy, const ppd_conv_geom* geom, int Cout, const float* w_hi, const float* w_lo,
+                                   const float* act_mask, float* dx, void* stream) {
+    PPD_REQUIRE(dy && geom && w_hi && w_lo && dx, "null pointer");
+    return ppd::tca::conv_dgrad(dy, geom, Cout, w_hi, w_lo, act_mask, dx, ppd::as_stream(stream));
+}
+
 extern "C" int ppd_tc_gemm_bsplit(const ppd_gemm_args* g, const float* b_lo, int flags, void* workspace, size_t workspace_bytes,
                                   void* stream) {
     PPD_REQUIRE(g && b_lo && (flags & PPD_TC_SPLIT3), "pre-split B operands are a 3xTF32 feature");

@@ -59,6 +59,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -131,7 +137,7 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int b_mn) {
     return d;
 }
 
-struct Item { int64_t i0, j0, kk_begin; int nkb; int z; };
+struct Item { int64_t i0, j0, kk_begin; int nkb; int z; int cls, seg0, nvalid; };
 
 // Pipeline timeline of CTA 0 (debug builds only: -DPPD_TCA_TRACE): trace[(it * 16 + slot)] = clock64()
 #ifdef PPD_TCA_TRACE
@@ -145,6 +151,15 @@ __device__ long long* g_trace = nullptr;
 
 __device__ __forceinline__ Item decode(const Args& a, int w) {
     Item it;
+    if (a.conv.mode) {
+        it.cls = w / a.conv.ntile_class;
+        it.seg0 = (w - it.cls * a.conv.ntile_class) * a.conv.nseg;
+        it.nvalid = min(a.conv.nseg, a.conv.nseg_class - it.seg0);
+        it.i0 = 0; it.j0 = 0; it.kk_begin = 0; it.z = 0;
+        it.nkb = a.conv.nkb;
+        return it;
+    }
+    it.cls = it.seg0 = it.nvalid = 0;
     const int n = w % a.num_n;
     const int r = w / a.num_n;
     const int m = r % a.num_m;
@@ -235,10 +250,31 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
                 if (elect_one()) {
                     TCA_TRACE1(it, 0);
-                    mbar_expect_tx(&full_a[s], a_bytes);
                     uint8_t* sa = smemA + s * a_bytes;
-                    if (!a.a_mn) tma_load_2d(&tmA, &full_a[s], sa, kk, (int)t.i0);     // box {32 k, 128 rows}, 128B swizzle
-                    else         tma_load_2d(&tmA, &full_a[s], sa, (int)t.i0, kk);     // box {128 rows, 32 k}, no swizzle
+                    if (a.conv.mode) {
+                        const ConvA& cv = a.conv;
+                        const uint32_t seg_bytes = (uint32_t)cv.segw * 128u;
+                        mbar_expect_tx(&full_a[s], (uint32_t)t.nvalid * seg_bytes);
+                        int c0, dx1, dy2;               // inner coordinate, pixel offset, row offset shared by the segments
+                        if (cv.mode == 1) {
+                            const int ky = kb / cv.kpk;
+                            c0 = (kb - ky * cv.kpk) * 32; dx1 = 0; dy2 = ky;
+                        } else {
+                            const int tap = kb / cv.kpk;
+                            const int dky = tap / cv.T, dkx = tap - dky * cv.T;
+                            c0 = (kb - tap * cv.kpk) * 32; dx1 = -dkx; dy2 = -dky;
+                        }
+                        const uint32_t dst0 = smem_u32(sa);
+                        for (int g = 0; g < t.nvalid; ++g) {
+                            const int sg = t.seg0 + g;
+                            const int b = sg / cv.rows_per_img, row = sg - b * cv.rows_per_img;
+                            tma_load_4d(&tmA, &full_a[s], dst0 + g * seg_bytes, c0, dx1, (cv.mode == 1 ? row * cv.s : row) + dy2, b);
+                        }
+                    } else {
+                        mbar_expect_tx(&full_a[s], a_bytes);
+                        if (!a.a_mn) tma_load_2d(&tmA, &full_a[s], sa, kk, (int)t.i0);     // box {32 k, 128 rows}, 128B swizzle
+                        else         tma_load_2d(&tmA, &full_a[s], sa, (int)t.i0, kk);     // box {128 rows, 32 k}, no swizzle
+                    }
                 }
                 __syncwarp();
             }
@@ -256,7 +292,18 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     TCA_TRACE1(it, 1);
                     mbar_expect_tx(&full_b[s], a.b_presplit ? 2 * b_bytes : b_bytes);
                     uint8_t* sb = smemB + s * 2 * b_bytes;
-                    if (!a.b_mn) {
+                    if (a.conv.mode == 2) {
+                        // W [Cout, (ky, kx, c)]: box {32 c, 32 couts} of filter tap (ky, kx) = (py + s dky, px + s dkx)
+                        const ConvA& cv = a.conv;
+                        const int tap = kb / cv.kpk, cch = kb - tap * cv.kpk;
+                        const int dky = tap / cv.T, dkx = tap - dky * cv.T;
+                        const int py = t.cls / cv.s, px = t.cls - py * cv.s;
+                        const int col = ((py + cv.s * dky) * cv.KW + (px + cv.s * dkx)) * cv.Cin;
+                        for (int q = 0; q < bn / 32; ++q) {
+                            tma_load_2d(&tmB, &full_b[s], sb + q * 4096, col + 32 * q, cch * 32);
+                            tma_load_2d(&tmBlo, &full_b[s], sb + b_bytes + q * 4096, col + 32 * q, cch * 32);
+                        }
+                    } else if (!a.b_mn) {
                         tma_load_2d(&tmB, &full_b[s], sb, kk, (int)t.j0);               // box {32 k, bn rows}
                         if (a.b_presplit) tma_load_2d(&tmBlo, &full_b[s], sb + b_bytes, kk, (int)t.j0);
                     } else {
@@ -390,6 +437,23 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(&acc_full[acc], (tile_it >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t i = t.i0 + q * 32 + lane;
+            bool row_ok = i < a.I;
+            int64_t crow_off = i * a.ldc + t.j0, mrow_off = i * a.ldm + t.j0;
+            if (a.conv.mode) {
+                const ConvA& cv = a.conv;
+                const int r = q * 32 + lane;
+                row_ok = r < t.nvalid * cv.segw;
+                if (cv.mode == 1) {
+                    crow_off = ((int64_t)t.seg0 * cv.segw + r) * a.ldc;            // output pixels of whole rows are contiguous
+                } else {
+                    const int g = r / cv.segw, j = r - g * cv.segw;
+                    const int sg = t.seg0 + g;
+                    const int b = sg / cv.rows_per_img, ii = sg - b * cv.rows_per_img;
+                    const int py = t.cls / cv.s, px = t.cls - py * cv.s;
+                    crow_off = (((int64_t)b * cv.Hin + (cv.s * ii + py)) * cv.Win + (cv.s * j + px)) * cv.Cin;
+                }
+                mrow_off = crow_off;
+            }
             for (int c0 = 0; c0 < bn; c0 += 32) {
                 float v[32];
                 {
@@ -441,9 +505,9 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             *p = a.accumulate ? (*p + x) : x;
                         }
                     }
-                } else if (i < a.I) {
-                    float* crow = a.C + i * a.ldc + jb;
-                    const float* mrow = a.mask ? a.mask + i * a.ldm + jb : nullptr;
+                } else if (row_ok) {
+                    float* crow = a.C + crow_off + c0;
+                    const float* mrow = a.mask ? a.mask + mrow_off + c0 : nullptr;
                     const bool vec = (jb + 31 < a.J) && ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) &&
                                      (!mrow || (((a.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)));
                     if (vec) {
@@ -542,6 +606,90 @@ int make_map_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, i
     return 0;
 }
 
+// N-D fp32 tensor map (dims / strides innermost first; strides in bytes for dims 1..nd-1), OOB elements read as zero.
+static int make_map_nd(CUtensorMap* m, const float* base, int nd, const cuuint64_t* dims, const cuuint64_t* strides,
+                       const cuuint32_t* box, CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("tca_gemm: cuTensorMapEncodeTiled not available"); return PPD_EINVAL; }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)nd, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tca_gemm: cuTensorMapEncodeTiled (%d-d) failed (%d)", nd, (int)r); return PPD_EINVAL; }
+    return 0;
+}
+
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, Args& a, cudaStream_t s) {
+    a.a_mn = 0; a.b_presplit = 1; a.transpose_out = 0; a.accumulate = 0; a.partial = nullptr;
+    a.num_m = 1; a.num_n = 1; a.splits = 1; a.kk_per_split = a.KK; a.ldm = a.ldc;
+    int sb_stages = (int)((kSmemBudget - 1024 - (size_t)kSA * BM * BK * 4) / ((size_t)2 * a.bn * BK * 4));
+    if (sb_stages > kMaxSB) sb_stages = kMaxSB;
+    a.sb_stages = sb_stages;
+    const size_t smem = (size_t)kSA * BM * BK * 4 + (size_t)sb_stages * 2 * a.bn * BK * 4 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(tca_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    if (e != cudaSuccess) { set_error("tca conv: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
+    const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+    tca_gemm_kernel<<<grid, kThreads, smem, s>>>(tmA, tmB, tmBlo, a);
+    return launch_status("tca_gemm_kernel(conv)");
+}
+
+int conv_forward(const float* x, const ppd_conv_geom* g, int Cout, const float* w_hi, const float* w_lo, const float* bias, int relu,
+                 float* out, cudaStream_t s) {
+    const int OH = (g->H - g->kh) / g->stride + 1, OW = (g->W - g->kw) / g->stride + 1;
+    const int rowf = g->kw * g->C;                                   // contiguous floats of one filter row in NHWC
+    PPD_REQUIRE(rowf % 32 == 0 && (Cout == 32 || Cout == 64) && OW >= 1 && OW <= BM && OH >= 1, "unsupported convolution shape");
+    PPD_REQUIRE(!(((uintptr_t)x | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)out) & 15), "pointers must be 16-byte aligned");
+    const int64_t K = (int64_t)g->kh * rowf;
+    CUtensorMap tmA, tmB, tmBlo;
+    cuuint64_t dims[4] = {(cuuint64_t)rowf, (cuuint64_t)OW, (cuuint64_t)g->H, (cuuint64_t)g->B};
+    cuuint64_t str[3] = {(cuuint64_t)g->stride * g->C * 4, (cuuint64_t)g->W * g->C * 4, (cuuint64_t)g->H * g->W * g->C * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)OW, 1, 1};
+    int rc = make_map_nd(&tmA, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if ((rc = make_map_2d(&tmB, w_hi, Cout, K, K, BK, Cout, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_map_2d(&tmBlo, w_lo, Cout, K, K, BK, Cout, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    Args a = {};
+    a.C = out; a.ldc = Cout; a.I = (int64_t)g->B * OH * OW; a.J = Cout; a.KK = K;
+    a.bias = bias; a.mask = nullptr; a.relu = relu;
+    a.bn = Cout; a.b_mn = 0;
+    ConvA& cv = a.conv;
+    cv.mode = 1; cv.segw = OW; cv.nseg = BM / OW; cv.nseg_class = g->B * OH;
+    cv.ntile_class = (cv.nseg_class + cv.nseg - 1) / cv.nseg;
+    cv.rows_per_img = OH; cv.s = g->stride; cv.kpk = rowf / 32; cv.T = 0; cv.KW = g->kw; cv.Cin = g->C; cv.Hin = g->H; cv.Win = g->W;
+    cv.nkb = g->kh * cv.kpk;
+    a.total_items = cv.ntile_class;
+    return launch_conv(tmA, tmB, tmBlo, a, s);
+}
+
+int conv_dgrad(const float* dy, const ppd_conv_geom* g, int Cout, const float* w_hi, const float* w_lo, const float* act_mask,
+               float* dx, cudaStream_t s) {
+    const int st = g->stride;
+    const int OH = (g->H - g->kh) / st + 1, OW = (g->W - g->kw) / st + 1;
+    PPD_REQUIRE(g->kh == g->kw && g->kh % st == 0 && g->H % st == 0 && g->W % st == 0, "filter and input sizes must be multiples of the stride");
+    PPD_REQUIRE(Cout % 32 == 0 && (g->C == 32 || g->C == 64) && g->W / st <= BM, "unsupported convolution shape");
+    PPD_REQUIRE(!(((uintptr_t)dy | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)dx | (uintptr_t)act_mask) & 15), "pointers must be 16-byte aligned");
+    const int Hq = g->H / st, Wq = g->W / st;
+    const int64_t K = (int64_t)g->kh * g->kw * g->C;                 // columns of the weight matrix [Cout, (ky, kx, c)]
+    CUtensorMap tmA, tmB, tmBlo;
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)g->B};
+    cuuint64_t str[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)OW * Cout * 4, (cuuint64_t)OH * OW * Cout * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)Wq, 1, 1};
+    int rc = make_map_nd(&tmA, dy, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if ((rc = make_map_2d(&tmB, w_hi, Cout, K, K, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map_2d(&tmBlo, w_lo, Cout, K, K, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    Args a = {};
+    a.C = dx; a.ldc = g->C; a.I = (int64_t)g->B * g->H * g->W; a.J = g->C; a.KK = (int64_t)(g->kh / st) * (g->kw / st) * Cout;
+    a.bias = nullptr; a.mask = act_mask; a.relu = 0;
+    a.bn = g->C; a.b_mn = 1;
+    ConvA& cv = a.conv;
+    cv.mode = 2; cv.segw = Wq; cv.nseg = BM / Wq; cv.nseg_class = g->B * Hq;
+    cv.ntile_class = (cv.nseg_class + cv.nseg - 1) / cv.nseg;
+    cv.rows_per_img = Hq; cv.s = st; cv.kpk = Cout / 32; cv.T = g->kh / st; cv.KW = g->kw; cv.Cin = g->C; cv.Hin = g->H; cv.Win = g->W;
+    cv.nkb = cv.T * cv.T * cv.kpk;
+    a.total_items = st * st * cv.ntile_class;
+    return launch_conv(tmA, tmB, tmBlo, a, s);
+}
+
 Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_avail, bool limit) {
     Plan p;
     p.bn = J <= 32 ? 32 : 64;          // the MMAs run at N = 2 bn ([hi | lo] of B side by side)
@@ -585,7 +733,7 @@ int launch(const ppd_gemm_args* g, int transpose_out, const float* b_lo, void* w
         if (rc) return rc;
     }
     if (!b_lo) tmBlo = tmB;
-    Args a;
+    Args a = {};
     a.C = g->C; a.ldc = g->ldc; a.I = g->I; a.J = g->J; a.KK = g->KK;
     a.bias = g->bias; a.mask = g->mask; a.ldm = g->ldm; a.relu = g->relu; a.accumulate = g->accumulate;
     a.transpose_out = transpose_out;

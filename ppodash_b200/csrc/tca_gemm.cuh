@@ -20,6 +20,29 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = 0, kAccStride = 128;   // two accumulators of up to 128 columns
 constexpr uint32_t kTaCol0 = 256;
 
+// Implicit-GEMM convolution: the A tile is not a slice of a matrix but `nseg` SEGMENTS of `segw` pixels, each loaded by
+// one 4-D TMA box {32 floats, segw pixels, 1, 1} straight from the NHWC activation tensor (OOB coordinates read as zero).
+//   mode 1, forward:  segment = output row (b, oy); k-block kb = 32 floats of the (ky, kx, c) patch: filter row
+//                     ky = kb / kpk, offset (kb % kpk) * 32 inside the KW*C contiguous floats of that row.
+//                     A map: dims {KW*C, OW (stride s*C), Hin, B} -- overlapping strides, an im2col VIEW of x.
+//   mode 2, dgrad:    gather form, no atomics.  dx pixels are grouped by their parity class (py, px) = (y % s, x % s);
+//                     segment = (b, i) with dx row y = s*i + py and the Wq = Win/s pixels x = s*j + px; k-block kb =
+//                     tap (dky, dkx) of the T x T taps that reach this class (ky = py + s*dky) x 32-channel chunk of dY.
+//                     A map: dY dims {Cout, OWy, OHy, B}; coordinates (chunk*32, -dkx, i - dky, b).
+struct ConvA {
+    int mode;                // 0 = plain GEMM
+    int segw, nseg;          // pixels per segment, segments per tile (nseg * segw <= 128)
+    int nseg_class;          // segments per class
+    int ntile_class;         // tiles per class
+    int rows_per_img;        // forward: OH; dgrad: Hq = Hin / s
+    int s;                   // convolution stride
+    int kpk;                 // forward: k-blocks per filter row; dgrad: k-blocks (32-channel chunks) per tap
+    int T;                   // dgrad: taps per dimension per class (k / s)
+    int KW, Cin;             // dgrad: filter width, input channels
+    int Hin, Win;            // dgrad: dx height / width
+    int nkb;                 // k-blocks per tile
+};
+
 struct Args {
     float* C; int64_t ldc;
     int64_t I, J, KK;
@@ -31,6 +54,7 @@ struct Args {
     float* partial;
     int total_items;
     int sb_stages;
+    ConvA conv;
 };
 
 struct Plan { int bn, num_m, num_n, splits; int64_t kk_per_split; size_t ws; };
@@ -44,6 +68,11 @@ int launch(const ppd_gemm_args* g, int transpose_out, const float* b_lo, void* w
            cudaStream_t s, Plan* plan_out);
 
 // hi = TF32(x), lo = TF32(x - hi) with the kernel's rounding; n a multiple of 4, pointers 16-byte aligned.
+// Implicit-GEMM NHWC convolution forward / dgrad on the same kernel (see ConvA).
+int conv_forward(const float* x, const ppd_conv_geom* g, int Cout, const float* w_hi, const float* w_lo, const float* bias, int relu,
+                 float* out, cudaStream_t s);
+int conv_dgrad(const float* dy, const ppd_conv_geom* g, int Cout, const float* w_hi, const float* w_lo, const float* act_mask,
+               float* dx, cudaStream_t s);
 int split_operand(const float* x, float* hi, float* lo, int64_t n, cudaStream_t s);
 
 }  // namespace tca

@@ -312,3 +312,69 @@ def test_colsum_multi():
     _lib.check(L.ppd_colsum_multi(segs, len(shapes), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
     for o, w, (I, J, ld) in zip(outs, want, shapes):
         np.testing.assert_allclose(o.cpu().numpy(), w.numpy(), rtol=1e-4, atol=2e-3 * np.sqrt(I) / 30)
+
+
+# --------------------------------------------------------------------------- implicit-GEMM NHWC convolutions (TMEM-A kernel)
+def _split(w):
+    L = _lib.lib()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _lib.check(L.ppd_split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), _lib.stream_ptr()))
+    return hi, lo
+
+
+def test_split_tf32_is_exact_and_tf32():
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(4096, generator=g) * torch.logspace(-20, 20, 4096)).to(DEV)
+    hi, lo = _split(x)
+    assert torch.all((hi.view(torch.int32) & 0x1FFF) == 0) and torch.all((lo.view(torch.int32) & 0x1FFF) == 0)   # 10-bit mantissas
+    err = (x.double() - hi.double() - lo.double()).abs()
+    assert torch.all(err <= x.abs().double() * 2.0 ** -21)          # hi + lo carries >= 21 mantissa bits of x
+
+
+@pytest.mark.parametrize("B,H,C,k,s,Cout", [(7, 20, 32, 4, 2, 64), (5, 9, 64, 3, 1, 32), (300, 20, 32, 4, 2, 64), (333, 9, 64, 3, 1, 32),
+                                            (3, 12, 32, 2, 2, 32)])
+def test_conv_fwd_nhwc_implicit_gemm(B, H, C, k, s, Cout):
+    """ppd_conv_fwd_nhwc == ReLU(conv2d + bias) (PKG/model.py:177-178), NHWC in / out, weights (o, ky, kx, c)."""
+    from ppodash_b200._lib import ConvGeom
+    L = _lib.lib()
+    g0 = torch.Generator().manual_seed(B + H + C + k)
+    x = torch.randn(B, H, H, C, generator=g0)
+    w = torch.randn(Cout, k, k, C, generator=g0) / np.sqrt(k * k * C)
+    b = torch.randn(Cout, generator=g0)
+    want = torch.relu(F.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), b.double(), stride=s)).permute(0, 2, 3, 1).float()
+    OH = (H - k) // s + 1
+    xd, wd, bd = x.to(DEV), w.to(DEV).contiguous(), b.to(DEV)
+    hi, lo = _split(wd)
+    out = torch.full((B * OH * OH + 3, Cout), -7.0, device=DEV)
+    geom = ConvGeom(B, H, H, C, k, k, s)
+    _lib.check(L.ppd_conv_fwd_nhwc(xd.data_ptr(), ctypes.byref(geom), Cout, hi.data_ptr(), lo.data_ptr(), bd.data_ptr(), 1,
+                                   out.data_ptr(), _lib.stream_ptr()))
+    got = out[:B * OH * OH].view(B, OH, OH, Cout).cpu()
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 1e-5 * scale        # 3xTF32: fp32-level accuracy
+    assert torch.all(out[B * OH * OH:] == -7.0)
+
+
+@pytest.mark.parametrize("B,H,C,k,s,Cout", [(7, 9, 64, 3, 1, 32), (5, 20, 32, 4, 2, 64), (300, 20, 32, 4, 2, 64), (333, 9, 64, 3, 1, 32),
+                                            (3, 12, 32, 2, 2, 32)])
+def test_conv_dgrad_nhwc_gather_form(B, H, C, k, s, Cout):
+    """ppd_conv_dgrad_nhwc == ReLU'(act) * conv_transpose2d(dy): every dx element written exactly once."""
+    from ppodash_b200._lib import ConvGeom
+    L = _lib.lib()
+    g0 = torch.Generator().manual_seed(B + H + C + 11)
+    OH = (H - k) // s + 1
+    dy = torch.randn(B, OH, OH, Cout, generator=g0)
+    w = torch.randn(Cout, k, k, C, generator=g0) / np.sqrt(Cout)
+    act = torch.randn(B, H, H, C, generator=g0)
+    full = F.conv_transpose2d(dy.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), stride=s)     # [B, C, H', H']
+    want = torch.zeros(B, C, H, H, dtype=torch.float64)
+    want[:, :, :full.shape[2], :full.shape[3]] = full
+    want = (want.permute(0, 2, 3, 1) * (act > 0)).float()
+    dyd, wd, actd = dy.to(DEV), w.to(DEV).contiguous(), act.to(DEV)
+    hi, lo = _split(wd)
+    dx = torch.full((B, H, H, C), 9.0, device=DEV)
+    geom = ConvGeom(B, H, H, C, k, k, s)
+    _lib.check(L.ppd_conv_dgrad_nhwc(dyd.data_ptr(), ctypes.byref(geom), Cout, hi.data_ptr(), lo.data_ptr(), actd.data_ptr(),
+                                     dx.data_ptr(), _lib.stream_ptr()))
+    scale = float(want.abs().max())
+    assert float((dx.cpu() - want).abs().max()) <= 1e-5 * scale
