@@ -219,6 +219,12 @@ int ppd_conv_fwd_nhwc(const float* x, const ppd_conv_geom* geom, int Cout, const
                       const float* bias, int relu, float* out, void* stream);
 int ppd_conv_dgrad_nhwc(const float* dy, const ppd_conv_geom* geom, int Cout, const float* w_hi, const float* w_lo,
                         const float* act_mask, float* dx, void* stream);
+/*   wgrad: dW[Cout, K] (+)= sum over output pixels of dy[pixel, cout] * patch(x)[pixel, k], contraction split over the SMs and
+ *          reduced in a fixed order.  nchw = 0: x is NHWC, patch / weight order (ky,kx,c), kw*C % 64 == 0;
+ *          nchw = 1: x is NCHW (the observations), patch order (c,ky,kx), 8x8 filter (5-D TMA view, no channel padding). */
+size_t ppd_conv_wgrad_workspace(const ppd_conv_geom* geom, int Cout);
+int ppd_conv_wgrad(const float* x, const ppd_conv_geom* geom, int nchw, const float* dy, int Cout, float* dW, int accumulate,
+                   void* workspace, size_t workspace_bytes, void* stream);
 /* dgrad of an NHWC convolution with col2im fused into the epilogue: the product dY[M,N] W[N,(ky,kx,c)] is not
  * stored but scatter-added (red.global.add.v4.f32) into dx[B,H,W,C], which the caller has zeroed; follow with
  * ppd_relu_mask.  Replaces the dcols round trip through HBM (write + col2im read).  g->C = dx, g->ldc ignored.

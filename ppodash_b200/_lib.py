@@ -92,6 +92,8 @@ _PROTOTYPES = {
     "ppd_split_tf32": (c_int, [_P, _P, _P, c_int64, _P]),
     "ppd_conv_fwd_nhwc": (c_int, [_P, POINTER(ConvGeom), c_int, _P, _P, _P, c_int, _P, _P]),
     "ppd_conv_dgrad_nhwc": (c_int, [_P, POINTER(ConvGeom), c_int, _P, _P, _P, _P, _P]),
+    "ppd_conv_wgrad_workspace": (c_size_t, [POINTER(ConvGeom), c_int]),
+    "ppd_conv_wgrad": (c_int, [_P, POINTER(ConvGeom), c_int, _P, c_int, _P, c_int, _P, c_size_t, _P]),
     "ppd_tc_gemm_bsplit": (c_int, [POINTER(GemmArgs), _P, c_int, _P, c_size_t, _P]),
     "ppd_tc_gemm_col2im": (c_int, [POINTER(GemmArgs), POINTER(ConvGeom), c_int, _P]),
     "ppd_relu_mask": (c_int, [_P, _P, c_int64, _P]),

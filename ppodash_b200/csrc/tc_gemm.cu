@@ -612,6 +612,26 @@ extern "C" int ppd_conv_dgrad_nhwc(const float* dy, const ppd_conv_geom* geom, i
     return ppd::tca::conv_dgrad(dy, geom, Cout, w_hi, w_lo, act_mask, dx, ppd::as_stream(stream));
 }
 
+extern "C" size_t ppd_conv_wgrad_workspace(const ppd_conv_geom* geom, int Cout) {
+    return geom ? ppd::tca::conv_wgrad_workspace(geom, Cout) : 0;
+}
+
+extern "C" int ppd_conv_wgrad(const float* x, const ppd_conv_geom* geom, int nchw, const float* dy, int Cout, float* dW, int accumulate,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    PPD_REQUIRE(x && geom && dy && dW, "null pointer");
+    cudaStream_t ts = ppd::as_stream(stream);
+    int splits = 0;
+    int rc = ppd::tca::conv_wgrad(x, geom, nchw, dy, Cout, dW, accumulate, workspace, workspace_bytes, ts, &splits);
+    if (rc) return rc;
+    const int64_t K = (int64_t)geom->kh * geom->kw * geom->C;
+    int64_t nb = (K * Cout + 255) / 256;
+    if (nb > 4 * ppd::kNumSMs) nb = 4 * ppd::kNumSMs;
+    // partials are [split][K, Cout]; dW is [Cout, K]: reduce and store transposed
+    tc_splitk_reduce_kernel<<<(unsigned)nb, 256, 0, ts>>>(reinterpret_cast<float*>(workspace), splits, K, Cout, dW, K, nullptr, nullptr, 0,
+                                                          0, accumulate, 1);
+    return ppd::launch_status("tc_splitk_reduce_kernel");
+}
+
 extern "C" int ppd_tc_gemm_bsplit(const ppd_gemm_args* g, const float* b_lo, int flags, void* workspace, size_t workspace_bytes,
                                   void* stream) {
     PPD_REQUIRE(g && b_lo && (flags & PPD_TC_SPLIT3), "pre-split B operands are a 3xTF32 feature");

@@ -65,6 +65,12 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -137,7 +143,7 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int b_mn) {
     return d;
 }
 
-struct Item { int64_t i0, j0, kk_begin; int nkb; int z; int cls, seg0, nvalid; };
+struct Item { int64_t i0, j0, kk_begin; int nkb; int z; int cls, seg0, nvalid, kb0; };
 
 // Pipeline timeline of CTA 0 (debug builds only: -DPPD_TCA_TRACE): trace[(it * 16 + slot)] = clock64()
 #ifdef PPD_TCA_TRACE
@@ -151,6 +157,16 @@ __device__ long long* g_trace = nullptr;
 
 __device__ __forceinline__ Item decode(const Args& a, int w) {
     Item it;
+    it.kb0 = 0;
+    if (a.conv.mode == 3) {
+        const int mt = w % a.num_m;
+        it.z = w / a.num_m;
+        it.i0 = (int64_t)mt * BM; it.j0 = 0; it.kk_begin = 0;
+        it.kb0 = it.z * a.conv.kbps;
+        it.nkb = min(a.conv.kbps, a.conv.total_kb - it.kb0);
+        it.cls = mt; it.seg0 = 0; it.nvalid = 0;
+        return it;
+    }
     if (a.conv.mode) {
         it.cls = w / a.conv.ntile_class;
         it.seg0 = (w - it.cls * a.conv.ntile_class) * a.conv.nseg;
@@ -251,7 +267,31 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (elect_one()) {
                     TCA_TRACE1(it, 0);
                     uint8_t* sa = smemA + s * a_bytes;
-                    if (a.conv.mode) {
+                    if (a.conv.mode == 3) {
+                        const ConvA& cv = a.conv;
+                        const int seg0 = (t.kb0 + kb) * cv.nseg;
+                        const int nvalid = min(cv.nseg, cv.total_seg - seg0);
+                        const int ch0 = 2 * t.cls;
+                        const int nhalf = min(2, cv.nchunks - ch0);
+                        const uint32_t seg_bytes = (uint32_t)cv.segw * 256u;
+                        mbar_expect_tx(&full_a[s], (uint32_t)(nvalid * nhalf) * seg_bytes);
+                        const uint32_t dst0 = smem_u32(sa);
+                        for (int g = 0; g < nvalid; ++g) {
+                            const int sg = seg0 + g;
+                            const int rowidx = sg / cv.spr, ox0 = (sg - rowidx * cv.spr) * cv.segw;
+                            const int b = rowidx / cv.rows_per_img, oy = rowidx - b * cv.rows_per_img;
+                            for (int hh = 0; hh < nhalf; ++hh) {
+                                const int ch = ch0 + hh;
+                                const uint32_t dst = dst0 + hh * 8192u + g * seg_bytes;
+                                if (cv.nchw) {
+                                    tma_load_5d(&tmA, &full_a[s], dst, 0, 0, ox0, oy, b * cv.C + ch);
+                                } else {
+                                    const int ky = ch / cv.cpr;
+                                    tma_load_4d(&tmA, &full_a[s], dst, (ch - ky * cv.cpr) * 64, ox0, oy * cv.s + ky, b);
+                                }
+                            }
+                        }
+                    } else if (a.conv.mode) {
                         const ConvA& cv = a.conv;
                         const uint32_t seg_bytes = (uint32_t)cv.segw * 128u;
                         mbar_expect_tx(&full_a[s], (uint32_t)t.nvalid * seg_bytes);
@@ -292,7 +332,12 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     TCA_TRACE1(it, 1);
                     mbar_expect_tx(&full_b[s], a.b_presplit ? 2 * b_bytes : b_bytes);
                     uint8_t* sb = smemB + s * 2 * b_bytes;
-                    if (a.conv.mode == 2) {
+                    if (a.conv.mode == 3) {
+                        // dY [pixels, Cout]: the 32 pixel rows starting at the k-block's first pixel (rows past its last valid
+                        // pixel belong to the next k-block: finite values that meet the zeroed pad slots of A)
+                        const int p0 = (t.kb0 + kb) * a.conv.nseg * a.conv.segw;
+                        for (int q = 0; q < bn / 32; ++q) tma_load_2d(&tmB, &full_b[s], sb + q * 4096, 32 * q, p0);
+                    } else if (a.conv.mode == 2) {
                         // W [Cout, (ky, kx, c)]: box {32 c, 32 couts} of filter tap (ky, kx) = (py + s dky, px + s dkx)
                         const ConvA& cv = a.conv;
                         const int tap = kb / cv.kpk, cch = kb - tap * cv.kpk;
@@ -376,7 +421,16 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (q == 0) TCA_TRACE(it, 3);
                 const uint32_t sa = smemA_u + s * a_bytes;
                 float x[32];
-                if (!a.a_mn) {
+                if (a.conv.mode == 3) {
+                    // [half][pixel slot][64 patch floats]; slots past the valid pixels and chunks past K are zero
+                    const ConvA& cv = a.conv;
+                    const int seg0 = (t.kb0 + kb) * cv.nseg;
+                    const int npx = min(cv.nseg, cv.total_seg - seg0) * cv.segw;
+                    const bool chunk_ok = 2 * t.cls + (r >> 6) < cv.nchunks;
+                    const uint32_t base = sa + (uint32_t)(r >> 6) * 8192u + (uint32_t)(r & 63) * 4u;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) x[c] = (chunk_ok && c < npx) ? lds32(base + c * 256) : 0.f;
+                } else if (!a.a_mn) {
                     // 128B-swizzled rows of 32 floats: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
@@ -439,7 +493,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int64_t i = t.i0 + q * 32 + lane;
             bool row_ok = i < a.I;
             int64_t crow_off = i * a.ldc + t.j0, mrow_off = i * a.ldm + t.j0;
-            if (a.conv.mode) {
+            if (a.conv.mode == 1 || a.conv.mode == 2) {
                 const ConvA& cv = a.conv;
                 const int r = q * 32 + lane;
                 row_ok = r < t.nvalid * cv.segw;
@@ -688,6 +742,82 @@ int conv_dgrad(const float* dy, const ppd_conv_geom* g, int Cout, const float* w
     cv.nkb = cv.T * cv.T * cv.kpk;
     a.total_items = st * st * cv.ntile_class;
     return launch_conv(tmA, tmB, tmBlo, a, s);
+}
+
+static void wgrad_plan(const ppd_conv_geom* g, int Cout, int nchw, ConvA& cv, int& num_m, int& splits) {
+    const int OH = (g->H - g->kh) / g->stride + 1, OW = (g->W - g->kw) / g->stride + 1;
+    int segw = 1, best = 0;                      // divisor of OW that fills most of the 32 pixel slots (ties: the larger one)
+    for (int d = 1; d <= OW && d <= 32; ++d) {
+        if (OW % d) continue;
+        const int cover = 32 / d * d;
+        if (cover >= best) { best = cover; segw = d; }
+    }
+    cv = ConvA{};
+    cv.mode = 3; cv.segw = segw; cv.nseg = 32 / segw; cv.spr = OW / segw; cv.rows_per_img = OH; cv.s = g->stride;
+    const int K = g->kh * g->kw * g->C;
+    cv.nchunks = K / 64; cv.nchw = nchw; cv.C = g->C; cv.cpr = nchw ? 1 : g->kw * g->C / 64;
+    cv.total_seg = g->B * OH * cv.spr;
+    cv.total_kb = (cv.total_seg + cv.nseg - 1) / cv.nseg;
+    num_m = (cv.nchunks + 1) / 2;
+    splits = kNumSMs / num_m;
+    if (splits > cv.total_kb / 8) splits = cv.total_kb / 8;
+    if (splits < 1) splits = 1;
+    cv.kbps = (cv.total_kb + splits - 1) / splits;
+    splits = (cv.total_kb + cv.kbps - 1) / cv.kbps;
+    (void)Cout;
+}
+
+size_t conv_wgrad_workspace(const ppd_conv_geom* g, int Cout) {
+    ConvA cv; int num_m, splits;
+    wgrad_plan(g, Cout, 0, cv, num_m, splits);
+    return (size_t)splits * g->kh * g->kw * g->C * Cout * sizeof(float);
+}
+
+int conv_wgrad(const float* x, const ppd_conv_geom* g, int nchw, const float* dy, int Cout, float* dW, int accumulate,
+               void* workspace, size_t workspace_bytes, cudaStream_t s, int* splits_out) {
+    const int OH = (g->H - g->kh) / g->stride + 1, OW = (g->W - g->kw) / g->stride + 1;
+    const int K = g->kh * g->kw * g->C;
+    PPD_REQUIRE(K % 64 == 0 && (Cout == 32 || Cout == 64) && OH >= 1 && OW >= 1, "unsupported convolution shape");
+    PPD_REQUIRE(nchw ? (g->kh * g->kw == 64 && g->kw * 4 % 16 == 0 && g->stride * 4 % 16 == 0 && g->W * 4 % 16 == 0)
+                     : (g->kw * g->C % 64 == 0), "unsupported patch layout");
+    PPD_REQUIRE(!(((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dW | (uintptr_t)workspace) & 15), "pointers must be 16-byte aligned");
+    Args a = {};
+    int num_m, splits;
+    wgrad_plan(g, Cout, nchw, a.conv, num_m, splits);
+    PPD_REQUIRE(workspace && workspace_bytes >= (size_t)splits * K * Cout * sizeof(float), "workspace too small (ppd_conv_wgrad_workspace)");
+    const ConvA& cv = a.conv;
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (nchw) {
+        cuuint64_t dims[5] = {(cuuint64_t)g->kw, (cuuint64_t)g->kh, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)g->B * g->C};
+        cuuint64_t str[4] = {(cuuint64_t)g->W * 4, (cuuint64_t)g->stride * 4, (cuuint64_t)g->stride * g->W * 4, (cuuint64_t)g->H * g->W * 4};
+        cuuint32_t box[5] = {(cuuint32_t)g->kw, (cuuint32_t)g->kh, (cuuint32_t)cv.segw, 1, 1};
+        rc = make_map_nd(&tmA, x, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    } else {
+        cuuint64_t dims[4] = {(cuuint64_t)g->kw * g->C, (cuuint64_t)OW, (cuuint64_t)g->H, (cuuint64_t)g->B};
+        cuuint64_t str[3] = {(cuuint64_t)g->stride * g->C * 4, (cuuint64_t)g->W * g->C * 4, (cuuint64_t)g->H * g->W * g->C * 4};
+        cuuint32_t box[4] = {64, (cuuint32_t)cv.segw, 1, 1};
+        rc = make_map_nd(&tmA, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    }
+    if (rc) return rc;
+    const int64_t M = (int64_t)g->B * OH * OW;
+    if ((rc = make_map_2d(&tmB, dy, M, Cout, Cout, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    a.C = nullptr; a.ldc = 0; a.I = K; a.J = Cout; a.KK = M;
+    a.bn = Cout; a.a_mn = 1; a.b_mn = 1; a.b_presplit = 0;
+    a.num_m = num_m; a.num_n = 1; a.splits = splits; a.kk_per_split = 0;
+    a.partial = reinterpret_cast<float*>(workspace);
+    a.total_items = num_m * splits;
+    int sb_stages = (int)((kSmemBudget - 1024 - (size_t)kSA * BM * BK * 4) / ((size_t)2 * a.bn * BK * 4));
+    if (sb_stages > kMaxSB) sb_stages = kMaxSB;
+    a.sb_stages = sb_stages;
+    const size_t smem = (size_t)kSA * BM * BK * 4 + (size_t)sb_stages * 2 * a.bn * BK * 4 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(tca_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    if (e != cudaSuccess) { set_error("tca conv: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
+    const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+    tca_gemm_kernel<<<grid, kThreads, smem, s>>>(tmA, tmB, tmB, a);
+    if (splits_out) *splits_out = splits;
+    (void)accumulate; (void)dW;
+    return launch_status("tca_gemm_kernel(wgrad)");
 }
 
 Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_avail, bool limit) {

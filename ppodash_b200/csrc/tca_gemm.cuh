@@ -29,6 +29,12 @@ constexpr uint32_t kTaCol0 = 256;
 //                     segment = (b, i) with dx row y = s*i + py and the Wq = Win/s pixels x = s*j + px; k-block kb =
 //                     tap (dky, dkx) of the T x T taps that reach this class (ky = py + s*dky) x 32-channel chunk of dY.
 //                     A map: dY dims {Cout, OWy, OHy, B}; coordinates (chunk*32, -dkx, i - dky, b).
+//   mode 3, wgrad:    dW^T[(ky,kx,c), cout] = sum over pixels of patch[pixel, (ky,kx,c)] * dY[pixel, cout].  The 128 tile rows are
+//                     two CHUNKS of 64 consecutive patch floats; a k-block is 32 pixel slots = nseg segments of segw pixels
+//                     (pad slots are zeroed by the transform warps); boxes {64 floats, segw pixels} land as [pixel][64] so
+//                     that consecutive lanes (= consecutive patch floats) read consecutive words.  NCHW inputs (the
+//                     observations, C = 3, one chunk = one channel's 8x8 patch) use a 5-D view {kx, ky, ox, oy, b*C+c}.
+//                     The contraction over all pixels is split over CTAs; partial products are reduced afterwards.
 struct ConvA {
     int mode;                // 0 = plain GEMM
     int segw, nseg;          // pixels per segment, segments per tile (nseg * segw <= 128)
@@ -41,6 +47,13 @@ struct ConvA {
     int KW, Cin;             // dgrad: filter width, input channels
     int Hin, Win;            // dgrad: dx height / width
     int nkb;                 // k-blocks per tile
+    int spr;                 // wgrad: segments per output row (OW / segw)
+    int cpr;                 // wgrad: chunks per filter row (NHWC) -- unused for NCHW
+    int nchunks;             // wgrad: K / 64
+    int nchw;                // wgrad: 5-D NCHW view (conv1) instead of the 4-D NHWC view
+    int C;                   // wgrad NCHW: channels
+    int total_kb, kbps;      // wgrad: k-blocks in total / per split
+    int total_seg;           // wgrad: B * OH * spr
 };
 
 struct Args {
@@ -73,6 +86,10 @@ int conv_forward(const float* x, const ppd_conv_geom* g, int Cout, const float* 
                  float* out, cudaStream_t s);
 int conv_dgrad(const float* dy, const ppd_conv_geom* g, int Cout, const float* w_hi, const float* w_lo, const float* act_mask,
                float* dx, cudaStream_t s);
+// dW[Cout, K] (+)= dY^T patches(x): x NHWC (nchw = 0, patch order (ky,kx,c)) or NCHW (nchw = 1, patch order (c,ky,kx)).
+size_t conv_wgrad_workspace(const ppd_conv_geom* g, int Cout);
+int conv_wgrad(const float* x, const ppd_conv_geom* g, int nchw, const float* dy, int Cout, float* dW, int accumulate,
+               void* workspace, size_t workspace_bytes, cudaStream_t s, int* splits_out);
 int split_operand(const float* x, float* hi, float* lo, int64_t n, cudaStream_t s);
 
 }  // namespace tca

@@ -378,3 +378,34 @@ def test_conv_dgrad_nhwc_gather_form(B, H, C, k, s, Cout):
                                      dx.data_ptr(), _lib.stream_ptr()))
     scale = float(want.abs().max())
     assert float((dx.cpu() - want).abs().max()) <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("B,H,C,k,s,Cout,nchw", [(7, 20, 32, 4, 2, 64, 0), (5, 9, 64, 3, 1, 32, 0), (300, 20, 32, 4, 2, 64, 0),
+                                                 (333, 9, 64, 3, 1, 32, 0), (3, 84, 3, 8, 4, 32, 1), (40, 84, 3, 8, 4, 32, 1),
+                                                 (2, 84, 1, 8, 4, 32, 1), (6, 84, 4, 8, 4, 32, 1)])
+def test_conv_wgrad_implicit_gemm(B, H, C, k, s, Cout, nchw):
+    """ppd_conv_wgrad == d(conv)/dW: NHWC inputs with (ky,kx,c) weights, NCHW observations with (c,ky,kx) weights."""
+    from ppodash_b200._lib import ConvGeom
+    L = _lib.lib()
+    g0 = torch.Generator().manual_seed(B + H + C + 5)
+    OH = (H - k) // s + 1
+    M = B * OH * OH
+    x = torch.randn(B, C, H, H, generator=g0)                              # reference layout NCHW
+    dy = torch.randn(B, OH, OH, Cout, generator=g0) / np.sqrt(M)
+    dW0 = torch.randn(Cout, C * k * k, generator=g0)
+    cols = F.unfold(x.double(), k, stride=s)                               # [B, C*k*k (c,ky,kx), OH*OW]
+    dw = torch.einsum("bpo,bkp->ok", dy.double().reshape(B, OH * OH, Cout), cols)           # [Cout, (c,ky,kx)]
+    if not nchw:
+        dw = dw.view(Cout, C, k, k).permute(0, 2, 3, 1).reshape(Cout, -1)  # -> (ky,kx,c)
+        xd = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    else:
+        xd = x.to(DEV)
+    for acc in (0, 1):
+        want = (dw + (dW0.double() if acc else 0)).float()
+        dW = dW0.to(DEV).clone()
+        geom = ConvGeom(B, H, H, C, k, k, s)
+        ws = _lib.workspace(L.ppd_conv_wgrad_workspace(ctypes.byref(geom), Cout), DEV, "wgrad_test")
+        _lib.check(L.ppd_conv_wgrad(xd.data_ptr(), ctypes.byref(geom), nchw, dy.to(DEV).data_ptr(), Cout, dW.data_ptr(), acc,
+                                    ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        scale = float(dw.abs().max())
+        assert float((dW.cpu() - want).abs().max()) <= 2e-5 * scale
