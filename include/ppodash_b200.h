@@ -219,6 +219,11 @@ int ppd_conv_fwd_nhwc(const float* x, const ppd_conv_geom* geom, int Cout, const
                       const float* bias, int relu, float* out, void* stream);
 int ppd_conv_dgrad_nhwc(const float* dy, const ppd_conv_geom* geom, int Cout, const float* w_hi, const float* w_lo,
                         const float* act_mask, float* dx, void* stream);
+/* Forward over NCHW observations x [B,C,H,W] (geom: same fields, C = channels), weights [Cout, (c,ky,kx)], NHWC output
+ * [B*OH*OW, Cout]: the kernel stages raw image rows and expands the 8-wide windows on the way to registers
+ * (replaces main.0 = Conv2d(C, 32, 8, stride 4), PKG/model.py:177).  kw == 8, stride % 4 == 0, W % 4 == 0. */
+int ppd_conv_fwd_nchw(const float* x, const ppd_conv_geom* geom, int Cout, const float* w_hi, const float* w_lo,
+                      const float* bias, int relu, float* out, void* stream);
 /*   wgrad: dW[Cout, K] (+)= sum over output pixels of dy[pixel, cout] * patch(x)[pixel, k], contraction split over the SMs and
  *          reduced in a fixed order.  nchw = 0: x is NHWC, patch / weight order (ky,kx,c), kw*C % 64 == 0;
  *          nchw = 1: x is NCHW (the observations), patch order (c,ky,kx), 8x8 filter (5-D TMA view, no channel padding). */

@@ -91,6 +91,7 @@ _PROTOTYPES = {
     "ppd_tc_gemm_set_option": (None, [c_int]),
     "ppd_split_tf32": (c_int, [_P, _P, _P, c_int64, _P]),
     "ppd_conv_fwd_nhwc": (c_int, [_P, POINTER(ConvGeom), c_int, _P, _P, _P, c_int, _P, _P]),
+    "ppd_conv_fwd_nchw": (c_int, [_P, POINTER(ConvGeom), c_int, _P, _P, _P, c_int, _P, _P]),
     "ppd_conv_dgrad_nhwc": (c_int, [_P, POINTER(ConvGeom), c_int, _P, _P, _P, _P, _P]),
     "ppd_conv_wgrad_workspace": (c_size_t, [POINTER(ConvGeom), c_int]),
     "ppd_conv_wgrad": (c_int, [_P, POINTER(ConvGeom), c_int, _P, c_int, _P, c_int, _P, c_size_t, _P]),

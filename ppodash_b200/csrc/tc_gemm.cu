@@ -606,6 +606,12 @@ extern "C" int ppd_conv_fwd_nhwc(const float* x, const ppd_conv_geom* geom, int 
     return ppd::tca::conv_forward(x, geom, Cout, w_hi, w_lo, bias, relu, out, ppd::as_stream(stream));
 }
 
+extern "C" int ppd_conv_fwd_nchw(const float* x, const ppd_conv_geom* geom, int Cout, const float* w_hi, const float* w_lo,
+                                 const float* bias, int relu, float* out, void* stream) {
+    PPD_REQUIRE(x && geom && w_hi && w_lo && out, "null pointer");
+    return ppd::tca::conv_forward_nchw(x, geom, Cout, w_hi, w_lo, bias, relu, out, ppd::as_stream(stream));
+}
+
 extern "C" int ppd_conv_dgrad_nhwc(const float* dy, const ppd_conv_geom* geom, int Cout, const float* w_hi, const float* w_lo,
                                    const float* act_mask, float* dx, void* stream) {
     PPD_REQUIRE(dy && geom && w_hi && w_lo && dx, "null pointer");

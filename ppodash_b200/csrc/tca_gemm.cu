@@ -291,6 +291,21 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 }
                             }
                         }
+                    } else if (a.conv.mode == 4) {
+                        // raw image rows: box {W floats, kyg rows} at row (b*C + c)*H + s*oy + kyq*kyg of x viewed as [B*C*H, W]
+                        const ConvA& cv = a.conv;
+                        const int kyg = 32 / cv.KW;
+                        const uint32_t seg_bytes = (uint32_t)(kyg * cv.Win) * 4u;
+                        const uint32_t seg_pitch = (seg_bytes + 127u) & ~127u;         // TMA destinations are 128-byte aligned
+                        mbar_expect_tx(&full_a[s], (uint32_t)t.nvalid * seg_bytes);
+                        const int c = kb / cv.kpk, kyq = kb - c * cv.kpk;
+                        const uint32_t dst0 = smem_u32(sa);
+                        for (int g = 0; g < t.nvalid; ++g) {
+                            const int sg = t.seg0 + g;
+                            const int b = sg / cv.rows_per_img, oy = sg - b * cv.rows_per_img;
+                            tma_load_2d(&tmA, &full_a[s], sa + g * seg_pitch, 0, (b * cv.C + c) * cv.Hin + oy * cv.s + kyq * kyg);
+                        }
+                        (void)dst0;
                     } else if (a.conv.mode) {
                         const ConvA& cv = a.conv;
                         const uint32_t seg_bytes = (uint32_t)cv.segw * 128u;
@@ -430,6 +445,19 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t base = sa + (uint32_t)(r >> 6) * 8192u + (uint32_t)(r & 63) * 4u;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) x[c] = (chunk_ok && c < npx) ? lds32(base + c * 256) : 0.f;
+                } else if (a.conv.mode == 4) {
+                    const ConvA& cv = a.conv;
+                    const int g = r / cv.segw, ox = r - g * cv.segw;
+                    const int kyg = 32 / cv.KW;                                  // 4 rows of 8 floats
+                    const uint32_t base = sa + (uint32_t)g * (((uint32_t)(kyg * cv.Win) * 4u + 127u) & ~127u) + (uint32_t)(ox * cv.s) * 4u;
+                    const bool ok = g < min(cv.nseg, cv.nseg_class - t.seg0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        // float4 index c: filter row c / 2 (kw = 8: two float4 per row)
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) v = lds128(base + (uint32_t)((c >> 1) * cv.Win) * 4u + (uint32_t)(c & 1) * 16u);
+                        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+                    }
                 } else if (!a.a_mn) {
                     // 128B-swizzled rows of 32 floats: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
 #pragma unroll
@@ -493,11 +521,11 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int64_t i = t.i0 + q * 32 + lane;
             bool row_ok = i < a.I;
             int64_t crow_off = i * a.ldc + t.j0, mrow_off = i * a.ldm + t.j0;
-            if (a.conv.mode == 1 || a.conv.mode == 2) {
+            if (a.conv.mode == 1 || a.conv.mode == 2 || a.conv.mode == 4) {
                 const ConvA& cv = a.conv;
                 const int r = q * 32 + lane;
                 row_ok = r < t.nvalid * cv.segw;
-                if (cv.mode == 1) {
+                if (cv.mode != 2) {
                     crow_off = ((int64_t)t.seg0 * cv.segw + r) * a.ldc;            // output pixels of whole rows are contiguous
                 } else {
                     const int g = r / cv.segw, j = r - g * cv.segw;
@@ -710,6 +738,34 @@ int conv_forward(const float* x, const ppd_conv_geom* g, int Cout, const float* 
     cv.ntile_class = (cv.nseg_class + cv.nseg - 1) / cv.nseg;
     cv.rows_per_img = OH; cv.s = g->stride; cv.kpk = rowf / 32; cv.T = 0; cv.KW = g->kw; cv.Cin = g->C; cv.Hin = g->H; cv.Win = g->W;
     cv.nkb = g->kh * cv.kpk;
+    a.total_items = cv.ntile_class;
+    return launch_conv(tmA, tmB, tmBlo, a, s);
+}
+
+int conv_forward_nchw(const float* x, const ppd_conv_geom* g, int Cout, const float* w_hi, const float* w_lo, const float* bias,
+                      int relu, float* out, cudaStream_t s) {
+    const int OH = (g->H - g->kh) / g->stride + 1, OW = (g->W - g->kw) / g->stride + 1;
+    PPD_REQUIRE(g->kw == 8 && g->kh % 4 == 0 && g->stride % 4 == 0 && g->W % 4 == 0, "NCHW forward supports 8-wide filters with stride % 4 == 0");
+    PPD_REQUIRE((Cout == 32 || Cout == 64) && OW >= 1 && OW <= BM && OH >= 1, "unsupported convolution shape");
+    PPD_REQUIRE(!(((uintptr_t)x | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)out) & 15), "pointers must be 16-byte aligned");
+    const int kyg = 32 / g->kw;
+    const int64_t K = (int64_t)g->C * g->kh * g->kw;
+    Args a = {};
+    ConvA& cv = a.conv;
+    cv.mode = 4; cv.segw = OW; cv.nseg = BM / OW;
+    while ((size_t)cv.nseg * (((size_t)kyg * g->W * 4 + 127) & ~(size_t)127) > (size_t)BM * BK * 4) --cv.nseg;       // the raw rows of a stage must fit its 16 KB
+    cv.nseg_class = g->B * OH;
+    cv.ntile_class = (cv.nseg_class + cv.nseg - 1) / cv.nseg;
+    cv.rows_per_img = OH; cv.s = g->stride; cv.kpk = g->kh / kyg; cv.KW = g->kw; cv.Cin = g->C; cv.C = g->C; cv.Hin = g->H; cv.Win = g->W;
+    cv.nkb = g->C * cv.kpk;
+    CUtensorMap tmA, tmB, tmBlo;
+    int rc = make_map_2d(&tmA, x, (int64_t)g->B * g->C * g->H, g->W, g->W, g->W, kyg, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    if ((rc = make_map_2d(&tmB, w_hi, Cout, K, K, BK, Cout, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_map_2d(&tmBlo, w_lo, Cout, K, K, BK, Cout, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    a.C = out; a.ldc = Cout; a.I = (int64_t)g->B * OH * OW; a.J = Cout; a.KK = K;
+    a.bias = bias; a.mask = nullptr; a.relu = relu;
+    a.bn = Cout; a.b_mn = 0;
     a.total_items = cv.ntile_class;
     return launch_conv(tmA, tmB, tmBlo, a, s);
 }

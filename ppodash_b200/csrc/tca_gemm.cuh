@@ -35,6 +35,11 @@ constexpr uint32_t kTaCol0 = 256;
 //                     that consecutive lanes (= consecutive patch floats) read consecutive words.  NCHW inputs (the
 //                     observations, C = 3, one chunk = one channel's 8x8 patch) use a 5-D view {kx, ky, ox, oy, b*C+c}.
 //                     The contraction over all pixels is split over CTAs; partial products are reduced afterwards.
+//   mode 4, forward over NCHW observations (conv1: C = 3, 8x8, stride 4): the contiguous runs of a patch are only kw floats,
+//                     too short for swizzled TMA rows, so the k-block (channel c, 32/kw filter rows) stages the RAW image rows
+//                     y = s*oy + ky as boxes {W floats, 32/kw rows}; the window expansion happens on the way to registers:
+//                     the thread of pixel ox reads floats [s*ox, s*ox + kw) of each row -- consecutive lanes read consecutive
+//                     16-byte words (s = 4), conflict-free, and every input element crosses L2 -> SM once, not kw/s times.
 struct ConvA {
     int mode;                // 0 = plain GEMM
     int segw, nseg;          // pixels per segment, segments per tile (nseg * segw <= 128)
@@ -86,6 +91,8 @@ int conv_forward(const float* x, const ppd_conv_geom* g, int Cout, const float* 
                  float* out, cudaStream_t s);
 int conv_dgrad(const float* dy, const ppd_conv_geom* g, int Cout, const float* w_hi, const float* w_lo, const float* act_mask,
                float* dx, cudaStream_t s);
+int conv_forward_nchw(const float* x, const ppd_conv_geom* g, int Cout, const float* w_hi, const float* w_lo, const float* bias,
+                      int relu, float* out, cudaStream_t s);
 // dW[Cout, K] (+)= dY^T patches(x): x NHWC (nchw = 0, patch order (ky,kx,c)) or NCHW (nchw = 1, patch order (c,ky,kx)).
 size_t conv_wgrad_workspace(const ppd_conv_geom* g, int Cout);
 int conv_wgrad(const float* x, const ppd_conv_geom* g, int nchw, const float* dy, int Cout, float* dW, int accumulate,

@@ -409,3 +409,23 @@ def test_conv_wgrad_implicit_gemm(B, H, C, k, s, Cout, nchw):
                                     ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
         scale = float(dw.abs().max())
         assert float((dW.cpu() - want).abs().max()) <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("B,C,Cout", [(3, 3, 32), (40, 3, 32), (2, 1, 32), (5, 4, 32), (3, 12, 32)])
+def test_conv_fwd_nchw_observations(B, C, Cout):
+    """ppd_conv_fwd_nchw == ReLU(Conv2d(C, 32, 8, stride 4)(obs)) with NCHW observations and NHWC output."""
+    from ppodash_b200._lib import ConvGeom
+    L = _lib.lib()
+    g0 = torch.Generator().manual_seed(B + C)
+    x = torch.randn(B, C, 84, 84, generator=g0)
+    w = torch.randn(Cout, C, 8, 8, generator=g0) / np.sqrt(64 * C)
+    b = torch.randn(Cout, generator=g0)
+    want = torch.relu(F.conv2d(x.double(), w.double(), b.double(), stride=4)).permute(0, 2, 3, 1).float()
+    hi, lo = _split(w.to(DEV))
+    out = torch.full((B * 400 + 3, Cout), -7.0, device=DEV)
+    geom = ConvGeom(B, 84, 84, C, 8, 8, 4)
+    _lib.check(L.ppd_conv_fwd_nchw(x.to(DEV).data_ptr(), ctypes.byref(geom), Cout, hi.data_ptr(), lo.data_ptr(), b.to(DEV).data_ptr(), 1,
+                                   out.data_ptr(), _lib.stream_ptr()))
+    got = out[:B * 400].view(B, 20, 20, Cout).cpu()
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    assert torch.all(out[B * 400:] == -7.0)
