@@ -40,6 +40,30 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifdef PPD_TCA_TRACE
+// debug builds: a wait that does not complete within ~2^26 polls reports itself and traps instead of hanging the GPU
+__device__ __noinline__ void mbar_wait_timeout(uint64_t* bar, uint32_t parity) {
+    printf("tca_gemm: mbarrier wait timed out: block %d thread %d barrier smem offset %u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+           smem_u32(bar), parity);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t n = 0;; ++n) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (n > (1u << 24)) mbar_wait_timeout(bar, parity);
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -52,6 +76,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+#endif
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -145,6 +170,22 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int b_mn) {
 
 struct Item { int64_t i0, j0, kk_begin; int nkb; int z; int cls, seg0, nvalid, kb0; };
 
+// x / d for 0 <= x < 2^24, d >= 1, through the float reciprocal.  Role loops are warp-uniform code, and an integer division
+// by a run-time divisor there is expanded on the UNIFORM datapath (no reciprocal unit, ~10-clock dependent ops): measured
+// ~2000 clocks per division-laden TMA issue.  I2F / MUFU.RCP / F2I run on the vector pipes in ~50.
+__device__ __forceinline__ int fdiv(int x, int d) {
+    int q = __float2int_rz(__int2float_rn(x) * __frcp_rn(__int2float_rn(d)));
+    const int r = x - q * d;
+    if (r < 0) --q;
+    else if (r >= d) ++q;
+    return q;
+}
+// stage index + phase bit of a ring with a run-time number of stages
+struct Ring {
+    uint32_t s = 0, ph = 0;
+    __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
+};
+
 // Pipeline timeline of CTA 0 (debug builds only: -DPPD_TCA_TRACE): trace[(it * 16 + slot)] = clock64()
 #ifdef PPD_TCA_TRACE
 __device__ long long* g_trace = nullptr;
@@ -159,8 +200,8 @@ __device__ __forceinline__ Item decode(const Args& a, int w) {
     Item it;
     it.kb0 = 0;
     if (a.conv.mode == 3) {
-        const int mt = w % a.num_m;
-        it.z = w / a.num_m;
+        it.z = fdiv(w, a.num_m);
+        const int mt = w - it.z * a.num_m;
         it.i0 = (int64_t)mt * BM; it.j0 = 0; it.kk_begin = 0;
         it.kb0 = it.z * a.conv.kbps;
         it.nkb = min(a.conv.kbps, a.conv.total_kb - it.kb0);
@@ -168,7 +209,7 @@ __device__ __forceinline__ Item decode(const Args& a, int w) {
         return it;
     }
     if (a.conv.mode) {
-        it.cls = w / a.conv.ntile_class;
+        it.cls = fdiv(w, a.conv.ntile_class);
         it.seg0 = (w - it.cls * a.conv.ntile_class) * a.conv.nseg;
         it.nvalid = min(a.conv.nseg, a.conv.nseg_class - it.seg0);
         it.i0 = 0; it.j0 = 0; it.kk_begin = 0; it.z = 0;
@@ -176,10 +217,10 @@ __device__ __forceinline__ Item decode(const Args& a, int w) {
         return it;
     }
     it.cls = it.seg0 = it.nvalid = 0;
-    const int n = w % a.num_n;
-    const int r = w / a.num_n;
-    const int m = r % a.num_m;
-    it.z = r / a.num_m;
+    const int r = fdiv(w, a.num_n);
+    const int n = w - r * a.num_n;
+    it.z = fdiv(r, a.num_m);
+    const int m = r - it.z * a.num_m;
     it.i0 = (int64_t)m * BM;
     it.j0 = (int64_t)n * a.bn;
     it.kk_begin = (int64_t)it.z * a.kk_per_split;
@@ -234,6 +275,12 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
+#ifdef PPD_TCA_TRACE
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        printf("tca_gemm barriers: full_a %u empty_a %u full_b %u empty_b %u ta_full %u ta_empty %u acc_full %u acc_empty %u | mode %d items %d\n",
+               smem_u32(full_a), smem_u32(empty_a), smem_u32(full_b), smem_u32(empty_b), smem_u32(ta_full), smem_u32(ta_empty),
+               smem_u32(acc_full), smem_u32(acc_empty), a.conv.mode, a.total_items);
+#endif
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 4); }
         for (int s = 0; s < kMaxSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
@@ -256,7 +303,8 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp == 0) {
-        // ================= TMA producer, A tiles
+        // ================= TMA producer, A tiles.  Convolution tiles are several boxes per stage: LANE g computes the
+        // coordinates of box g (vector datapath, all boxes in parallel) and issues its own copy.
         uint32_t it = 0;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
             const Item t = decode(a, w);
@@ -264,71 +312,68 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int kk = (int)(t.kk_begin + (int64_t)kb * BK);
                 const uint32_t s = it % kSA;
                 mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
-                if (elect_one()) {
-                    TCA_TRACE1(it, 0);
-                    uint8_t* sa = smemA + s * a_bytes;
-                    if (a.conv.mode == 3) {
-                        const ConvA& cv = a.conv;
-                        const int seg0 = (t.kb0 + kb) * cv.nseg;
-                        const int nvalid = min(cv.nseg, cv.total_seg - seg0);
-                        const int ch0 = 2 * t.cls;
-                        const int nhalf = min(2, cv.nchunks - ch0);
-                        const uint32_t seg_bytes = (uint32_t)cv.segw * 256u;
-                        mbar_expect_tx(&full_a[s], (uint32_t)(nvalid * nhalf) * seg_bytes);
-                        const uint32_t dst0 = smem_u32(sa);
-                        for (int g = 0; g < nvalid; ++g) {
-                            const int sg = seg0 + g;
-                            const int rowidx = sg / cv.spr, ox0 = (sg - rowidx * cv.spr) * cv.segw;
-                            const int b = rowidx / cv.rows_per_img, oy = rowidx - b * cv.rows_per_img;
-                            for (int hh = 0; hh < nhalf; ++hh) {
-                                const int ch = ch0 + hh;
-                                const uint32_t dst = dst0 + hh * 8192u + g * seg_bytes;
-                                if (cv.nchw) {
-                                    tma_load_5d(&tmA, &full_a[s], dst, 0, 0, ox0, oy, b * cv.C + ch);
-                                } else {
-                                    const int ky = ch / cv.cpr;
-                                    tma_load_4d(&tmA, &full_a[s], dst, (ch - ky * cv.cpr) * 64, ox0, oy * cv.s + ky, b);
-                                }
-                            }
-                        }
-                    } else if (a.conv.mode == 4) {
-                        // raw image rows: box {W floats, kyg rows} at row (b*C + c)*H + s*oy + kyq*kyg of x viewed as [B*C*H, W]
-                        const ConvA& cv = a.conv;
-                        const int kyg = 32 / cv.KW;
-                        const uint32_t seg_bytes = (uint32_t)(kyg * cv.Win) * 4u;
-                        const uint32_t seg_pitch = (seg_bytes + 127u) & ~127u;         // TMA destinations are 128-byte aligned
-                        mbar_expect_tx(&full_a[s], (uint32_t)t.nvalid * seg_bytes);
-                        const int c = kb / cv.kpk, kyq = kb - c * cv.kpk;
-                        const uint32_t dst0 = smem_u32(sa);
-                        for (int g = 0; g < t.nvalid; ++g) {
-                            const int sg = t.seg0 + g;
-                            const int b = sg / cv.rows_per_img, oy = sg - b * cv.rows_per_img;
-                            tma_load_2d(&tmA, &full_a[s], sa + g * seg_pitch, 0, (b * cv.C + c) * cv.Hin + oy * cv.s + kyq * kyg);
-                        }
-                        (void)dst0;
-                    } else if (a.conv.mode) {
-                        const ConvA& cv = a.conv;
-                        const uint32_t seg_bytes = (uint32_t)cv.segw * 128u;
-                        mbar_expect_tx(&full_a[s], (uint32_t)t.nvalid * seg_bytes);
-                        int c0, dx1, dy2;               // inner coordinate, pixel offset, row offset shared by the segments
-                        if (cv.mode == 1) {
-                            const int ky = kb / cv.kpk;
-                            c0 = (kb - ky * cv.kpk) * 32; dx1 = 0; dy2 = ky;
-                        } else {
-                            const int tap = kb / cv.kpk;
-                            const int dky = tap / cv.T, dkx = tap - dky * cv.T;
-                            c0 = (kb - tap * cv.kpk) * 32; dx1 = -dkx; dy2 = -dky;
-                        }
-                        const uint32_t dst0 = smem_u32(sa);
-                        for (int g = 0; g < t.nvalid; ++g) {
-                            const int sg = t.seg0 + g;
-                            const int b = sg / cv.rows_per_img, row = sg - b * cv.rows_per_img;
-                            tma_load_4d(&tmA, &full_a[s], dst0 + g * seg_bytes, c0, dx1, (cv.mode == 1 ? row * cv.s : row) + dy2, b);
-                        }
-                    } else {
+                uint8_t* sa = smemA + s * a_bytes;
+                const uint32_t dst0 = smem_u32(sa);
+                const ConvA& cv = a.conv;
+                if (cv.mode == 0) {
+                    if (elect_one()) {
+                        TCA_TRACE1(it, 0);
                         mbar_expect_tx(&full_a[s], a_bytes);
                         if (!a.a_mn) tma_load_2d(&tmA, &full_a[s], sa, kk, (int)t.i0);     // box {32 k, 128 rows}, 128B swizzle
                         else         tma_load_2d(&tmA, &full_a[s], sa, (int)t.i0, kk);     // box {128 rows, 32 k}, no swizzle
+                    }
+                } else if (cv.mode == 3) {
+                    const int seg0 = (t.kb0 + kb) * cv.nseg;
+                    const int nvalid = min(cv.nseg, cv.total_seg - seg0);
+                    const int ch0 = 2 * t.cls;
+                    const int nhalf = min(2, cv.nchunks - ch0);
+                    const uint32_t seg_bytes = (uint32_t)cv.segw * 256u;
+                    if (lane == 0) { TCA_TRACE1(it, 0); mbar_expect_tx(&full_a[s], (uint32_t)(nvalid * nhalf) * seg_bytes); }
+                    __syncwarp();
+                    if (lane < nvalid * nhalf) {
+                        const int g = (nhalf == 2) ? (lane >> 1) : lane, hh = (nhalf == 2) ? (lane & 1) : 0;
+                        const int sg = seg0 + g;
+                        const int rowidx = fdiv(sg, cv.spr), ox0 = (sg - rowidx * cv.spr) * cv.segw;
+                        const int b = fdiv(rowidx, cv.rows_per_img), oy = rowidx - b * cv.rows_per_img;
+                        const int ch = ch0 + hh;
+                        const uint32_t dst = dst0 + hh * 8192u + g * seg_bytes;
+                        if (cv.nchw) {
+                            tma_load_5d(&tmA, &full_a[s], dst, 0, 0, ox0, oy, b * cv.C + ch);
+                        } else {
+                            const int ky = fdiv(ch, cv.cpr);
+                            tma_load_4d(&tmA, &full_a[s], dst, (ch - ky * cv.cpr) * 64, ox0, oy * cv.s + ky, b);
+                        }
+                    }
+                } else if (cv.mode == 4) {
+                    // raw image rows: box {W floats, kyg rows} at row (b*C + c)*H + s*oy + kyq*kyg of x viewed as [B*C*H, W]
+                    const int kyg = 32 / cv.KW;
+                    const uint32_t seg_bytes = (uint32_t)(kyg * cv.Win) * 4u;
+                    const uint32_t seg_pitch = (seg_bytes + 127u) & ~127u;         // TMA destinations are 128-byte aligned
+                    if (lane == 0) { TCA_TRACE1(it, 0); mbar_expect_tx(&full_a[s], (uint32_t)t.nvalid * seg_bytes); }
+                    __syncwarp();
+                    if (lane < t.nvalid) {
+                        const int c = fdiv(kb, cv.kpk), kyq = kb - c * cv.kpk;
+                        const int sg = t.seg0 + lane;
+                        const int b = fdiv(sg, cv.rows_per_img), oy = sg - b * cv.rows_per_img;
+                        tma_load_2d(&tmA, &full_a[s], sa + lane * seg_pitch, 0, (b * cv.C + c) * cv.Hin + oy * cv.s + kyq * kyg);
+                    }
+                } else {
+                    const uint32_t seg_bytes = (uint32_t)cv.segw * 128u;
+                    if (lane == 0) { TCA_TRACE1(it, 0); mbar_expect_tx(&full_a[s], (uint32_t)t.nvalid * seg_bytes); }
+                    __syncwarp();
+                    if (lane < t.nvalid) {
+                        int c0, dx1, dy2;               // inner coordinate, pixel offset, row offset shared by the segments
+                        if (cv.mode == 1) {
+                            const int ky = fdiv(kb, cv.kpk);
+                            c0 = (kb - ky * cv.kpk) * 32; dx1 = 0; dy2 = ky;
+                        } else {
+                            const int tap = fdiv(kb, cv.kpk);
+                            const int dky = fdiv(tap, cv.T), dkx = tap - dky * cv.T;
+                            c0 = (kb - tap * cv.kpk) * 32; dx1 = -dkx; dy2 = -dky;
+                        }
+                        const int sg = t.seg0 + lane;
+                        const int b = fdiv(sg, cv.rows_per_img), row = sg - b * cv.rows_per_img;
+                        tma_load_4d(&tmA, &full_a[s], dst0 + lane * seg_bytes, c0, dx1, (cv.mode == 1 ? row * cv.s : row) + dy2, b);
                     }
                 }
                 __syncwarp();
@@ -337,12 +382,13 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else if (warp == 2) {
         // ================= TMA producer, B tiles
         uint32_t it = 0;
+        Ring rb;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
             const Item t = decode(a, w);
-            for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+            for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB)) {
                 const int kk = (int)(t.kk_begin + (int64_t)kb * BK);
-                const uint32_t s = it % kSB;
-                mbar_wait(&empty_b[s], ((it / kSB) & 1u) ^ 1u);
+                const uint32_t s = rb.s;
+                mbar_wait(&empty_b[s], rb.ph ^ 1u);
                 if (elect_one()) {
                     TCA_TRACE1(it, 1);
                     mbar_expect_tx(&full_b[s], a.b_presplit ? 2 * b_bytes : b_bytes);
@@ -355,9 +401,9 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     } else if (a.conv.mode == 2) {
                         // W [Cout, (ky, kx, c)]: box {32 c, 32 couts} of filter tap (ky, kx) = (py + s dky, px + s dkx)
                         const ConvA& cv = a.conv;
-                        const int tap = kb / cv.kpk, cch = kb - tap * cv.kpk;
-                        const int dky = tap / cv.T, dkx = tap - dky * cv.T;
-                        const int py = t.cls / cv.s, px = t.cls - py * cv.s;
+                        const int tap = fdiv(kb, cv.kpk), cch = kb - tap * cv.kpk;
+                        const int dky = fdiv(tap, cv.T), dkx = tap - dky * cv.T;
+                        const int py = fdiv(t.cls, cv.s), px = t.cls - py * cv.s;
                         const int col = ((py + cv.s * dky) * cv.KW + (px + cv.s * dkx)) * cv.Cin;
                         for (int q = 0; q < bn / 32; ++q) {
                             tma_load_2d(&tmB, &full_b[s], sb + q * 4096, col + 32 * q, cch * 32);
@@ -386,16 +432,17 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                        : make_desc(smem_u32(smemB), 0, 1024, kLayoutSw128);
         const uint32_t kstep = a.b_mn ? (1024u >> 4) : (32u >> 4);          // descriptor start-address step per 8 k
         uint32_t it = 0, tile_it = 0;
+        Ring rb;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
             const Item t = decode(a, w);
             const uint32_t acc = tile_it & 1u;
             mbar_wait(&acc_empty[acc], ((tile_it >> 1) & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d = tmem_base + kAccCol0 + acc * kAccStride;
-            for (int kb = 0; kb < t.nkb; ++kb, ++it) {
-                const uint32_t ts = it % kTA, s = it % kSB;
+            for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB)) {
+                const uint32_t ts = it % kTA, s = rb.s;
                 mbar_wait(&ta_full[ts], (it / kTA) & 1u);
-                if (a.b_presplit) mbar_wait(&full_b[s], (it / kSB) & 1u);
+                if (a.b_presplit) mbar_wait(&full_b[s], rb.ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     TCA_TRACE1(it, 8);
@@ -426,9 +473,10 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int gt = (threadIdx.x - 128) & 127;     // thread index within the group
         const uint32_t smemA_u = smem_u32(smemA), smemB_u = smem_u32(smemB);
         uint32_t it = 0;
+        Ring rb;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
             const Item t = decode(a, w);
-            for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+            for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB)) {
                 if ((int)(it & 1u) != grp) continue;
                 const uint32_t s = it % kSA;
                 if (q == 0) TCA_TRACE(it, 2);
@@ -486,8 +534,8 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tmem_st16(ta + 48u, lo + 16);
                 if (q == 0) TCA_TRACE(it, 6);
                 if (!a.b_presplit) {
-                    const uint32_t sbs = it % kSB;
-                    mbar_wait(&full_b[sbs], (it / kSB) & 1u);
+                    const uint32_t sbs = rb.s;
+                    mbar_wait(&full_b[sbs], rb.ph);
                     const uint32_t src = smemB_u + sbs * 2 * b_bytes;
                     const int nvec = (int)(b_bytes >> 4);
                     for (int v = gt; v < nvec; v += 128) {
@@ -739,6 +787,7 @@ int conv_forward(const float* x, const ppd_conv_geom* g, int Cout, const float* 
     cv.rows_per_img = OH; cv.s = g->stride; cv.kpk = rowf / 32; cv.T = 0; cv.KW = g->kw; cv.Cin = g->C; cv.Hin = g->H; cv.Win = g->W;
     cv.nkb = g->kh * cv.kpk;
     a.total_items = cv.ntile_class;
+    PPD_REQUIRE(cv.nseg <= 32, "output width not supported (too many TMA boxes per tile)");
     return launch_conv(tmA, tmB, tmBlo, a, s);
 }
 
@@ -767,6 +816,7 @@ int conv_forward_nchw(const float* x, const ppd_conv_geom* g, int Cout, const fl
     a.bias = bias; a.mask = nullptr; a.relu = relu;
     a.bn = Cout; a.b_mn = 0;
     a.total_items = cv.ntile_class;
+    PPD_REQUIRE(cv.nseg <= 32, "output width not supported (too many TMA boxes per tile)");
     return launch_conv(tmA, tmB, tmBlo, a, s);
 }
 
@@ -797,17 +847,20 @@ int conv_dgrad(const float* dy, const ppd_conv_geom* g, int Cout, const float* w
     cv.rows_per_img = Hq; cv.s = st; cv.kpk = Cout / 32; cv.T = g->kh / st; cv.KW = g->kw; cv.Cin = g->C; cv.Hin = g->H; cv.Win = g->W;
     cv.nkb = cv.T * cv.T * cv.kpk;
     a.total_items = st * st * cv.ntile_class;
+    PPD_REQUIRE(cv.nseg <= 32, "input width not supported (too many TMA boxes per tile)");
     return launch_conv(tmA, tmB, tmBlo, a, s);
 }
 
 static void wgrad_plan(const ppd_conv_geom* g, int Cout, int nchw, ConvA& cv, int& num_m, int& splits) {
     const int OH = (g->H - g->kh) / g->stride + 1, OW = (g->W - g->kw) / g->stride + 1;
-    int segw = 1, best = 0;                      // divisor of OW that fills most of the 32 pixel slots (ties: the larger one)
+    // divisor of OW that fills most of the 32 pixel slots with at most 8 segments (16 TMA boxes) per k-block; ties: the larger
+    int segw = 0, best = -1;
     for (int d = 1; d <= OW && d <= 32; ++d) {
-        if (OW % d) continue;
+        if (OW % d || 32 / d > 8) continue;
         const int cover = 32 / d * d;
         if (cover >= best) { best = cover; segw = d; }
     }
+    if (!segw) segw = OW <= 32 ? OW : 1;         // (conv_wgrad rejects shapes that would need more than 32 boxes)
     cv = ConvA{};
     cv.mode = 3; cv.segw = segw; cv.nseg = 32 / segw; cv.spr = OW / segw; cv.rows_per_img = OH; cv.s = g->stride;
     const int K = g->kh * g->kw * g->C;
@@ -840,6 +893,7 @@ int conv_wgrad(const float* x, const ppd_conv_geom* g, int nchw, const float* dy
     Args a = {};
     int num_m, splits;
     wgrad_plan(g, Cout, nchw, a.conv, num_m, splits);
+    PPD_REQUIRE(a.conv.nseg * 2 <= 32, "output width not supported (too many TMA boxes per k-block)");
     PPD_REQUIRE(workspace && workspace_bytes >= (size_t)splits * K * Cout * sizeof(float), "workspace too small (ppd_conv_wgrad_workspace)");
     const ConvA& cv = a.conv;
     CUtensorMap tmA, tmB;

@@ -265,6 +265,12 @@ class PolicyEngine:
         return t[:n].view(*shape)
 
     # ------------------------------------------------------------------ kernel wrappers
+    @property
+    def _hilo(self):
+        """Device addresses of the TF32 hi / residual copies of a parameter segment."""
+        return (lambda name: self.flat_hi.data_ptr() + 4 * self.segs[name].off,
+                lambda name: self.flat_lo.data_ptr() + 4 * self.segs[name].off)
+
     def split_params(self):
         """hi = TF32(w), lo = TF32(w - hi) for every parameter, in one launch over the flat buffer."""
         if self.precision != "tf32x3":
@@ -343,19 +349,23 @@ class PolicyEngine:
         time-major), so that the GRU of one time chunk runs on its own stream concurrently with the conv trunk
         of the next one (forward) / the previous one (backward); every chunk is also at most chunk_rows rows so
         that the im2col scratch stays bounded."""
+        implicit = self.precision == "tf32x3"         # implicit-GEMM convolutions: no im2col scratch to bound
         if E:
             T = B // E
             nc = self.time_chunks if (self.overlap_gru and T >= 8 * self.time_chunks) else 1
-            nc = max(nc, -(-B // self.chunk_rows))
+            if not implicit:
+                nc = max(nc, -(-B // self.chunk_rows))
             nc = min(nc, T)
             tl = -(-T // nc)
             return [(t0 * E, min(T, t0 + tl) * E) for t0 in range(0, T, tl)]
-        ch = min(self.chunk_rows, B)
+        ch = B if implicit else min(self.chunk_rows, B)
         return [(r0, min(B, r0 + ch)) for r0 in range(0, B, ch)]
 
     def _cols(self, B, chunks, keep):
         """im2col scratch.  If the matrices of the whole minibatch fit the budget they are kept for backward
         (row offset = chunk start); otherwise one chunk-sized set is reused and backward recomputes them."""
+        if self.precision == "tf32x3":
+            return (None, None, None, True)
         C = self.C
         s1, s2, s3 = self.sp
         K1, K2, K3 = C * 64, 512, 576
@@ -378,8 +388,21 @@ class PolicyEngine:
         a2 = self.buf("a2", B, s2 * s2 * 64)
         a3 = self.buf("a3", B, s3 * s3 * 32)
         a3t = self.buf("a3t", B, self.flat_dim)
-        c1, c2, c3 = cols[0][off * s1 * s1:], cols[1][off * s2 * s2:], cols[2][off * s3 * s3:]
         st = self.stream
+        if self.precision == "tf32x3":
+            # implicit-GEMM convolutions on the TMEM-A kernel: patches come straight from obs / a1 / a2 through TMA
+            hi, lo = self._hilo
+            check(L.ppd_conv_fwd_nchw(obs[r0:].data_ptr(), ctypes.byref(ConvGeom(n, hw, hw, C, 8, 8, 4)), 32, hi("conv1.w"), lo("conv1.w"),
+                                      self.seg("conv1.b").data_ptr(), 1, a1[r0:].data_ptr(), st), "conv1.fwd")
+            check(L.ppd_conv_fwd_nhwc(a1[r0:].data_ptr(), ctypes.byref(ConvGeom(n, s1, s1, 32, 4, 4, 2)), 64, hi("conv2.w"), lo("conv2.w"),
+                                      self.seg("conv2.b").data_ptr(), 1, a2[r0:].data_ptr(), st), "conv2.fwd")
+            check(L.ppd_conv_fwd_nhwc(a2[r0:].data_ptr(), ctypes.byref(ConvGeom(n, s2, s2, 64, 3, 3, 1)), 32, hi("conv3.w"), lo("conv3.w"),
+                                      self.seg("conv3.b").data_ptr(), 1, a3[r0:].data_ptr(), st), "conv3.fwd")
+            check(L.ppd_batched_transpose(a3[r0:].data_ptr(), n, s3 * s3, 32, a3t[r0:].data_ptr(), st), "transpose")
+            self._gemm(a3t[r0:], self.flat_dim, 1, self.seg("fc.w"), self.flat_dim, 1, feat[r0:], ldf, n, H, self.flat_dim,
+                       bias=self.seg("fc.b"), relu=1, b_param=True)
+            return
+        c1, c2, c3 = cols[0][off * s1 * s1:], cols[1][off * s2 * s2:], cols[2][off * s3 * s3:]
         check(L.ppd_im2col_nchw(obs[r0:].data_ptr(), n, C, hw, hw, 8, 8, 4, c1.data_ptr(), K1, st), "im2col1")
         self._gemm(c1, K1, 1, self.seg("conv1.w"), K1, 1, a1[r0:], 32, n * s1 * s1, 32, K1, bias=self.seg("conv1.b"), relu=1, b_param=True)
         check(L.ppd_im2col_nhwc(a1[r0:].data_ptr(), n, s1, s1, 32, 4, 4, 2, c2.data_ptr(), K2, st), "im2col2")
@@ -407,8 +430,34 @@ class PolicyEngine:
         dy3 = self.buf("dy3", B, s3 * s3 * 32)                   # NHWC = [B*49, 32]
         dy2 = self.buf("dy2", B, s2 * s2 * 64)
         dy1 = self.buf("dy1", B, s1 * s1 * 32)
-        c1, c2, c3 = cols[0][off * s1 * s1:], cols[1][off * s2 * s2:], cols[2][off * s3 * s3:]
         M3, M2, M1 = n * s3 * s3, n * s2 * s2, n * s1 * s1
+        if self.precision == "tf32x3":
+            hi, lo = self._hilo
+            with self._Side(self):
+                self._gemm(dfeat[r0:], ldd, 0, a3t[r0:], fd, 0, self.seg("fc.w", True), fd, H, fd, n, acc=acc)
+                self._colsum(dfeat[r0:], ldd, n, H, self.seg("fc.b", True), acc)
+            self._gemm(dfeat[r0:], ldd, 1, self.seg("fc.w"), fd, 0, da3t[r0:], fd, n, fd, H, mask=a3t[r0:], ldm=fd, b_param=True)
+            check(L.ppd_batched_transpose(da3t[r0:].data_ptr(), n, 32, s3 * s3, dy3[r0:].data_ptr(), self.stream), "transpose")
+            g3, g2, g1 = ConvGeom(n, s2, s2, 64, 3, 3, 1), ConvGeom(n, s1, s1, 32, 4, 4, 2), ConvGeom(n, hw, hw, C, 8, 8, 4)
+
+            def wgrad(x, geom, nchw, dy, cout, name):
+                ws = self._ws(L.ppd_conv_wgrad_workspace(ctypes.byref(geom), cout), "convwgrad")
+                check(L.ppd_conv_wgrad(x.data_ptr(), ctypes.byref(geom), nchw, dy.data_ptr(), cout, self.seg(name, True).data_ptr(), acc,
+                                       ws.data_ptr(), ws.numel(), self.stream), name + ".wgrad")
+            with self._Side(self):
+                wgrad(a2[r0:], g3, 0, dy3[r0:], 32, "conv3.w")
+                self._colsum(dy3[r0:], 32, M3, 32, self.seg("conv3.b", True), acc)
+            check(L.ppd_conv_dgrad_nhwc(dy3[r0:].data_ptr(), ctypes.byref(g3), 32, hi("conv3.w"), lo("conv3.w"), a2[r0:].data_ptr(),
+                                        dy2[r0:].data_ptr(), self.stream), "conv3.dgrad")
+            with self._Side(self):
+                wgrad(a1[r0:], g2, 0, dy2[r0:], 64, "conv2.w")
+                self._colsum(dy2[r0:], 64, M2, 64, self.seg("conv2.b", True), acc)
+            check(L.ppd_conv_dgrad_nhwc(dy2[r0:].data_ptr(), ctypes.byref(g2), 64, hi("conv2.w"), lo("conv2.w"), a1[r0:].data_ptr(),
+                                        dy1[r0:].data_ptr(), self.stream), "conv2.dgrad")
+            wgrad(obs[r0:], g1, 1, dy1[r0:], 32, "conv1.w")
+            self._colsum(dy1[r0:], 32, M1, 32, self.seg("conv1.b", True), acc)
+            return
+        c1, c2, c3 = cols[0][off * s1 * s1:], cols[1][off * s2 * s2:], cols[2][off * s3 * s3:]
         with self._Side(self):
             self._gemm(dfeat[r0:], ldd, 0, a3t[r0:], fd, 0, self.seg("fc.w", True), fd, H, fd, n, acc=acc)
             self._colsum(dfeat[r0:], ldd, n, H, self.seg("fc.b", True), acc)

@@ -178,7 +178,8 @@ def test_c2_shaped_minibatch_vs_oracle(precision):
     sample = (dd(obs), dd(vobs), dd(h0), dd(actions), dd(old_v), dd(ret), dd(masks), dd(old_logp), dd(adv))
     for chunk_rows, time_chunks, budget in ((40, 4, 6 << 30), (2048, 3, 6 << 30), (32, 4, 0)):
         eng.chunk_rows, eng.time_chunks, eng.cols_budget, eng.overlap_gru = chunk_rows, time_chunks, budget, True
-        assert len(eng._chunks(B, E)) >= 3
+        # (the implicit-GEMM convolutions of the tf32x3 mode have no im2col scratch to bound: only the time chunks cut there)
+        assert len(eng._chunks(B, E)) >= (1 if precision == "tf32x3" else 3)
         eng.train_minibatch(sample, 0.1, 0.5, 0.001)
         torch.cuda.synchronize()
         np.testing.assert_allclose(eng.flat_grad.cpu().numpy(), g1.cpu().numpy(), rtol=1e-3 if loose else 1e-4,
