@@ -282,7 +282,8 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                smem_u32(acc_full), smem_u32(acc_empty), a.conv.mode, a.total_items);
 #endif
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 4); }
+        // convolution stages are filled by TWO producer warps (each arms the barrier for its own boxes)
+        for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], a.conv.mode ? 2 : 1); mbar_init(&empty_a[s], 4); }
         for (int s = 0; s < kMaxSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < kTA; ++s) { mbar_init(&ta_full[s], 4); mbar_init(&ta_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
@@ -302,9 +303,12 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (warp == 0) {
+    if (warp == 0 || (warp == 3 && a.conv.mode)) {
         // ================= TMA producer, A tiles.  Convolution tiles are several boxes per stage: LANE g computes the
-        // coordinates of box g (vector datapath, all boxes in parallel) and issues its own copy.
+        // coordinates of box g (vector datapath, all boxes in parallel) and issues its own copy.  Issuing a box costs
+        // ~130 clocks (the compiler serialises the per-lane copies through uniform registers), so the boxes of a stage are
+        // shared between two producer warps: warp 0 takes the first half, warp 3 the second.
+        const int pw = warp == 0 ? 0 : 1;
         uint32_t it = 0;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
             const Item t = decode(a, w);
@@ -328,10 +332,12 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int ch0 = 2 * t.cls;
                     const int nhalf = min(2, cv.nchunks - ch0);
                     const uint32_t seg_bytes = (uint32_t)cv.segw * 256u;
-                    if (lane == 0) { TCA_TRACE1(it, 0); mbar_expect_tx(&full_a[s], (uint32_t)(nvalid * nhalf) * seg_bytes); }
+                    const int nops = nvalid * nhalf, lo_op = pw ? (nops + 1) / 2 : 0, hi_op = pw ? nops : (nops + 1) / 2;
+                    if (lane == 0) { TCA_TRACE1(it, pw ? 10 : 0); mbar_expect_tx(&full_a[s], (uint32_t)(hi_op - lo_op) * seg_bytes); }
                     __syncwarp();
-                    if (lane < nvalid * nhalf) {
-                        const int g = (nhalf == 2) ? (lane >> 1) : lane, hh = (nhalf == 2) ? (lane & 1) : 0;
+                    const int op = lo_op + lane;
+                    if (op < hi_op) {
+                        const int g = (nhalf == 2) ? (op >> 1) : op, hh = (nhalf == 2) ? (op & 1) : 0;
                         const int sg = seg0 + g;
                         const int rowidx = fdiv(sg, cv.spr), ox0 = (sg - rowidx * cv.spr) * cv.segw;
                         const int b = fdiv(rowidx, cv.rows_per_img), oy = rowidx - b * cv.rows_per_img;
@@ -349,19 +355,23 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int kyg = 32 / cv.KW;
                     const uint32_t seg_bytes = (uint32_t)(kyg * cv.Win) * 4u;
                     const uint32_t seg_pitch = (seg_bytes + 127u) & ~127u;         // TMA destinations are 128-byte aligned
-                    if (lane == 0) { TCA_TRACE1(it, 0); mbar_expect_tx(&full_a[s], (uint32_t)t.nvalid * seg_bytes); }
+                    const int lo_op = pw ? (t.nvalid + 1) / 2 : 0, hi_op = pw ? t.nvalid : (t.nvalid + 1) / 2;
+                    if (lane == 0) { TCA_TRACE1(it, pw ? 10 : 0); mbar_expect_tx(&full_a[s], (uint32_t)(hi_op - lo_op) * seg_bytes); }
                     __syncwarp();
-                    if (lane < t.nvalid) {
+                    const int op = lo_op + lane;
+                    if (op < hi_op) {
                         const int c = fdiv(kb, cv.kpk), kyq = kb - c * cv.kpk;
-                        const int sg = t.seg0 + lane;
+                        const int sg = t.seg0 + op;
                         const int b = fdiv(sg, cv.rows_per_img), oy = sg - b * cv.rows_per_img;
-                        tma_load_2d(&tmA, &full_a[s], sa + lane * seg_pitch, 0, (b * cv.C + c) * cv.Hin + oy * cv.s + kyq * kyg);
+                        tma_load_2d(&tmA, &full_a[s], sa + op * seg_pitch, 0, (b * cv.C + c) * cv.Hin + oy * cv.s + kyq * kyg);
                     }
                 } else {
                     const uint32_t seg_bytes = (uint32_t)cv.segw * 128u;
-                    if (lane == 0) { TCA_TRACE1(it, 0); mbar_expect_tx(&full_a[s], (uint32_t)t.nvalid * seg_bytes); }
+                    const int lo_op = pw ? (t.nvalid + 1) / 2 : 0, hi_op = pw ? t.nvalid : (t.nvalid + 1) / 2;
+                    if (lane == 0) { TCA_TRACE1(it, pw ? 10 : 0); mbar_expect_tx(&full_a[s], (uint32_t)(hi_op - lo_op) * seg_bytes); }
                     __syncwarp();
-                    if (lane < t.nvalid) {
+                    const int op = lo_op + lane;
+                    if (op < hi_op) {
                         int c0, dx1, dy2;               // inner coordinate, pixel offset, row offset shared by the segments
                         if (cv.mode == 1) {
                             const int ky = fdiv(kb, cv.kpk);
@@ -371,9 +381,9 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             const int dky = fdiv(tap, cv.T), dkx = tap - dky * cv.T;
                             c0 = (kb - tap * cv.kpk) * 32; dx1 = -dkx; dy2 = -dky;
                         }
-                        const int sg = t.seg0 + lane;
+                        const int sg = t.seg0 + op;
                         const int b = fdiv(sg, cv.rows_per_img), row = sg - b * cv.rows_per_img;
-                        tma_load_4d(&tmA, &full_a[s], dst0 + lane * seg_bytes, c0, dx1, (cv.mode == 1 ? row * cv.s : row) + dy2, b);
+                        tma_load_4d(&tmA, &full_a[s], dst0 + op * seg_bytes, c0, dx1, (cv.mode == 1 ? row * cv.s : row) + dy2, b);
                     }
                 }
                 __syncwarp();
@@ -463,7 +473,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             __syncwarp();
         }
     } else if (warp == 3) {
-        // spare
+        // (second A producer in convolution modes, handled above; idle for plain GEMMs)
     } else if (warp < 4 + kXformWarps) {
         // ================= transform: two groups of four warps take alternate k-blocks (two k-blocks in flight hide
         // the shared-memory / TMEM / barrier latencies of one another); thread = one tile row, all 32 contraction columns

@@ -18,6 +18,7 @@ Data layout in HBM
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -84,7 +85,8 @@ class PolicyEngine:
         self.device = None
         self.flat = None
         self._buffers = {}
-        self.overlap_wgrad = True         # weight-gradient GEMMs / bias sums on a second stream, concurrent with the dgrad chain
+        # weight-gradient GEMMs / bias sums on a second stream, concurrent with the dgrad chain
+        self.overlap_wgrad = os.environ.get("PPD_OVERLAP_WGRAD", "1") != "0"
         # GRU time chunks on their own stream, concurrent with the trunk of other chunks.  Off by default: measured on
         # B200 at the PPO-Dash shape (T=512, E=4) it is SLOWER (265.6 vs 248.6 ms per update): a 16-CTA cluster with the
         # full register file per CTA cannot be co-scheduled while trunk kernels occupy the SMs, so the chunks serialise
