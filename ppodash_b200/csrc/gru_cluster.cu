@@ -288,21 +288,24 @@ __global__ void __launch_bounds__(kThreads, 1) gru_bwd_cluster_kernel(const BwdA
 // =====================================================================================================
 // H = 512 specialisations with the W_hh slice held in REGISTERS (the generic kernels above stream the
 // 192 KB slice from shared memory every step: 1536 cycles at 128 B/clk, the dominant per-step cost).
-//   forward : 384 threads; thread (row r = tid/4, quarter q = tid%4) keeps W_hh[row r][q*128 .. +128) in
-//             128 registers; per step 32 broadcast LDS.128 of the state + 128 FMAs + 2 shuffles.
+//   forward : 384 threads; thread (row group rg = tid/16, column chunk cc = tid%16) keeps the 4 x 32 block
+//             W_hh[rows 4rg..4rg+3][32cc .. +32) in 128 registers; per step 8 LDS.128 of the state (each value feeds
+//             4 rows: 384 shared-memory wavefronts per step instead of the 1536 of a one-row-per-thread mapping, which
+//             was the dominant per-step cost), 128 FMAs and a 16-lane shuffle reduction of the 4 partial sums.
 //   backward: 512 threads; thread k keeps the column W_hh[own rows][k] in 96 registers; per step 24
 //             broadcast LDS.128 of d(gates) + 96 FMAs, no reduction, result pushed straight to its owner.
 // =====================================================================================================
 constexpr int kH = 512, kHU = kH / CS, kR = 3 * kHU;      // 32 units, 96 rows per CTA
 constexpr int kFwdThreads = kR * 4;                        // 384
-constexpr int kQ = kH / 4;                                 // 128 state values per quarter
-constexpr int kQPad = kQ + 4;                              // quarter stride in smem: conflict-free broadcast reads
+constexpr int kCW = 32;                                    // state values per column chunk
+constexpr int kNC = kH / kCW;                              // 16 chunks
+constexpr int kCPad = kCW + 4;                             // chunk stride in smem: the 8 lanes of an LDS.128 phase hit 32 banks
 
-__device__ __forceinline__ int hpad(int j) { return (j / kQ) * kQPad + (j % kQ); }
+__device__ __forceinline__ int hpad(int j) { return (j / kCW) * kCPad + (j % kCW); }
 
 __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(const FwdArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
-    __shared__ __align__(16) float hb[2][4 * kQPad];      // masked previous state, padded quarters, double-buffered
+    __shared__ __align__(16) float hb[2][kNC * kCPad];    // masked previous state, padded chunks, double-buffered
     __shared__ float gh[kR];
     __shared__ float stage[kHU];
     __shared__ __align__(8) uint64_t hbar[2];
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(cons
     const int env = blockIdx.x / CS;
     const int j0 = rank * kHU;
     const int tid = threadIdx.x;
-    const int r = tid >> 2, q = tid & 3;
+    const int rg = tid >> 4, cc = tid & 15;
     const uint32_t step_bytes = kH * 4;
     if (tid == 0) {
         mbar_init(&hbar[0], 1);
@@ -320,14 +323,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(cons
         mbar_arm(&hbar[1], step_bytes);
         mbar_arm(&hbar[0], step_bytes);
     }
-    float w[kQ];
-    {
-        const int g = r / kHU, u = r - g * kHU;
-        const float4* src = reinterpret_cast<const float4*>(a.w_hh + (size_t)(g * kH + j0 + u) * kH + q * kQ);
+    float w[4][kCW];
 #pragma unroll
-        for (int i = 0; i < kQ / 4; ++i) {
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = 4 * rg + rr;
+        const int g = r / kHU, u = r - g * kHU;
+        const float4* src = reinterpret_cast<const float4*>(a.w_hh + (size_t)(g * kH + j0 + u) * kH + cc * kCW);
+#pragma unroll
+        for (int i = 0; i < kCW / 4; ++i) {
             const float4 v = __ldg(src + i);
-            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            w[rr][4 * i] = v.x; w[rr][4 * i + 1] = v.y; w[rr][4 * i + 2] = v.z; w[rr][4 * i + 3] = v.w;
         }
     }
     {
@@ -349,22 +354,32 @@ __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(cons
     for (int t = 0; t < a.T; ++t) {
         const float* hcur = hb[t & 1];
         if (t > 0) mbar_wait(&hbar[t & 1], (uint32_t)((t - 1) >> 1) & 1u);
-        // ---- quarter dot product, 4 independent accumulators
+        // ---- 4 x 32 block of the mat-vec: every state value read from shared memory feeds four rows
         {
-            const float4* h4 = reinterpret_cast<const float4*>(hcur + q * kQPad);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            const float4* h4 = reinterpret_cast<const float4*>(hcur + cc * kCPad);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int i = 0; i < kQ / 4; ++i) {
+            for (int i = 0; i < kCW / 4; ++i) {
                 const float4 hv = h4[i];
-                a0 = fmaf(w[4 * i], hv.x, a0);
-                a1 = fmaf(w[4 * i + 1], hv.y, a1);
-                a2 = fmaf(w[4 * i + 2], hv.z, a2);
-                a3 = fmaf(w[4 * i + 3], hv.w, a3);
+                s0 = fmaf(w[0][4 * i], hv.x, s0); s1 = fmaf(w[1][4 * i], hv.x, s1); s2 = fmaf(w[2][4 * i], hv.x, s2); s3 = fmaf(w[3][4 * i], hv.x, s3);
+                s0 = fmaf(w[0][4 * i + 1], hv.y, s0); s1 = fmaf(w[1][4 * i + 1], hv.y, s1); s2 = fmaf(w[2][4 * i + 1], hv.y, s2); s3 = fmaf(w[3][4 * i + 1], hv.y, s3);
+                s0 = fmaf(w[0][4 * i + 2], hv.z, s0); s1 = fmaf(w[1][4 * i + 2], hv.z, s1); s2 = fmaf(w[2][4 * i + 2], hv.z, s2); s3 = fmaf(w[3][4 * i + 2], hv.z, s3);
+                s0 = fmaf(w[0][4 * i + 3], hv.w, s0); s1 = fmaf(w[1][4 * i + 3], hv.w, s1); s2 = fmaf(w[2][4 * i + 3], hv.w, s2); s3 = fmaf(w[3][4 * i + 3], hv.w, s3);
             }
-            float acc = (a0 + a1) + (a2 + a3);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            if (q == 0) gh[r] = acc;
+            // sum over the 16 column chunks (lanes of one half-warp); after each exchange a lane keeps the sums it still owns:
+            // xor 8: rows {0,1} <-> {2,3}; xor 4: row pairs; then plain butterflies -- 4 + 2 + 1 + 1 = 8 shuffles instead of 16
+            {
+                const bool up = (cc & 8) != 0;
+                const float k0 = up ? s2 : s0, k1 = up ? s3 : s1, g0 = up ? s0 : s2, g1 = up ? s1 : s3;
+                const float r0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 8), r1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 8);
+                const bool up4 = (cc & 4) != 0;
+                const float kk = up4 ? r1 : r0, gg = up4 ? r0 : r1;
+                float acc = kk + __shfl_xor_sync(0xffffffffu, gg, 4);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                // lanes with cc % 4 == 0 hold row 4rg + 2*(cc>>3 & 1) + (cc>>2 & 1)
+                if ((cc & 3) == 0) gh[4 * rg + ((cc >> 3) & 1) * 2 + ((cc >> 2) & 1)] = acc;
+            }
         }
         __syncthreads();
         const size_t row = (size_t)t * E + env;

@@ -84,6 +84,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void*, int, int, uint32_t dst, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(smem_u32(bar)), "r"(0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
@@ -304,10 +310,8 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp == 0 || (warp == 3 && a.conv.mode)) {
-        // ================= TMA producer, A tiles.  Convolution tiles are several boxes per stage: LANE g computes the
-        // coordinates of box g (vector datapath, all boxes in parallel) and issues its own copy.  Issuing a box costs
-        // ~130 clocks (the compiler serialises the per-lane copies through uniform registers), so the boxes of a stage are
-        // shared between two producer warps: warp 0 takes the first half, warp 3 the second.
+        // ================= TMA producer, A tiles.  A convolution stage is several boxes; they are shared between two
+        // producer warps (warp 0 and, in convolution modes, warp 3), each walking its boxes from one elected thread.
         const int pw = warp == 0 ? 0 : 1;
         uint32_t it = 0;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
@@ -327,63 +331,74 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         else         tma_load_2d(&tmA, &full_a[s], sa, (int)t.i0, kk);     // box {128 rows, 32 k}, no swizzle
                     }
                 } else if (cv.mode == 3) {
+                    // boxes of this stage: (segment g, chunk half hh).  Two chunk halves: warp 0 loads half 0, warp 3 half 1;
+                    // a single half: the segments are split between the warps.  One elected thread walks its boxes with
+                    // incrementally updated coordinates (a uniform-datapath loop: ~55 clocks per box, against ~200 when
+                    // every lane issues its own box and the compiler serialises them through R2UR broadcasts).
                     const int seg0 = (t.kb0 + kb) * cv.nseg;
                     const int nvalid = min(cv.nseg, cv.total_seg - seg0);
                     const int ch0 = 2 * t.cls;
                     const int nhalf = min(2, cv.nchunks - ch0);
                     const uint32_t seg_bytes = (uint32_t)cv.segw * 256u;
-                    const int nops = nvalid * nhalf, lo_op = pw ? (nops + 1) / 2 : 0, hi_op = pw ? nops : (nops + 1) / 2;
-                    if (lane == 0) { TCA_TRACE1(it, pw ? 10 : 0); mbar_expect_tx(&full_a[s], (uint32_t)(hi_op - lo_op) * seg_bytes); }
-                    __syncwarp();
-                    const int op = lo_op + lane;
-                    if (op < hi_op) {
-                        const int g = (nhalf == 2) ? (op >> 1) : op, hh = (nhalf == 2) ? (op & 1) : 0;
-                        const int sg = seg0 + g;
-                        const int rowidx = fdiv(sg, cv.spr), ox0 = (sg - rowidx * cv.spr) * cv.segw;
-                        const int b = fdiv(rowidx, cv.rows_per_img), oy = rowidx - b * cv.rows_per_img;
+                    int g_lo, g_hi, hh;
+                    if (nhalf == 2) { g_lo = 0; g_hi = nvalid; hh = pw; }
+                    else { g_lo = pw ? (nvalid + 1) / 2 : 0; g_hi = pw ? nvalid : (nvalid + 1) / 2; hh = 0; }
+                    const int sg0 = seg0 + g_lo;
+                    const int rowidx0 = fdiv(sg0, cv.spr);
+                    const int b0 = fdiv(rowidx0, cv.rows_per_img);
+                    if (elect_one()) {
+                        TCA_TRACE1(it, pw ? 10 : 0);
+                        mbar_expect_tx(&full_a[s], (uint32_t)(g_hi - g_lo) * seg_bytes);
+                        int sub = sg0 - rowidx0 * cv.spr, oy = rowidx0 - b0 * cv.rows_per_img, b = b0;
                         const int ch = ch0 + hh;
-                        const uint32_t dst = dst0 + hh * 8192u + g * seg_bytes;
-                        if (cv.nchw) {
-                            tma_load_5d(&tmA, &full_a[s], dst, 0, 0, ox0, oy, b * cv.C + ch);
-                        } else {
-                            const int ky = fdiv(ch, cv.cpr);
-                            tma_load_4d(&tmA, &full_a[s], dst, (ch - ky * cv.cpr) * 64, ox0, oy * cv.s + ky, b);
+                        const int ky = cv.nchw ? 0 : fdiv(ch, cv.cpr);
+                        const int j0 = (ch - ky * cv.cpr) * 64;
+                        uint32_t dst = dst0 + hh * 8192u + g_lo * seg_bytes;
+                        for (int g = g_lo; g < g_hi; ++g, dst += seg_bytes) {
+                            if (cv.nchw) tma_load_5d(&tmA, &full_a[s], dst, 0, 0, sub * cv.segw, oy, b * cv.C + ch);
+                            else         tma_load_4d(&tmA, &full_a[s], dst, j0, sub * cv.segw, oy * cv.s + ky, b);
+                            if (++sub == cv.spr) { sub = 0; if (++oy == cv.rows_per_img) { oy = 0; ++b; } }
                         }
-                    }
-                } else if (cv.mode == 4) {
-                    // raw image rows: box {W floats, kyg rows} at row (b*C + c)*H + s*oy + kyq*kyg of x viewed as [B*C*H, W]
-                    const int kyg = 32 / cv.KW;
-                    const uint32_t seg_bytes = (uint32_t)(kyg * cv.Win) * 4u;
-                    const uint32_t seg_pitch = (seg_bytes + 127u) & ~127u;         // TMA destinations are 128-byte aligned
-                    const int lo_op = pw ? (t.nvalid + 1) / 2 : 0, hi_op = pw ? t.nvalid : (t.nvalid + 1) / 2;
-                    if (lane == 0) { TCA_TRACE1(it, pw ? 10 : 0); mbar_expect_tx(&full_a[s], (uint32_t)(hi_op - lo_op) * seg_bytes); }
-                    __syncwarp();
-                    const int op = lo_op + lane;
-                    if (op < hi_op) {
-                        const int c = fdiv(kb, cv.kpk), kyq = kb - c * cv.kpk;
-                        const int sg = t.seg0 + op;
-                        const int b = fdiv(sg, cv.rows_per_img), oy = sg - b * cv.rows_per_img;
-                        tma_load_2d(&tmA, &full_a[s], sa + op * seg_pitch, 0, (b * cv.C + c) * cv.Hin + oy * cv.s + kyq * kyg);
                     }
                 } else {
-                    const uint32_t seg_bytes = (uint32_t)cv.segw * 128u;
+                    // modes 1, 2, 4: the segments of a tile are consecutive rows (b, row); the two producer warps take half each
                     const int lo_op = pw ? (t.nvalid + 1) / 2 : 0, hi_op = pw ? t.nvalid : (t.nvalid + 1) / 2;
-                    if (lane == 0) { TCA_TRACE1(it, pw ? 10 : 0); mbar_expect_tx(&full_a[s], (uint32_t)(hi_op - lo_op) * seg_bytes); }
-                    __syncwarp();
-                    const int op = lo_op + lane;
-                    if (op < hi_op) {
-                        int c0, dx1, dy2;               // inner coordinate, pixel offset, row offset shared by the segments
-                        if (cv.mode == 1) {
-                            const int ky = fdiv(kb, cv.kpk);
-                            c0 = (kb - ky * cv.kpk) * 32; dx1 = 0; dy2 = ky;
+                    const int sg0 = t.seg0 + lo_op;
+                    const int b0 = fdiv(sg0, cv.rows_per_img);
+                    int c0 = 0, dx1 = 0, dy2 = 0, cch = 0;
+                    if (cv.mode == 1) {
+                        const int ky = fdiv(kb, cv.kpk);
+                        c0 = (kb - ky * cv.kpk) * 32; dy2 = ky;
+                    } else if (cv.mode == 2) {
+                        const int tap = fdiv(kb, cv.kpk);
+                        const int dky = fdiv(tap, cv.T), dkx = tap - dky * cv.T;
+                        c0 = (kb - tap * cv.kpk) * 32; dx1 = -dkx; dy2 = -dky;
+                    } else {
+                        cch = fdiv(kb, cv.kpk);                      // channel; dy2 = first filter row of this k-block
+                        dy2 = (kb - cch * cv.kpk) * (32 / cv.KW);
+                    }
+                    if (elect_one()) {
+                        TCA_TRACE1(it, pw ? 10 : 0);
+                        int row = sg0 - b0 * cv.rows_per_img, b = b0;
+                        if (cv.mode == 4) {
+                            // raw image rows: box {W floats, kyg rows} at row (b*C + c)*H + s*oy + ky0 of x viewed as [B*C*H, W]
+                            const uint32_t seg_bytes = (uint32_t)(32 / cv.KW * cv.Win) * 4u;
+                            const uint32_t seg_pitch = (seg_bytes + 127u) & ~127u;         // TMA destinations are 128-byte aligned
+                            mbar_expect_tx(&full_a[s], (uint32_t)(hi_op - lo_op) * seg_bytes);
+                            uint32_t dst = dst0 + lo_op * seg_pitch;
+                            for (int g = lo_op; g < hi_op; ++g, dst += seg_pitch) {
+                                tma_load_2d(&tmA, &full_a[s], reinterpret_cast<void*>(0), 0, 0, dst, (b * cv.C + cch) * cv.Hin + row * cv.s + dy2);
+                                if (++row == cv.rows_per_img) { row = 0; ++b; }
+                            }
                         } else {
-                            const int tap = fdiv(kb, cv.kpk);
-                            const int dky = fdiv(tap, cv.T), dkx = tap - dky * cv.T;
-                            c0 = (kb - tap * cv.kpk) * 32; dx1 = -dkx; dy2 = -dky;
+                            const uint32_t seg_bytes = (uint32_t)cv.segw * 128u;
+                            mbar_expect_tx(&full_a[s], (uint32_t)(hi_op - lo_op) * seg_bytes);
+                            uint32_t dst = dst0 + lo_op * seg_bytes;
+                            for (int g = lo_op; g < hi_op; ++g, dst += seg_bytes) {
+                                tma_load_4d(&tmA, &full_a[s], dst, c0, dx1, (cv.mode == 1 ? row * cv.s : row) + dy2, b);
+                                if (++row == cv.rows_per_img) { row = 0; ++b; }
+                            }
                         }
-                        const int sg = t.seg0 + op;
-                        const int b = fdiv(sg, cv.rows_per_img), row = sg - b * cv.rows_per_img;
-                        tma_load_4d(&tmA, &full_a[s], dst0 + op * seg_bytes, c0, dx1, (cv.mode == 1 ? row * cv.s : row) + dy2, b);
                     }
                 }
                 __syncwarp();

@@ -36,9 +36,9 @@ _lib.check(fn())
 torch.cuda.synchronize()
 t = tr.cpu().view(256, 16)
 t0 = int(t[0, 0])
-names = ["A.issue", "B.issue", "X.wait", "X.full", "X.read", "X.ta", "X.st", "X.done", "M.ready", "M.issued"]
+names = ["A.issue", "B.issue", "X.wait", "X.full", "X.read", "X.ta", "X.st", "X.done", "M.ready", "M.issued", "A2.issue"]
 print(case, "k-block timeline of CTA 0 (clocks since first A issue)")
 print("  it " + " ".join(f"{n:>9s}" for n in names))
 for it in range(40, 60):
-    print(f"{it:4d} " + " ".join(f"{int(t[it, k]) - t0:9d}" if int(t[it, k]) else "        -" for k in range(10)))
+    print(f"{it:4d} " + " ".join(f"{int(t[it, k]) - t0:9d}" if int(t[it, k]) else "        -" for k in range(11)))
 print("clocks per k-block (steady state):", (t[200, 9] - t[40, 9]).item() / 160)
