@@ -292,8 +292,10 @@ __global__ void __launch_bounds__(kThreads, 1) gru_bwd_cluster_kernel(const BwdA
 //             W_hh[rows 4rg..4rg+3][32cc .. +32) in 128 registers; per step 8 LDS.128 of the state (each value feeds
 //             4 rows: 384 shared-memory wavefronts per step instead of the 1536 of a one-row-per-thread mapping, which
 //             was the dominant per-step cost), 128 FMAs and a 16-lane shuffle reduction of the 4 partial sums.
-//   backward: 512 threads; thread k keeps the column W_hh[own rows][k] in 96 registers; per step 24
-//             broadcast LDS.128 of d(gates) + 96 FMAs, no reduction, result pushed straight to its owner.
+//   backward: 512 threads; thread (column group cg = tid/4, row quarter rq = tid%4) keeps the 24 x 4 block
+//             W_hh[own rows 24rq..24rq+23][4cg .. +4) in 96 registers; per step 6 LDS.128 of d(gates) (each value feeds
+//             4 columns: 384 shared-memory wavefronts per step instead of 1536), 96 FMAs and a 3-shuffle reduction over the
+//             4 row quarters that leaves thread tid with the partial sum of unit tid, pushed straight to its owner.
 // =====================================================================================================
 constexpr int kH = 512, kHU = kH / CS, kR = 3 * kHU;      // 32 units, 96 rows per CTA
 constexpr int kFwdThreads = kR * 4;                        // 384
@@ -434,11 +436,14 @@ __global__ void __launch_bounds__(kH, 1) gru_bwd_cluster512_kernel(const BwdArgs
         mbar_arm(&rbar[0], step_bytes);
         mbar_arm(&rbar[1], step_bytes);
     }
-    float wc[kR];                                 // W_hh[own row r][k = tid]
+    const int cg4 = tid >> 2, rq = tid & 3;
+    float wc[kR / 4][4];                          // W_hh[own row 24rq + i][4cg4 + c]
 #pragma unroll
-    for (int r = 0; r < kR; ++r) {
+    for (int i = 0; i < kR / 4; ++i) {
+        const int r = (kR / 4) * rq + i;
         const int g = r / kHU, u = r - g * kHU;
-        wc[r] = __ldg(a.w_hh + (size_t)(g * kH + j0 + u) * kH + tid);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.w_hh + (size_t)(g * kH + j0 + u) * kH + 4 * cg4));
+        wc[i][0] = v.x; wc[i][1] = v.y; wc[i][2] = v.z; wc[i][3] = v.w;
     }
     const bool gate_thread = tid < kHU;
     const int ju = j0 + tid;
@@ -484,17 +489,23 @@ __global__ void __launch_bounds__(kH, 1) gru_bwd_cluster512_kernel(const BwdArgs
         // ---- partial dh_{t-1}[k] over this CTA's 96 rows
         float s;
         {
-            const float4* d4 = reinterpret_cast<const float4*>(dgh);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            const float4* d4 = reinterpret_cast<const float4*>(dgh + (kR / 4) * rq);
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;      // columns 4cg4 .. +3 over this thread's 24 rows
 #pragma unroll
-            for (int i = 0; i < kR / 4; ++i) {
+            for (int i = 0; i < kR / 16; ++i) {
                 const float4 dv = d4[i];
-                a0 = fmaf(dv.x, wc[4 * i], a0);
-                a1 = fmaf(dv.y, wc[4 * i + 1], a1);
-                a2 = fmaf(dv.z, wc[4 * i + 2], a2);
-                a3 = fmaf(dv.w, wc[4 * i + 3], a3);
+                c0 = fmaf(dv.x, wc[4 * i][0], c0); c1 = fmaf(dv.x, wc[4 * i][1], c1); c2 = fmaf(dv.x, wc[4 * i][2], c2); c3 = fmaf(dv.x, wc[4 * i][3], c3);
+                c0 = fmaf(dv.y, wc[4 * i + 1][0], c0); c1 = fmaf(dv.y, wc[4 * i + 1][1], c1); c2 = fmaf(dv.y, wc[4 * i + 1][2], c2); c3 = fmaf(dv.y, wc[4 * i + 1][3], c3);
+                c0 = fmaf(dv.z, wc[4 * i + 2][0], c0); c1 = fmaf(dv.z, wc[4 * i + 2][1], c1); c2 = fmaf(dv.z, wc[4 * i + 2][2], c2); c3 = fmaf(dv.z, wc[4 * i + 2][3], c3);
+                c0 = fmaf(dv.w, wc[4 * i + 3][0], c0); c1 = fmaf(dv.w, wc[4 * i + 3][1], c1); c2 = fmaf(dv.w, wc[4 * i + 3][2], c2); c3 = fmaf(dv.w, wc[4 * i + 3][3], c3);
             }
-            s = (a0 + a1) + (a2 + a3);
+            // sum over the 4 row quarters (adjacent lanes); each exchange halves what a lane keeps: lane rq ends with column rq,
+            // i.e. thread tid with unit 4cg4 + rq = tid
+            const bool up2 = (rq & 2) != 0;
+            const float k0 = up2 ? c2 : c0, k1 = up2 ? c3 : c1, g0 = up2 ? c0 : c2, g1 = up2 ? c1 : c3;
+            const float r0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 2), r1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 2);
+            const bool up1 = (rq & 1) != 0;
+            s = (up1 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, up1 ? r0 : r1, 1);
         }
         // ---- reduce-scatter: push to the owner of unit k
         st_async_f32(map_to_rank(smem_u32(&recv[t & 1][slot]), dst_rank), s, map_to_rank(smem_u32(&rbar[t & 1]), dst_rank));
