@@ -279,8 +279,13 @@ def run_b200(args, cfg):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- attribute the step to kernels (one extra, untimed-for-the-metric step with per-call CUDA events)
+    # (weight-gradient kernels normally run on a side stream; for attribution everything is put on one stream, so a kernel's
+    # time is its own and not the time it spent queued behind a concurrent persistent kernel)
+    eng = pol.engine()
+    ov, eng.overlap_wgrad = eng.overlap_wgrad, False
     with _lib.profiled() as prof:
         step(False)
+    eng.overlap_wgrad = ov
     per_kernel = prof.summary()
 
     if rank != 0:
@@ -295,6 +300,13 @@ def run_b200(args, cfg):
     total_ms = sum(d["ms"] for d in per_kernel.values())
     shares = sorted(((d["ms"], k, d["calls"]) for k, d in per_kernel.items()), reverse=True)
     top_ms, top_name, top_calls = shares[0]
+    # every convolution and every large GEMM of the network is one device kernel (tca_gemm_kernel, csrc/tca_gemm.cu) behind
+    # several C-ABI entry points: pool them, they are "the dominant kernel"
+    TCA = ("ppd_conv_fwd_nchw", "ppd_conv_fwd_nhwc", "ppd_conv_dgrad_nhwc", "ppd_conv_wgrad", "ppd_tc_gemm", "ppd_tc_gemm_bsplit")
+    tca_ms = sum(per_kernel[k]["ms"] for k in TCA if k in per_kernel)
+    tca_calls = sum(per_kernel[k]["calls"] for k in TCA if k in per_kernel)
+    if args.precision == "tf32x3" and tca_ms >= top_ms:
+        top_ms, top_name, top_calls = tca_ms, "tca_gemm_kernel", tca_calls
 
     # ---- roofline of the dominant kernel (algorithmic work per launch / measured launch time)
     H, V, A, C = cfg.hidden_size, cfg.vector_obs_len, cfg.num_actions, cfg.channels
@@ -312,6 +324,34 @@ def run_b200(args, cfg):
                     note=f"strictly sequential over T={T} with E={E} envs per minibatch: latency-bound (one grid "
                          f"barrier per timestep), the tensor roofline is not reachable at this E (SURVEY.md 7); "
                          f"peak = bf16 burst {pk['how']}")
+    elif top_name == "tca_gemm_kernel":
+        # Implicit-GEMM convolutions + the FC / GRU-projection GEMMs, 3xTF32.  Algorithmic bytes: every
+        # activation / gradient tensor read once and written once per product, weights once; NO im2col matrices (they do not
+        # exist any more).  Pooled over all launches of one step against the measured copy bandwidth.
+        Bm = rows_mb
+        s1, s2, s3 = 20, 9, 7
+        obs_b, a1_b, a2_b, a3_b = Bm * C * cfg.obs_hw ** 2, Bm * s1 * s1 * 32, Bm * s2 * s2 * 64, Bm * s3 * s3 * 32
+        K1, K2, K3, FD = C * 64, 512, 576, 1568
+        Ip = (H + V + 3) // 4 * 4
+        w = dict(c1=32 * K1, c2=64 * K2, c3=32 * K3, fc=H * FD, ih=3 * H * Ip, hh=3 * H * H)
+        rec = cfg.recurrent
+        fwd_b = (obs_b + w["c1"] + a1_b) + (a1_b + w["c2"] + a2_b) + (a2_b + w["c3"] + a3_b) + (a3_b + w["fc"] + Bm * H) + \
+                ((Bm * Ip + w["ih"] + Bm * 3 * H) if rec else 0)
+        dgrad_b = (Bm * H + w["fc"] + 2 * a3_b) + (a3_b + w["c3"] + 2 * a2_b) + (a2_b + w["c2"] + 2 * a1_b) + \
+                  ((Bm * 3 * H + w["ih"] + Bm * H + Bm * Ip) if rec else 0)          # dx written + ReLU mask read
+        wgrad_b = (obs_b + a1_b + w["c1"]) + (a1_b + a2_b + w["c2"]) + (a2_b + a3_b + w["c3"]) + (Bm * H + a3_b + w["fc"]) + \
+                  ((Bm * 3 * H + Bm * Ip + w["ih"] + Bm * 3 * H + 2 * Bm * H + w["hh"]) if rec else 0)
+        bytes_step = 4.0 * (fwd_b + dgrad_b + wgrad_b) * cfg.ppo_epoch * cfg.num_mini_batch
+        ach = bytes_step / (top_ms * 1e-3) / 1e9
+        fwd = 2.0 * (819200 * C + 2654208 + 903168 + 802816 + ((3 * H * (H + V)) if rec else 0))
+        tf = 3.0 * fwd * Bm * cfg.ppo_epoch * cfg.num_mini_batch / (top_ms * 1e-3) / 1e12
+        roof.update(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], tflops=tf,
+                    entry_points={k: round(per_kernel[k]["ms"], 3) for k in TCA if k in per_kernel},
+                    note=f"tca_gemm_kernel = persistent tcgen05 3xTF32 kernel (A operand through tensor memory) behind all "
+                         f"convolutions (implicit GEMM: TMA im2col views, no im2col matrix in HBM) and the FC / GRU-projection "
+                         f"GEMMs, all launches of one step pooled; achieved = algorithmic activation+gradient+weight bytes / summed "
+                         f"launch time; peak = copy bandwidth {pk['how']}; useful math {tf:.1f} TFLOP/s fp32-equivalent (x3 on the "
+                         f"TF32 pipe).  The conv2-class products (Cout = 64) are nearer the TF32 pipe than HBM: see profiles/.")
     elif top_name in ("ppd_sgemm", "ppd_tc_gemm"):
         # The network's GEMMs are skinny (N = 32 / 64 output channels, or a 2048-row minibatch): ~15-60 FLOP per byte,
         # far left of the tensor ridge (~170 FLOP/B for TF32), i.e. HBM-bound.  Algorithmic bytes = every operand read

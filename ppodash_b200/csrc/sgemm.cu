@@ -315,20 +315,31 @@ __global__ void __launch_bounds__(kThreads) colsum_multi_partial_kernel(const Mu
 }
 
 __global__ void __launch_bounds__(kThreads) colsum_multi_final_kernel(const MultiSegs m, const float* __restrict__ ws) {
+    // one block per 256 columns of a segment; when the segment is narrower the spare threads split the partials between them
+    // (a 32-column bias over ~800k rows has thousands of partials: one thread per column walking them all took 180 us)
+    __shared__ float sm[kThreads];
     int s = 0;
     while (s + 1 < m.n && (int)blockIdx.x >= m.final_off[s + 1]) ++s;
-    const int64_t j = (int64_t)(blockIdx.x - m.final_off[s]) * kThreads + threadIdx.x;
     const int64_t J = m.J[s];
-    if (j >= J) return;
-    const float* partial = ws + m.part_off[s];
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int64_t p = 0;
-    for (; p + 3 < m.parts[s]; p += 4) {
-        s0 += partial[p * J + j]; s1 += partial[(p + 1) * J + j]; s2 += partial[(p + 2) * J + j]; s3 += partial[(p + 3) * J + j];
+    const int64_t jb = (int64_t)(blockIdx.x - m.final_off[s]) * kThreads;
+    const int cols = (int)min((int64_t)kThreads, J - jb);
+    const int G = kThreads / cols;
+    const int g = threadIdx.x / cols, c = threadIdx.x - g * cols;
+    const float* partial = ws + m.part_off[s] + jb + c;
+    float s0 = 0.f, s1 = 0.f;
+    if (g < G) {
+        int64_t p = g;
+        for (; p + G < m.parts[s]; p += 2 * G) { s0 += partial[p * J]; s1 += partial[(p + G) * J]; }
+        if (p < m.parts[s]) s0 += partial[p * J];
     }
-    for (; p < m.parts[s]; ++p) s0 += partial[p * J + j];
-    const float t = (s0 + s1) + (s2 + s3);
-    m.out[s][j] = m.accumulate[s] ? (m.out[s][j] + t) : t;
+    sm[threadIdx.x] = s0 + s1;
+    __syncthreads();
+    if (g == 0) {
+        float t = 0.f;
+        for (int q = 0; q < G; ++q) t += sm[q * cols + c];
+        float* o = m.out[s] + jb + c;
+        *o = m.accumulate[s] ? (*o + t) : t;
+    }
 }
 
 struct Plan { int bi, bj; int64_t gx, gy; int splits; int64_t kk_per_split; size_t ws; };
