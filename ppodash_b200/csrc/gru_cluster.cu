@@ -305,6 +305,15 @@ constexpr int kCPad = kCW + 4;                             // chunk stride in sm
 
 __device__ __forceinline__ int hpad(int j) { return (j / kCW) * kCPad + (j % kCW); }
 
+// Packed fp32 FMA (sm_100a FFMA2): two independent fused multiply-adds per lane and instruction, c = a * b + c elementwise.
+// The mat-vec of a step is 49 152 FMAs per CTA; as scalar FFMA that alone is several hundred issue cycles of every step.
+__device__ __forceinline__ void ffma2(float2& c, const float2 a, const float2 b) {
+    unsigned long long cc = *reinterpret_cast<unsigned long long*>(&c);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cc) : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    c = *reinterpret_cast<float2*>(&cc);
+}
+
 __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(const FwdArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ __align__(16) float hb[2][kNC * kCPad];    // masked previous state, padded chunks, double-buffered
@@ -325,7 +334,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(cons
         mbar_arm(&hbar[1], step_bytes);
         mbar_arm(&hbar[0], step_bytes);
     }
-    float w[4][kCW];
+    float2 w[4][kCW / 2];
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
         const int r = 4 * rg + rr;
@@ -334,7 +343,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(cons
 #pragma unroll
         for (int i = 0; i < kCW / 4; ++i) {
             const float4 v = __ldg(src + i);
-            w[rr][4 * i] = v.x; w[rr][4 * i + 1] = v.y; w[rr][4 * i + 2] = v.z; w[rr][4 * i + 3] = v.w;
+            w[rr][2 * i] = make_float2(v.x, v.y); w[rr][2 * i + 1] = make_float2(v.z, v.w);
         }
     }
     {
@@ -359,15 +368,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(cons
         // ---- 4 x 32 block of the mat-vec: every state value read from shared memory feeds four rows
         {
             const float4* h4 = reinterpret_cast<const float4*>(hcur + cc * kCPad);
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;       // (even-k, odd-k) partial sums of the 4 rows
 #pragma unroll
             for (int i = 0; i < kCW / 4; ++i) {
                 const float4 hv = h4[i];
-                s0 = fmaf(w[0][4 * i], hv.x, s0); s1 = fmaf(w[1][4 * i], hv.x, s1); s2 = fmaf(w[2][4 * i], hv.x, s2); s3 = fmaf(w[3][4 * i], hv.x, s3);
-                s0 = fmaf(w[0][4 * i + 1], hv.y, s0); s1 = fmaf(w[1][4 * i + 1], hv.y, s1); s2 = fmaf(w[2][4 * i + 1], hv.y, s2); s3 = fmaf(w[3][4 * i + 1], hv.y, s3);
-                s0 = fmaf(w[0][4 * i + 2], hv.z, s0); s1 = fmaf(w[1][4 * i + 2], hv.z, s1); s2 = fmaf(w[2][4 * i + 2], hv.z, s2); s3 = fmaf(w[3][4 * i + 2], hv.z, s3);
-                s0 = fmaf(w[0][4 * i + 3], hv.w, s0); s1 = fmaf(w[1][4 * i + 3], hv.w, s1); s2 = fmaf(w[2][4 * i + 3], hv.w, s2); s3 = fmaf(w[3][4 * i + 3], hv.w, s3);
+                const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+                ffma2(q0, w[0][2 * i], h01); ffma2(q1, w[1][2 * i], h01); ffma2(q2, w[2][2 * i], h01); ffma2(q3, w[3][2 * i], h01);
+                ffma2(q0, w[0][2 * i + 1], h23); ffma2(q1, w[1][2 * i + 1], h23); ffma2(q2, w[2][2 * i + 1], h23); ffma2(q3, w[3][2 * i + 1], h23);
             }
+            const float s0 = q0.x + q0.y, s1 = q1.x + q1.y, s2 = q2.x + q2.y, s3 = q3.x + q3.y;
             // sum over the 16 column chunks (lanes of one half-warp); after each exchange a lane keeps the sums it still owns:
             // xor 8: rows {0,1} <-> {2,3}; xor 4: row pairs; then plain butterflies -- 4 + 2 + 1 + 1 = 8 shuffles instead of 16
             {
@@ -437,13 +446,13 @@ __global__ void __launch_bounds__(kH, 1) gru_bwd_cluster512_kernel(const BwdArgs
         mbar_arm(&rbar[1], step_bytes);
     }
     const int cg4 = tid >> 2, rq = tid & 3;
-    float wc[kR / 4][4];                          // W_hh[own row 24rq + i][4cg4 + c]
+    float2 wc[kR / 4][2];                         // W_hh[own row 24rq + i][4cg4 + (0,1) | (2,3)]
 #pragma unroll
     for (int i = 0; i < kR / 4; ++i) {
         const int r = (kR / 4) * rq + i;
         const int g = r / kHU, u = r - g * kHU;
         const float4 v = __ldg(reinterpret_cast<const float4*>(a.w_hh + (size_t)(g * kH + j0 + u) * kH + 4 * cg4));
-        wc[i][0] = v.x; wc[i][1] = v.y; wc[i][2] = v.z; wc[i][3] = v.w;
+        wc[i][0] = make_float2(v.x, v.y); wc[i][1] = make_float2(v.z, v.w);
     }
     const bool gate_thread = tid < kHU;
     const int ju = j0 + tid;
@@ -490,15 +499,17 @@ __global__ void __launch_bounds__(kH, 1) gru_bwd_cluster512_kernel(const BwdArgs
         float s;
         {
             const float4* d4 = reinterpret_cast<const float4*>(dgh + (kR / 4) * rq);
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;      // columns 4cg4 .. +3 over this thread's 24 rows
+            float2 c01 = make_float2(0.f, 0.f), c23 = c01;      // columns 4cg4 .. +3 over this thread's 24 rows
 #pragma unroll
             for (int i = 0; i < kR / 16; ++i) {
                 const float4 dv = d4[i];
-                c0 = fmaf(dv.x, wc[4 * i][0], c0); c1 = fmaf(dv.x, wc[4 * i][1], c1); c2 = fmaf(dv.x, wc[4 * i][2], c2); c3 = fmaf(dv.x, wc[4 * i][3], c3);
-                c0 = fmaf(dv.y, wc[4 * i + 1][0], c0); c1 = fmaf(dv.y, wc[4 * i + 1][1], c1); c2 = fmaf(dv.y, wc[4 * i + 1][2], c2); c3 = fmaf(dv.y, wc[4 * i + 1][3], c3);
-                c0 = fmaf(dv.z, wc[4 * i + 2][0], c0); c1 = fmaf(dv.z, wc[4 * i + 2][1], c1); c2 = fmaf(dv.z, wc[4 * i + 2][2], c2); c3 = fmaf(dv.z, wc[4 * i + 2][3], c3);
-                c0 = fmaf(dv.w, wc[4 * i + 3][0], c0); c1 = fmaf(dv.w, wc[4 * i + 3][1], c1); c2 = fmaf(dv.w, wc[4 * i + 3][2], c2); c3 = fmaf(dv.w, wc[4 * i + 3][3], c3);
+                const float2 dx = make_float2(dv.x, dv.x), dy = make_float2(dv.y, dv.y), dz = make_float2(dv.z, dv.z), dw = make_float2(dv.w, dv.w);
+                ffma2(c01, dx, wc[4 * i][0]); ffma2(c23, dx, wc[4 * i][1]);
+                ffma2(c01, dy, wc[4 * i + 1][0]); ffma2(c23, dy, wc[4 * i + 1][1]);
+                ffma2(c01, dz, wc[4 * i + 2][0]); ffma2(c23, dz, wc[4 * i + 2][1]);
+                ffma2(c01, dw, wc[4 * i + 3][0]); ffma2(c23, dw, wc[4 * i + 3][1]);
             }
+            const float c0 = c01.x, c1 = c01.y, c2 = c23.x, c3 = c23.y;
             // sum over the 4 row quarters (adjacent lanes); each exchange halves what a lane keeps: lane rq ends with column rq,
             // i.e. thread tid with unit 4cg4 + rq = tid
             const bool up2 = (rq & 2) != 0;
