@@ -18,11 +18,15 @@ gw2 = torch.zeros(64, 512, device=dev); gw1 = torch.zeros(32, 192, device=dev)
 ws = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
 w2 = torch.randn(64, 512, device=dev); hi2, lo2 = torch.empty_like(w2), torch.empty_like(w2)
 _lib.check(L.ppd_split_tf32(w2.data_ptr(), hi2.data_ptr(), lo2.data_ptr(), w2.numel(), st))
+w1 = torch.randn(32, 192, device=dev); hi1, lo1 = torch.empty_like(w1), torch.empty_like(w1)
+_lib.check(L.ppd_split_tf32(w1.data_ptr(), hi1.data_ptr(), lo1.data_ptr(), w1.numel(), st))
+o1 = torch.empty(B, 20, 20, 32, device=dev); b1 = torch.zeros(32, device=dev)
 o2 = torch.empty(B, 9, 9, 64, device=dev); b2 = torch.zeros(64, device=dev); dx1 = torch.empty_like(a1)
 fns = {
     "conv2.wgrad": lambda: L.ppd_conv_wgrad(a1.data_ptr(), ctypes.byref(g2), 0, dy2.data_ptr(), 64, gw2.data_ptr(), 0, ws.data_ptr(), ws.numel(), st),
     "conv1.wgrad": lambda: L.ppd_conv_wgrad(obs.data_ptr(), ctypes.byref(g1), 1, dy1.data_ptr(), 32, gw1.data_ptr(), 0, ws.data_ptr(), ws.numel(), st),
     "conv2.fwd": lambda: L.ppd_conv_fwd_nhwc(a1.data_ptr(), ctypes.byref(g2), 64, hi2.data_ptr(), lo2.data_ptr(), b2.data_ptr(), 1, o2.data_ptr(), st),
+    "conv1.fwd": lambda: L.ppd_conv_fwd_nchw(obs.data_ptr(), ctypes.byref(g1), 32, hi1.data_ptr(), lo1.data_ptr(), b1.data_ptr(), 1, o1.data_ptr(), st),
     "conv2.dgrad": lambda: L.ppd_conv_dgrad_nhwc(dy2.data_ptr(), ctypes.byref(g2), 64, hi2.data_ptr(), lo2.data_ptr(), a1.data_ptr(), dx1.data_ptr(), st),
 }
 fn = fns[case]
