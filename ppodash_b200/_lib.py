@@ -11,7 +11,8 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppodash_b200.so")
+# PPD_LIB: an alternative build of the same library (A/B timing of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("PPD_LIB") or os.path.join(_HERE, "libppodash_b200.so")
 
 
 class PpdError(RuntimeError):

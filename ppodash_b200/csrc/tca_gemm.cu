@@ -124,6 +124,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
         "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
     asm volatile(
@@ -309,10 +320,8 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (warp == 0 || (warp == 3 && a.conv.mode)) {
-        // ================= TMA producer, A tiles.  A convolution stage is several boxes; they are shared between two
-        // producer warps (warp 0 and, in convolution modes, warp 3), each walking its boxes from one elected thread.
-        const int pw = warp == 0 ? 0 : 1;
+    if (warp == 0 && a.conv.mode == 0) {
+        // ================= TMA producer, A tiles of a plain GEMM: one box per stage
         uint32_t it = 0;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
             const Item t = decode(a, w);
@@ -320,88 +329,117 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int kk = (int)(t.kk_begin + (int64_t)kb * BK);
                 const uint32_t s = it % kSA;
                 mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
-                uint8_t* sa = smemA + s * a_bytes;
-                const uint32_t dst0 = smem_u32(sa);
-                const ConvA& cv = a.conv;
-                if (cv.mode == 0) {
-                    if (elect_one()) {
-                        TCA_TRACE1(it, 0);
-                        mbar_expect_tx(&full_a[s], a_bytes);
-                        if (!a.a_mn) tma_load_2d(&tmA, &full_a[s], sa, kk, (int)t.i0);     // box {32 k, 128 rows}, 128B swizzle
-                        else         tma_load_2d(&tmA, &full_a[s], sa, (int)t.i0, kk);     // box {128 rows, 32 k}, no swizzle
-                    }
-                } else if (cv.mode == 3) {
-                    // boxes of this stage: (segment g, chunk half hh).  Two chunk halves: warp 0 loads half 0, warp 3 half 1;
-                    // a single half: the segments are split between the warps.  One elected thread walks its boxes with
-                    // incrementally updated coordinates (a uniform-datapath loop: ~55 clocks per box, against ~200 when
-                    // every lane issues its own box and the compiler serialises them through R2UR broadcasts).
-                    const int seg0 = (t.kb0 + kb) * cv.nseg;
-                    const int nvalid = min(cv.nseg, cv.total_seg - seg0);
-                    const int ch0 = 2 * t.cls;
-                    const int nhalf = min(2, cv.nchunks - ch0);
-                    const uint32_t seg_bytes = (uint32_t)cv.segw * 256u;
-                    int g_lo, g_hi, hh;
-                    if (nhalf == 2) { g_lo = 0; g_hi = nvalid; hh = pw; }
-                    else { g_lo = pw ? (nvalid + 1) / 2 : 0; g_hi = pw ? nvalid : (nvalid + 1) / 2; hh = 0; }
-                    const int sg0 = seg0 + g_lo;
-                    const int rowidx0 = fdiv(sg0, cv.spr);
-                    const int b0 = fdiv(rowidx0, cv.rows_per_img);
-                    if (elect_one()) {
-                        TCA_TRACE1(it, pw ? 10 : 0);
-                        mbar_expect_tx(&full_a[s], (uint32_t)(g_hi - g_lo) * seg_bytes);
-                        int sub = sg0 - rowidx0 * cv.spr, oy = rowidx0 - b0 * cv.rows_per_img, b = b0;
-                        const int ch = ch0 + hh;
-                        const int ky = cv.nchw ? 0 : fdiv(ch, cv.cpr);
-                        const int j0 = (ch - ky * cv.cpr) * 64;
-                        uint32_t dst = dst0 + hh * 8192u + g_lo * seg_bytes;
-                        for (int g = g_lo; g < g_hi; ++g, dst += seg_bytes) {
-                            if (cv.nchw) tma_load_5d(&tmA, &full_a[s], dst, 0, 0, sub * cv.segw, oy, b * cv.C + ch);
-                            else         tma_load_4d(&tmA, &full_a[s], dst, j0, sub * cv.segw, oy * cv.s + ky, b);
-                            if (++sub == cv.spr) { sub = 0; if (++oy == cv.rows_per_img) { oy = 0; ++b; } }
-                        }
-                    }
-                } else {
-                    // modes 1, 2, 4: the segments of a tile are consecutive rows (b, row); the two producer warps take half each
-                    const int lo_op = pw ? (t.nvalid + 1) / 2 : 0, hi_op = pw ? t.nvalid : (t.nvalid + 1) / 2;
-                    const int sg0 = t.seg0 + lo_op;
-                    const int b0 = fdiv(sg0, cv.rows_per_img);
-                    int c0 = 0, dx1 = 0, dy2 = 0, cch = 0;
-                    if (cv.mode == 1) {
-                        const int ky = fdiv(kb, cv.kpk);
-                        c0 = (kb - ky * cv.kpk) * 32; dy2 = ky;
-                    } else if (cv.mode == 2) {
-                        const int tap = fdiv(kb, cv.kpk);
-                        const int dky = fdiv(tap, cv.T), dkx = tap - dky * cv.T;
-                        c0 = (kb - tap * cv.kpk) * 32; dx1 = -dkx; dy2 = -dky;
-                    } else {
-                        cch = fdiv(kb, cv.kpk);                      // channel; dy2 = first filter row of this k-block
-                        dy2 = (kb - cch * cv.kpk) * (32 / cv.KW);
-                    }
-                    if (elect_one()) {
-                        TCA_TRACE1(it, pw ? 10 : 0);
-                        int row = sg0 - b0 * cv.rows_per_img, b = b0;
-                        if (cv.mode == 4) {
-                            // raw image rows: box {W floats, kyg rows} at row (b*C + c)*H + s*oy + ky0 of x viewed as [B*C*H, W]
-                            const uint32_t seg_bytes = (uint32_t)(32 / cv.KW * cv.Win) * 4u;
-                            const uint32_t seg_pitch = (seg_bytes + 127u) & ~127u;         // TMA destinations are 128-byte aligned
-                            mbar_expect_tx(&full_a[s], (uint32_t)(hi_op - lo_op) * seg_bytes);
-                            uint32_t dst = dst0 + lo_op * seg_pitch;
-                            for (int g = lo_op; g < hi_op; ++g, dst += seg_pitch) {
-                                tma_load_2d(&tmA, &full_a[s], reinterpret_cast<void*>(0), 0, 0, dst, (b * cv.C + cch) * cv.Hin + row * cv.s + dy2);
-                                if (++row == cv.rows_per_img) { row = 0; ++b; }
-                            }
-                        } else {
-                            const uint32_t seg_bytes = (uint32_t)cv.segw * 128u;
-                            mbar_expect_tx(&full_a[s], (uint32_t)(hi_op - lo_op) * seg_bytes);
-                            uint32_t dst = dst0 + lo_op * seg_bytes;
-                            for (int g = lo_op; g < hi_op; ++g, dst += seg_bytes) {
-                                tma_load_4d(&tmA, &full_a[s], dst, c0, dx1, (cv.mode == 1 ? row * cv.s : row) + dy2, b);
-                                if (++row == cv.rows_per_img) { row = 0; ++b; }
-                            }
-                        }
-                    }
+                if (elect_one()) {
+                    TCA_TRACE1(it, 0);
+                    uint8_t* sa = smemA + s * a_bytes;
+                    mbar_expect_tx(&full_a[s], a_bytes);
+                    if (!a.a_mn) tma_load_2d(&tmA, &full_a[s], sa, kk, (int)t.i0);     // box {32 k, 128 rows}, 128B swizzle
+                    else         tma_load_2d(&tmA, &full_a[s], sa, (int)t.i0, kk);     // box {128 rows, 32 k}, no swizzle
                 }
                 __syncwarp();
+            }
+        }
+    } else if ((warp == 0 || warp == 3) && a.conv.mode) {
+        // ================= TMA producers of a convolution: a stage is several boxes, shared between warp 0 and warp 3, each
+        // walking its boxes from one elected thread (~55 clocks per box in a uniform-datapath loop; every lane issuing its
+        // own box costs ~200: the compiler serialises them through R2UR broadcasts).  The k loop carries NO division: the
+        // position inside the filter and the (sample, row) of the first box advance as counters -- a run-time division on
+        // this path (even the float-reciprocal one) costs the producer hundreds of clocks per k-block, and the producer's own
+        // loop time, not the TMA engine or the transform warps, was what bounded every implicit convolution.
+        const ConvA& cv = a.conv;
+        const int pw = warp == 0 ? 0 : 1;
+        uint32_t it = 0;
+        if (cv.mode == 3) {
+            const uint32_t seg_bytes = (uint32_t)cv.segw * 256u;
+            for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
+                const Item t = decode(a, w);
+                const int ch0 = 2 * t.cls;
+                const int nhalf = min(2, cv.nchunks - ch0);
+                const int hh = nhalf == 2 ? pw : 0;
+                const int ch = ch0 + hh;
+                const int ky = cv.nchw ? 0 : fdiv(ch, cv.cpr);
+                const int j0 = (ch - ky * cv.cpr) * 64;
+                // running position of the next segment of this item: (sample b, output row oy, row segment sub)
+                int seg = t.kb0 * cv.nseg;
+                const int rowidx0 = fdiv(seg, cv.spr);
+                int b = fdiv(rowidx0, cv.rows_per_img);
+                int oy = rowidx0 - b * cv.rows_per_img, sub = seg - rowidx0 * cv.spr;
+                for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+                    const uint32_t s = it % kSA;
+                    mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
+                    const int nvalid = min(cv.nseg, cv.total_seg - seg);
+                    // two chunk halves: warp 0 loads half 0, warp 3 half 1 of every segment; one half: the segments are split
+                    int g_lo = 0, g_hi = nvalid;
+                    if (nhalf != 2) { g_lo = pw ? (nvalid + 1) / 2 : 0; g_hi = pw ? nvalid : (nvalid + 1) / 2; }
+                    const bool leader = elect_one();
+                    if (leader) {
+                        TCA_TRACE1(it, pw ? 10 : 0);
+                        mbar_expect_tx(&full_a[s], (uint32_t)(g_hi - g_lo) * seg_bytes);
+                    }
+                    uint32_t dst = smem_u32(smemA + s * a_bytes) + hh * 8192u;
+                    for (int g = 0; g < nvalid; ++g, dst += seg_bytes) {          // every lane walks (the position is per-thread state)
+                        if (leader && g >= g_lo && g < g_hi) {
+                            if (cv.nchw) tma_load_5d(&tmA, &full_a[s], dst, 0, 0, sub * cv.segw, oy, b * cv.C + ch);
+                            else         tma_load_4d(&tmA, &full_a[s], dst, j0, sub * cv.segw, oy * cv.s + ky, b);
+                        }
+                        if (++sub == cv.spr) { sub = 0; if (++oy == cv.rows_per_img) { oy = 0; ++b; } }
+                    }
+                    seg += nvalid;
+                    __syncwarp();
+                }
+            }
+        } else {
+            const int kyg = 32 / max(cv.KW, 1);
+            const uint32_t seg_bytes = cv.mode == 4 ? (uint32_t)(kyg * cv.Win) * 4u : (uint32_t)cv.segw * 128u;
+            const uint32_t seg_pitch = cv.mode == 4 ? ((seg_bytes + 127u) & ~127u) : seg_bytes;     // TMA destinations: 128-byte aligned
+            for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
+                const Item t = decode(a, w);
+                // modes 1, 2, 4: the segments of a tile are consecutive rows (b, row); the two producer warps take half each
+                const int lo_op = pw ? (t.nvalid + 1) / 2 : 0, hi_op = pw ? t.nvalid : (t.nvalid + 1) / 2;
+                const int sg0 = t.seg0 + lo_op;
+                const int b0 = fdiv(sg0, cv.rows_per_img);
+                const int row0 = sg0 - b0 * cv.rows_per_img;
+                // position inside the filter, advanced once per k-block:
+                //   mode 1: (c0 = float offset in the filter row, ky)   mode 2: (c0 = 32-channel chunk, dkx, dky)   mode 4: (kyq, channel)
+                int k0 = 0, k1 = 0, k2 = 0;
+                for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+                    const uint32_t s = it % kSA;
+                    mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
+                    if (elect_one()) {
+                        TCA_TRACE1(it, pw ? 10 : 0);
+                        mbar_expect_tx(&full_a[s], (uint32_t)(hi_op - lo_op) * seg_bytes);
+                        uint32_t dst = smem_u32(smemA + s * a_bytes) + lo_op * seg_pitch;
+                        int row = row0, b = b0;
+                        // one tight loop per mode: c = the coordinate that moves with the row, the rest is fixed for the stage
+                        if (cv.mode == 1) {
+                            const int c0 = k0 * 32;
+                            int y = row * cv.s + k1;
+                            for (int g = lo_op; g < hi_op; ++g, dst += seg_pitch) {
+                                tma_load_4d(&tmA, &full_a[s], dst, c0, 0, y, b);
+                                y += cv.s;
+                                if (++row == cv.rows_per_img) { row = 0; ++b; y = k1; }
+                            }
+                        } else if (cv.mode == 2) {
+                            const int c0 = k0 * 32, x0 = -k1;
+                            int y = row - k2;
+                            for (int g = lo_op; g < hi_op; ++g, dst += seg_pitch) {
+                                tma_load_4d(&tmA, &full_a[s], dst, c0, x0, y, b);
+                                ++y;
+                                if (++row == cv.rows_per_img) { row = 0; ++b; y = -k2; }
+                            }
+                        } else {
+                            int y = (b * cv.C + k1) * cv.Hin + row * cv.s + k0 * kyg;
+                            for (int g = lo_op; g < hi_op; ++g, dst += seg_pitch) {
+                                tma_load_2d(&tmA, &full_a[s], nullptr, 0, 0, dst, y);
+                                y += cv.s;
+                                if (++row == cv.rows_per_img) { row = 0; ++b; y = (b * cv.C + k1) * cv.Hin + k0 * kyg; }
+                            }
+                        }
+                    }
+                    if (cv.mode == 2) { if (++k0 == cv.kpk) { k0 = 0; if (++k1 == cv.T) { k1 = 0; ++k2; } } }
+                    else              { if (++k0 == cv.kpk) { k0 = 0; ++k1; } }
+                    __syncwarp();
+                }
             }
         }
     } else if (warp == 2) {
@@ -410,6 +448,9 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         Ring rb;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
             const Item t = decode(a, w);
+            // dgrad: (channel chunk, dkx, dky) of the k-block as counters, parity class of the tile
+            int bk0 = 0, bk1 = 0, bk2 = 0;
+            const int bpy = a.conv.mode == 2 ? fdiv(t.cls, a.conv.s) : 0, bpx = a.conv.mode == 2 ? t.cls - bpy * a.conv.s : 0;
             for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB)) {
                 const int kk = (int)(t.kk_begin + (int64_t)kb * BK);
                 const uint32_t s = rb.s;
@@ -426,13 +467,10 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     } else if (a.conv.mode == 2) {
                         // W [Cout, (ky, kx, c)]: box {32 c, 32 couts} of filter tap (ky, kx) = (py + s dky, px + s dkx)
                         const ConvA& cv = a.conv;
-                        const int tap = fdiv(kb, cv.kpk), cch = kb - tap * cv.kpk;
-                        const int dky = fdiv(tap, cv.T), dkx = tap - dky * cv.T;
-                        const int py = fdiv(t.cls, cv.s), px = t.cls - py * cv.s;
-                        const int col = ((py + cv.s * dky) * cv.KW + (px + cv.s * dkx)) * cv.Cin;
+                        const int col = ((bpy + cv.s * bk2) * cv.KW + (bpx + cv.s * bk1)) * cv.Cin;
                         for (int q = 0; q < bn / 32; ++q) {
-                            tma_load_2d(&tmB, &full_b[s], sb + q * 4096, col + 32 * q, cch * 32);
-                            tma_load_2d(&tmBlo, &full_b[s], sb + b_bytes + q * 4096, col + 32 * q, cch * 32);
+                            tma_load_2d(&tmB, &full_b[s], sb + q * 4096, col + 32 * q, bk0 * 32);
+                            tma_load_2d(&tmBlo, &full_b[s], sb + b_bytes + q * 4096, col + 32 * q, bk0 * 32);
                         }
                     } else if (!a.b_mn) {
                         tma_load_2d(&tmB, &full_b[s], sb, kk, (int)t.j0);               // box {32 k, bn rows}
@@ -444,6 +482,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                 }
+                if (a.conv.mode == 2) { if (++bk0 == a.conv.kpk) { bk0 = 0; if (++bk1 == a.conv.T) { bk1 = 0; ++bk2; } } }
                 __syncwarp();
             }
         }
@@ -498,11 +537,12 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int gt = (threadIdx.x - 128) & 127;     // thread index within the group
         const uint32_t smemA_u = smem_u32(smemA), smemB_u = smem_u32(smemB);
         uint32_t it = 0;
+        int turn = 0;                                  // it % kGroups
         Ring rb;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
             const Item t = decode(a, w);
-            for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB)) {
-                if ((int)(it & 1u) != grp) continue;
+            for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB), turn = (turn + 1 == kGroups) ? 0 : turn + 1) {
+                if (turn != grp) continue;
                 const uint32_t s = it % kSA;
                 if (q == 0) TCA_TRACE(it, 2);
                 mbar_wait(&full_a[s], (it / kSA) & 1u);
@@ -553,10 +593,15 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (q == 0) TCA_TRACE(it, 5);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kTaCol0 + ts * 64u;
+#ifdef PPD_ST32
+                tmem_st32(ta, hi);
+                tmem_st32(ta + 32u, lo);
+#else
                 tmem_st16(ta, hi);
                 tmem_st16(ta + 16u, hi + 16);
                 tmem_st16(ta + 32u, lo);
                 tmem_st16(ta + 48u, lo + 16);
+#endif
                 if (q == 0) TCA_TRACE(it, 6);
                 if (!a.b_presplit) {
                     const uint32_t sbs = rb.s;

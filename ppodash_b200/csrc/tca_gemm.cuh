@@ -13,7 +13,11 @@ constexpr int kSA = 8;             // shared-memory A stages (128 KB in flight p
 constexpr int kMaxSB = 8;          // shared-memory B stages ([hi | lo] each): as many as fit, at most 8
 constexpr size_t kSmemBudget = 225 * 1024;
 constexpr int kTA = 4;             // tensor-memory A stages (64 columns each: 32 hi + 32 lo)
-constexpr int kXformWarps = 8;
+#ifndef PPD_GROUPS
+#define PPD_GROUPS 2
+#endif
+constexpr int kGroups = PPD_GROUPS;   // transform groups of four warps taking k-blocks in turn
+constexpr int kXformWarps = 4 * kGroups;
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 32 * (4 + kXformWarps + kEpiWarps);   // + A producer, MMA issuer, B producer, spare
 constexpr uint32_t kTmemCols = 512;
