@@ -371,19 +371,32 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     // two chunk halves: warp 0 loads half 0, warp 3 half 1 of every segment; one half: the segments are split
                     int g_lo = 0, g_hi = nvalid;
                     if (nhalf != 2) { g_lo = pw ? (nvalid + 1) / 2 : 0; g_hi = pw ? nvalid : (nvalid + 1) / 2; }
-                    const bool leader = elect_one();
-                    if (leader) {
+                    // skip the segments of the other producer warp (single-half tiles only), then walk this warp's boxes
+                    for (int g = 0; g < g_lo; ++g)
+                        if (++sub == cv.spr) { sub = 0; if (++oy == cv.rows_per_img) { oy = 0; ++b; } }
+                    if (elect_one()) {
                         TCA_TRACE1(it, pw ? 10 : 0);
                         mbar_expect_tx(&full_a[s], (uint32_t)(g_hi - g_lo) * seg_bytes);
-                    }
-                    uint32_t dst = smem_u32(smemA + s * a_bytes) + hh * 8192u;
-                    for (int g = 0; g < nvalid; ++g, dst += seg_bytes) {          // every lane walks (the position is per-thread state)
-                        if (leader && g >= g_lo && g < g_hi) {
-                            if (cv.nchw) tma_load_5d(&tmA, &full_a[s], dst, 0, 0, sub * cv.segw, oy, b * cv.C + ch);
-                            else         tma_load_4d(&tmA, &full_a[s], dst, j0, sub * cv.segw, oy * cv.s + ky, b);
+                        uint32_t dst = smem_u32(smemA + s * a_bytes) + hh * 8192u + g_lo * seg_bytes;
+                        int sb2 = sub, oy2 = oy, b2 = b;
+                        if (cv.nchw) {
+                            int x = sb2 * cv.segw, cb = b2 * cv.C + ch;
+                            for (int g = g_lo; g < g_hi; ++g, dst += seg_bytes) {
+                                tma_load_5d(&tmA, &full_a[s], dst, 0, 0, x, oy2, cb);
+                                x += cv.segw;
+                                if (++sb2 == cv.spr) { sb2 = 0; x = 0; if (++oy2 == cv.rows_per_img) { oy2 = 0; cb += cv.C; } }
+                            }
+                        } else {
+                            int x = sb2 * cv.segw, y = oy2 * cv.s + ky;
+                            for (int g = g_lo; g < g_hi; ++g, dst += seg_bytes) {
+                                tma_load_4d(&tmA, &full_a[s], dst, j0, x, y, b2);
+                                x += cv.segw;
+                                if (++sb2 == cv.spr) { sb2 = 0; x = 0; y += cv.s; if (++oy2 == cv.rows_per_img) { oy2 = 0; y = ky; ++b2; } }
+                            }
                         }
-                        if (++sub == cv.spr) { sub = 0; if (++oy == cv.rows_per_img) { oy = 0; ++b; } }
                     }
+                    for (int g = g_lo; g < nvalid; ++g)            // every lane keeps the running position
+                        if (++sub == cv.spr) { sub = 0; if (++oy == cv.rows_per_img) { oy = 0; ++b; } }
                     seg += nvalid;
                     __syncwarp();
                 }
