@@ -300,7 +300,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #endif
     if (threadIdx.x == 0) {
         // convolution stages are filled by TWO producer warps (each arms the barrier for its own boxes)
-        for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], a.conv.mode ? 2 : 1); mbar_init(&empty_a[s], 4); }
+        for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], a.conv.mode ? kAProd : 1); mbar_init(&empty_a[s], 4); }
         for (int s = 0; s < kMaxSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < kTA; ++s) { mbar_init(&ta_full[s], 4); mbar_init(&ta_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
@@ -339,7 +339,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 __syncwarp();
             }
         }
-    } else if ((warp == 0 || warp == 3) && a.conv.mode) {
+    } else if ((warp == 0 || warp == 3 || warp >= kFirstExtra) && a.conv.mode) {
         // ================= TMA producers of a convolution: a stage is several boxes, shared between warp 0 and warp 3, each
         // walking its boxes from one elected thread (~55 clocks per box in a uniform-datapath loop; every lane issuing its
         // own box costs ~200: the compiler serialises them through R2UR broadcasts).  The k loop carries NO division: the
@@ -347,7 +347,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // this path (even the float-reciprocal one) costs the producer hundreds of clocks per k-block, and the producer's own
         // loop time, not the TMA engine or the transform warps, was what bounded every implicit convolution.
         const ConvA& cv = a.conv;
-        const int pw = warp == 0 ? 0 : 1;
+        const int pw = warp == 0 ? 0 : (warp == 3 ? 1 : warp - kFirstExtra + 2);       // producer index 0 .. kAProd-1
         uint32_t it = 0;
         if (cv.mode == 3) {
             const uint32_t seg_bytes = (uint32_t)cv.segw * 256u;
@@ -355,7 +355,10 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const Item t = decode(a, w);
                 const int ch0 = 2 * t.cls;
                 const int nhalf = min(2, cv.nchunks - ch0);
-                const int hh = nhalf == 2 ? pw : 0;
+                // two chunk halves: producers (pw & 1) take one half each, and with four producers (pw >> 1) splits the segments;
+                // one half: the segments are split between all producers
+                const int hh = nhalf == 2 ? (pw & 1) : 0;
+                const int part = nhalf == 2 ? (pw >> 1) : pw, nparts = nhalf == 2 ? kAProd / 2 : kAProd;
                 const int ch = ch0 + hh;
                 const int ky = cv.nchw ? 0 : fdiv(ch, cv.cpr);
                 const int j0 = (ch - ky * cv.cpr) * 64;
@@ -368,9 +371,8 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t s = it % kSA;
                     mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
                     const int nvalid = min(cv.nseg, cv.total_seg - seg);
-                    // two chunk halves: warp 0 loads half 0, warp 3 half 1 of every segment; one half: the segments are split
-                    int g_lo = 0, g_hi = nvalid;
-                    if (nhalf != 2) { g_lo = pw ? (nvalid + 1) / 2 : 0; g_hi = pw ? nvalid : (nvalid + 1) / 2; }
+                    const int per = (nvalid + nparts - 1) / nparts;
+                    const int g_lo = min(nvalid, part * per), g_hi = min(nvalid, g_lo + per);
                     // skip the segments of the other producer warp (single-half tiles only), then walk this warp's boxes
                     for (int g = 0; g < g_lo; ++g)
                         if (++sub == cv.spr) { sub = 0; if (++oy == cv.rows_per_img) { oy = 0; ++b; } }
@@ -408,7 +410,8 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
                 const Item t = decode(a, w);
                 // modes 1, 2, 4: the segments of a tile are consecutive rows (b, row); the two producer warps take half each
-                const int lo_op = pw ? (t.nvalid + 1) / 2 : 0, hi_op = pw ? t.nvalid : (t.nvalid + 1) / 2;
+                const int per = (t.nvalid + kAProd - 1) / kAProd;
+                const int lo_op = min(t.nvalid, pw * per), hi_op = min(t.nvalid, lo_op + per);
                 const int sg0 = t.seg0 + lo_op;
                 const int b0 = fdiv(sg0, cv.rows_per_img);
                 const int row0 = sg0 - b0 * cv.rows_per_img;

@@ -19,7 +19,12 @@ constexpr int kTA = 4;             // tensor-memory A stages (64 columns each: 3
 constexpr int kGroups = PPD_GROUPS;   // transform groups of four warps taking k-blocks in turn
 constexpr int kXformWarps = 4 * kGroups;
 constexpr int kEpiWarps = 4;
-constexpr int kThreads = 32 * (4 + kXformWarps + kEpiWarps);   // + A producer, MMA issuer, B producer, spare
+#ifndef PPD_APROD
+#define PPD_APROD 2
+#endif
+constexpr int kAProd = PPD_APROD;      // A-producer warps of a convolution: warps 0, 3 (and, with 4, two extra warps: measured no faster)
+constexpr int kFirstExtra = 4 + kXformWarps + kEpiWarps;
+constexpr int kThreads = 32 * (kFirstExtra + (kAProd == 4 ? 2 : 0));   // A producer, MMA issuer, B producer, A producer 2, transform, epilogue (, A producers 3-4)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol0 = 0, kAccStride = 128;   // two accumulators of up to 128 columns
 constexpr uint32_t kTaCol0 = 256;
