@@ -11,7 +11,8 @@ Everything heavy runs in hand-written CUDA kernels behind the C ABI of include/p
 from . import algo  # noqa: F401
 from .model import CNNBase, Categorical, FixedCategorical, NNBase, Policy  # noqa: F401
 from .obs_norm import RunningMeanStd, VecNormalizeObs  # noqa: F401
+from .rollout import RolloutLoop  # noqa: F401
 from .storage import FusedAdvantages, RolloutStorage  # noqa: F401
 
 __all__ = ["algo", "RolloutStorage", "FusedAdvantages", "Policy", "CNNBase", "NNBase", "Categorical",
-           "FixedCategorical", "RunningMeanStd", "VecNormalizeObs"]
+           "FixedCategorical", "RunningMeanStd", "VecNormalizeObs", "RolloutLoop"]
