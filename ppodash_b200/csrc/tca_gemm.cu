@@ -90,6 +90,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(0), "r"(c1)
         : "memory");
 }
+// 1-D bulk copy of `bytes` contiguous bytes (16-byte aligned on both sides)
+__device__ __forceinline__ void bulk_load_1d(const void* src, uint64_t* bar, uint32_t dst, uint32_t bytes) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
@@ -349,7 +355,55 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const ConvA& cv = a.conv;
         const int pw = warp == 0 ? 0 : (warp == 3 ? 1 : warp - kFirstExtra + 2);       // producer index 0 .. kAProd-1
         uint32_t it = 0;
-        if (cv.mode == 3) {
+        if (cv.mode == 3 && cv.raw) {
+            // weight gradient over NCHW observations, raw rows: a k-block is 32 consecutive pixels of the flattened (b, oy, ox)
+            // grid = at most 3 output rows; output row (b, oy) of channel c needs image rows s*oy .. s*oy + kh - 1, one
+            // CONTIGUOUS range -> one 1-D bulk copy per (output row, channel).  (The 5-D im2col view of the same data is 80 runs
+            // of 32 bytes per box, 480 per k-block: TMA-engine-bound.)  Stage = [channel half][output row 0..2][kh rows][W].
+            const uint32_t row_bytes = (uint32_t)(cv.KW * cv.Win) * 4u;          // kh == kw image rows
+            const int OW = cv.spr;                                                // pixels per output row
+            for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
+                const Item t = decode(a, w);
+                const int ch0 = 2 * t.cls;
+                const int nhalf = min(2, cv.nchunks - ch0);
+                if (pw >= nhalf) {                                                 // nothing to load: only arrive
+                    for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+                        const uint32_t s = it % kSA;
+                        mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
+                        if (elect_one()) mbar_expect_tx(&full_a[s], 0u);
+                        __syncwarp();
+                    }
+                    continue;
+                }
+                const int ch = ch0 + pw;
+                int P0 = t.kb0 * 32;
+                int R = fdiv(P0, OW), ox0 = P0 - R * OW;                          // first output row (flattened b*OH + oy) and pixel
+                int b = fdiv(R, cv.rows_per_img), oy = R - b * cv.rows_per_img;
+                for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+                    const uint32_t s = it % kSA;
+                    mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
+                    const int npx = min(32, cv.total_seg - P0);
+                    const int nrows = (ox0 + npx + OW - 1) / OW;                  // 1..3 (small constant divisor path: OW is run-time, but
+                                                                                  // this is one division per k-block on the vector pipe)
+                    if (elect_one()) {
+                        TCA_TRACE1(it, pw ? 10 : 0);
+                        mbar_expect_tx(&full_a[s], (uint32_t)nrows * row_bytes);
+                        uint32_t dst = smem_u32(smemA + s * a_bytes) + (uint32_t)pw * 3u * row_bytes;
+                        int b2 = b, oy2 = oy;
+                        for (int r = 0; r < nrows; ++r, dst += row_bytes) {
+                            const float* src = a.a_ptr + ((size_t)(b2 * cv.C + ch) * cv.Hin + (size_t)oy2 * cv.s) * cv.Win;
+                            bulk_load_1d(src, &full_a[s], dst, row_bytes);
+                            if (++oy2 == cv.rows_per_img) { oy2 = 0; ++b2; }
+                        }
+                    }
+                    // advance 32 pixels
+                    P0 += 32;
+                    ox0 += 32;
+                    while (ox0 >= OW) { ox0 -= OW; if (++oy == cv.rows_per_img) { oy = 0; ++b; } }
+                    __syncwarp();
+                }
+            }
+        } else if (cv.mode == 3) {
             const uint32_t seg_bytes = (uint32_t)cv.segw * 256u;
             for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
                 const Item t = decode(a, w);
@@ -565,7 +619,24 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (q == 0) TCA_TRACE(it, 3);
                 const uint32_t sa = smemA_u + s * a_bytes;
                 float x[32];
-                if (a.conv.mode == 3) {
+                if (a.conv.mode == 3 && a.conv.raw) {
+                    // raw rows [half][output row][ky][W]: patch element (ky, kx) of pixel slot p sits at row ky, float s*ox_p + kx
+                    const ConvA& cv = a.conv;
+                    const int OW = cv.spr;
+                    const int P0 = (t.kb0 + kb) * 32;
+                    const int npx = min(32, cv.total_seg - P0);
+                    const bool chunk_ok = 2 * t.cls + (r >> 6) < cv.nchunks;
+                    const uint32_t row_bytes = (uint32_t)(cv.KW * cv.Win) * 4u;
+                    const uint32_t base = sa + (uint32_t)(r >> 6) * 3u * row_bytes + (uint32_t)(((r >> 3) & 7) * cv.Win + (r & 7)) * 4u;
+                    int ox = P0 - fdiv(P0, OW) * OW;
+                    uint32_t rowoff = 0, off = (uint32_t)(ox * cv.s) * 4u;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        x[c] = (chunk_ok && c < npx) ? lds32(base + off) : 0.f;
+                        off += (uint32_t)cv.s * 4u;
+                        if (++ox == OW) { ox = 0; rowoff += row_bytes; off = rowoff; }
+                    }
+                } else if (a.conv.mode == 3) {
                     // [half][pixel slot][64 patch floats]; slots past the valid pixels and chunks past K are zero
                     const ConvA& cv = a.conv;
                     const int seg0 = (t.kb0 + kb) * cv.nseg;
@@ -951,6 +1022,10 @@ static void wgrad_plan(const ppd_conv_geom* g, int Cout, int nchw, ConvA& cv, in
     cv.mode = 3; cv.segw = segw; cv.nseg = 32 / segw; cv.spr = OW / segw; cv.rows_per_img = OH; cv.s = g->stride;
     const int K = g->kh * g->kw * g->C;
     cv.nchunks = K / 64; cv.nchw = nchw; cv.C = g->C; cv.cpr = nchw ? 1 : g->kw * g->C / 64;
+    // NCHW 8x8 filters: raw-row staging (1-D bulk copies, windows expanded on the register read) when 32 pixels span <= 3 output rows
+    cv.raw = (nchw && g->kh == 8 && g->kw == 8 && OW >= 16 && (size_t)6 * g->kw * g->W * 4 <= (size_t)BM * BK * 4 && g->stride % 4 == 0) ? 1 : 0;
+    cv.KW = g->kw; cv.Win = g->W; cv.Hin = g->H;
+    if (cv.raw) { cv.segw = 1; cv.nseg = 32; cv.spr = OW; }          // "segments" are single pixels: k-block = 32 consecutive pixels
     cv.total_seg = g->B * OH * cv.spr;
     cv.total_kb = (cv.total_seg + cv.nseg - 1) / cv.nseg;
     num_m = (cv.nchunks + 1) / 2;
@@ -963,9 +1038,10 @@ static void wgrad_plan(const ppd_conv_geom* g, int Cout, int nchw, ConvA& cv, in
 }
 
 size_t conv_wgrad_workspace(const ppd_conv_geom* g, int Cout) {
-    ConvA cv; int num_m, splits;
-    wgrad_plan(g, Cout, 0, cv, num_m, splits);
-    return (size_t)splits * g->kh * g->kw * g->C * Cout * sizeof(float);
+    ConvA cv; int num_m, s0, s1;
+    wgrad_plan(g, Cout, 0, cv, num_m, s0);
+    wgrad_plan(g, Cout, 1, cv, num_m, s1);
+    return (size_t)(s0 > s1 ? s0 : s1) * g->kh * g->kw * g->C * Cout * sizeof(float);
 }
 
 int conv_wgrad(const float* x, const ppd_conv_geom* g, int nchw, const float* dy, int Cout, float* dW, int accumulate,
@@ -979,7 +1055,7 @@ int conv_wgrad(const float* x, const ppd_conv_geom* g, int nchw, const float* dy
     Args a = {};
     int num_m, splits;
     wgrad_plan(g, Cout, nchw, a.conv, num_m, splits);
-    PPD_REQUIRE(a.conv.nseg * 2 <= 32, "output width not supported (too many TMA boxes per k-block)");
+    PPD_REQUIRE(a.conv.raw || a.conv.nseg * 2 <= 32, "output width not supported (too many TMA boxes per k-block)");
     PPD_REQUIRE(workspace && workspace_bytes >= (size_t)splits * K * Cout * sizeof(float), "workspace too small (ppd_conv_wgrad_workspace)");
     const ConvA& cv = a.conv;
     CUtensorMap tmA, tmB;
@@ -999,6 +1075,7 @@ int conv_wgrad(const float* x, const ppd_conv_geom* g, int nchw, const float* dy
     const int64_t M = (int64_t)g->B * OH * OW;
     if ((rc = make_map_2d(&tmB, dy, M, Cout, Cout, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
     a.C = nullptr; a.ldc = 0; a.I = K; a.J = Cout; a.KK = M;
+    a.a_ptr = x;
     a.bn = Cout; a.a_mn = 1; a.b_mn = 1; a.b_presplit = 0;
     a.num_m = num_m; a.num_n = 1; a.splits = splits; a.kk_per_split = 0;
     a.partial = reinterpret_cast<float*>(workspace);

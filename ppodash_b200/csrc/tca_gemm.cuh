@@ -65,6 +65,7 @@ struct ConvA {
     int cpr;                 // wgrad: chunks per filter row (NHWC) -- unused for NCHW
     int nchunks;             // wgrad: K / 64
     int nchw;                // wgrad: 5-D NCHW view (conv1) instead of the 4-D NHWC view
+    int raw;                 // wgrad NCHW: stage raw image rows with 1-D bulk copies, windows expanded on the register read
     int C;                   // wgrad NCHW: channels
     int total_kb, kbps;      // wgrad: k-blocks in total / per split
     int total_seg;           // wgrad: B * OH * spr
@@ -81,6 +82,7 @@ struct Args {
     float* partial;
     int total_items;
     int sb_stages;
+    const float* a_ptr;      // A tensor base (1-D bulk copies of the raw-row wgrad)
     ConvA conv;
 };
 
