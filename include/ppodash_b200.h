@@ -221,7 +221,7 @@ int ppd_conv_dgrad_nhwc(const float* dy, const ppd_conv_geom* geom, int Cout, co
                         const float* act_mask, float* dx, void* stream);
 /* Forward over NCHW observations x [B,C,H,W] (geom: same fields, C = channels), weights [Cout, (c,ky,kx)], NHWC output
  * [B*OH*OW, Cout]: the kernel stages raw image rows and expands the 8-wide windows on the way to registers
- * (replaces main.0 = Conv2d(C, 32, 8, stride 4), PKG/model.py:177).  kw == 8, stride % 4 == 0, W % 4 == 0. */
+ * (replaces main.0 = Conv2d(C, 32, 8, stride 4), PKG/model.py:177).  kw == 8, stride == 4, W % 4 == 0. */
 int ppd_conv_fwd_nchw(const float* x, const ppd_conv_geom* geom, int Cout, const float* w_hi, const float* w_lo,
                       const float* bias, int relu, float* out, void* stream);
 /*   wgrad: dW[Cout, K] (+)= sum over output pixels of dy[pixel, cout] * patch(x)[pixel, k], contraction split over the SMs and

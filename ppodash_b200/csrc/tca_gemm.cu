@@ -460,7 +460,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else {
             const int kyg = 32 / max(cv.KW, 1);
             const uint32_t seg_bytes = cv.mode == 4 ? (uint32_t)(kyg * cv.Win) * 4u : (uint32_t)cv.segw * 128u;
-            const uint32_t seg_pitch = cv.mode == 4 ? ((seg_bytes + 127u) & ~127u) : seg_bytes;     // TMA destinations: 128-byte aligned
+            const uint32_t seg_pitch = seg_bytes;
             for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
                 const Item t = decode(a, w);
                 // modes 1, 2, 4: the segments of a tile are consecutive rows (b, row); the two producer warps take half each
@@ -498,11 +498,14 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 if (++row == cv.rows_per_img) { row = 0; ++b; y = -k2; }
                             }
                         } else {
-                            int y = (b * cv.C + k1) * cv.Hin + row * cv.s + k0 * kyg;
-                            for (int g = lo_op; g < hi_op; ++g, dst += seg_pitch) {
-                                tma_load_2d(&tmA, &full_a[s], nullptr, 0, 0, dst, y);
-                                y += cv.s;
-                                if (++row == cv.rows_per_img) { row = 0; ++b; y = (b * cv.C + k1) * cv.Hin + k0 * kyg; }
+                            // mode 4: output row oy needs the kyg = s image rows s*oy + k0*kyg .. +kyg-1 of channel k1, so the rows of
+                            // CONSECUTIVE output rows are one contiguous range of the image: one 1-D bulk copy per run inside a sample
+                            int left = hi_op - lo_op;
+                            while (left > 0) {
+                                const int run = min(left, cv.rows_per_img - row);
+                                const float* src = a.a_ptr + ((size_t)(b * cv.C + k1) * cv.Hin + row * cv.s + k0 * kyg) * cv.Win;
+                                bulk_load_1d(src, &full_a[s], dst, (uint32_t)run * seg_bytes);
+                                dst += (uint32_t)run * seg_bytes; left -= run; row = 0; ++b;
                             }
                         }
                     }
@@ -649,7 +652,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const ConvA& cv = a.conv;
                     const int g = r / cv.segw, ox = r - g * cv.segw;
                     const int kyg = 32 / cv.KW;                                  // 4 rows of 8 floats
-                    const uint32_t base = sa + (uint32_t)g * (((uint32_t)(kyg * cv.Win) * 4u + 127u) & ~127u) + (uint32_t)(ox * cv.s) * 4u;
+                    const uint32_t base = sa + (uint32_t)(g * kyg * cv.Win + ox * cv.s) * 4u;
                     const bool ok = g < min(cv.nseg, cv.nseg_class - t.seg0);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
@@ -951,7 +954,7 @@ int conv_forward(const float* x, const ppd_conv_geom* g, int Cout, const float* 
 int conv_forward_nchw(const float* x, const ppd_conv_geom* g, int Cout, const float* w_hi, const float* w_lo, const float* bias,
                       int relu, float* out, cudaStream_t s) {
     const int OH = (g->H - g->kh) / g->stride + 1, OW = (g->W - g->kw) / g->stride + 1;
-    PPD_REQUIRE(g->kw == 8 && g->kh % 4 == 0 && g->stride % 4 == 0 && g->W % 4 == 0, "NCHW forward supports 8-wide filters with stride % 4 == 0");
+    PPD_REQUIRE(g->kw == 8 && g->kh % 4 == 0 && g->stride == 4 && g->W % 4 == 0, "NCHW forward supports 8-wide filters with stride 4");
     PPD_REQUIRE((Cout == 32 || Cout == 64) && OW >= 1 && OW <= BM && OH >= 1, "unsupported convolution shape");
     PPD_REQUIRE(!(((uintptr_t)x | (uintptr_t)w_hi | (uintptr_t)w_lo | (uintptr_t)out) & 15), "pointers must be 16-byte aligned");
     const int kyg = 32 / g->kw;
@@ -959,7 +962,7 @@ int conv_forward_nchw(const float* x, const ppd_conv_geom* g, int Cout, const fl
     Args a = {};
     ConvA& cv = a.conv;
     cv.mode = 4; cv.segw = OW; cv.nseg = BM / OW;
-    while ((size_t)cv.nseg * (((size_t)kyg * g->W * 4 + 127) & ~(size_t)127) > (size_t)BM * BK * 4) --cv.nseg;       // the raw rows of a stage must fit its 16 KB
+    while ((size_t)cv.nseg * kyg * g->W * 4 > (size_t)BM * BK * 4) --cv.nseg;       // the raw rows of a stage must fit its 16 KB       // the raw rows of a stage must fit its 16 KB
     cv.nseg_class = g->B * OH;
     cv.ntile_class = (cv.nseg_class + cv.nseg - 1) / cv.nseg;
     cv.rows_per_img = OH; cv.s = g->stride; cv.kpk = g->kh / kyg; cv.KW = g->kw; cv.Cin = g->C; cv.C = g->C; cv.Hin = g->H; cv.Win = g->W;
@@ -972,6 +975,7 @@ int conv_forward_nchw(const float* x, const ppd_conv_geom* g, int Cout, const fl
     a.C = out; a.ldc = Cout; a.I = (int64_t)g->B * OH * OW; a.J = Cout; a.KK = K;
     a.bias = bias; a.mask = nullptr; a.relu = relu;
     a.bn = Cout; a.b_mn = 0;
+    a.a_ptr = x;
     a.total_items = cv.ntile_class;
     PPD_REQUIRE(cv.nseg <= 32, "output width not supported (too many TMA boxes per tile)");
     return launch_conv(tmA, tmB, tmBlo, a, s);
