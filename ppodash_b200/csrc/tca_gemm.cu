@@ -84,12 +84,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void*, int, int, uint32_t dst, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(smem_u32(bar)), "r"(0), "r"(c1)
-        : "memory");
-}
 // 1-D bulk copy of `bytes` contiguous bytes (16-byte aligned on both sides)
 __device__ __forceinline__ void bulk_load_1d(const void* src, uint64_t* bar, uint32_t dst, uint32_t bytes) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -130,6 +124,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
         "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
+#ifdef PPD_ST32
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -141,6 +136,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
         "r"(v[30]), "r"(v[31])
         : "memory");
 }
+#endif
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
     asm volatile(
@@ -626,6 +622,10 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (q == 0) TCA_TRACE(it, 3);
                 const uint32_t sa = smemA_u + s * a_bytes;
                 float x[32];
+#ifdef PPD_ABL_NOLDS
+                for (int c = 0; c < 32; ++c) x[c] = __uint_as_float(sa + c);
+                if (sa == 0xffffffffu)
+#endif
                 if (a.conv.mode == 3 && a.conv.raw) {
                     // raw rows [half][output row][ky][W]: patch element (ky, kx) of pixel slot p sits at row ky, float s*ox_p + kx
                     const ConvA& cv = a.conv;
@@ -691,7 +691,9 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (q == 0) TCA_TRACE(it, 5);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kTaCol0 + ts * 64u;
-#ifdef PPD_ST32
+#if defined(PPD_ABL_NOSTTM)
+                if (hi[0] == 0x12345678u) tmem_st16(ta, hi);
+#elif defined(PPD_ST32)
                 tmem_st32(ta, hi);
                 tmem_st32(ta + 32u, lo);
 #else
