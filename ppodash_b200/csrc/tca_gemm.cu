@@ -289,7 +289,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int bn = a.bn;
     const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)bn * BK * 4;
     uint8_t* smemA = smem;                               // kSA stages of one 128 x 32 fp32 tile
-    uint8_t* smemB = smem + kSA * a_bytes;               // kSB stages of [B hi | B lo]
+    uint8_t* smemB = smem + (a.a_region_bytes ? a.a_region_bytes : kSA * a_bytes);      // kSB stages of [B hi | B lo]
     const uint32_t kSB = (uint32_t)a.sb_stages;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -302,7 +302,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #endif
     if (threadIdx.x == 0) {
         // convolution stages are filled by TWO producer warps (each arms the barrier for its own boxes)
-        for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], a.conv.mode ? kAProd : 1); mbar_init(&empty_a[s], 4); }
+        for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], a.conv.mode ? kAProd : 1); mbar_init(&empty_a[s], a.conv.mode == 6 ? kXformWarps : 4); }
         for (int s = 0; s < kMaxSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < kTA; ++s) { mbar_init(&ta_full[s], 4); mbar_init(&ta_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
@@ -351,7 +351,46 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const ConvA& cv = a.conv;
         const int pw = warp == 0 ? 0 : (warp == 3 ? 1 : warp - kFirstExtra + 2);       // producer index 0 .. kAProd-1
         uint32_t it = 0;
-        if (cv.mode == 3 && cv.raw) {
+        if (cv.mode == 6) {
+            // tile-resident raw input: one stage per TILE (two stages); image rows s*oy_a .. s*oy_b + KH - 1 of every run of output
+            // rows inside one sample, per channel plane, as plain NHWC boxes {32 channels, Win pixels}; rows alternate between the
+            // two producer warps.  Nothing is loaded per k-block.
+            const uint32_t row_bytes = (uint32_t)cv.Win * 128u;
+            uint32_t tile_it = 0;
+            for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
+                const Item t = decode(a, w);
+                const uint32_t st = tile_it & 1u;
+                mbar_wait(&empty_a[st], ((tile_it >> 1) & 1u) ^ 1u);
+                const int b0 = fdiv(t.seg0, cv.rows_per_img);
+                const int oy0 = t.seg0 - b0 * cv.rows_per_img;
+                if (elect_one()) {
+                    // pass 1: rows of this producer
+                    int mine = 0;
+                    {
+                        int left = t.nvalid, oy = oy0, slot = 0;
+                        while (left > 0) {
+                            const int run = min(left, cv.rows_per_img - oy);
+                            const int nr = cv.s * (run - 1) + cv.KH;
+                            mine += (nr + ((slot & 1) == pw ? 1 : 0)) >> 1;           // rows with (slot + y) & 1 == pw
+                            slot += nr; left -= run; oy = 0;
+                        }
+                    }
+                    mbar_expect_tx(&full_a[st], (uint32_t)(mine * cv.planes) * row_bytes);
+                    const uint32_t base = smem_u32(smemA) + st * cv.tile_stage_bytes;
+                    int left = t.nvalid, oy = oy0, slot = 0, b = b0;
+                    while (left > 0) {
+                        const int run = min(left, cv.rows_per_img - oy);
+                        const int nr = cv.s * (run - 1) + cv.KH;
+                        for (int y = ((slot & 1) == pw) ? 0 : 1; y < nr; y += 2)
+                            for (int p2 = 0; p2 < cv.planes; ++p2)
+                                tma_load_4d(&tmA, &full_a[st], base + (uint32_t)((p2 * cv.nrows_max + slot + y)) * row_bytes, p2 * 32, 0,
+                                            cv.s * oy + y, b);
+                        slot += nr; left -= run; oy = 0; ++b;
+                    }
+                }
+                __syncwarp();
+            }
+        } else if (cv.mode == 3 && cv.raw) {
             // weight gradient over NCHW observations, raw rows: a k-block is 32 consecutive pixels of the flattened (b, oy, ox)
             // grid = at most 3 output rows; output row (b, oy) of channel c needs image rows s*oy .. s*oy + kh - 1, one
             // CONTIGUOUS range -> one 1-D bulk copy per (output row, channel).  (The 5-D im2col view of the same data is 80 runs
@@ -609,16 +648,35 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int r = q * 32 + lane;
         const int gt = (threadIdx.x - 128) & 127;     // thread index within the group
         const uint32_t smemA_u = smem_u32(smemA), smemB_u = smem_u32(smemB);
-        uint32_t it = 0;
+        uint32_t it = 0, tile_it = 0;
         int turn = 0;                                  // it % kGroups
         Ring rb;
-        for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
+        for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
             const Item t = decode(a, w);
+            // mode 6 (tile-resident raw input): this thread's pixel is line `line0` of the stage for tap (0, 0); wait for the stage once
+            uint32_t line0 = 0, stage6 = 0;
+            int k_p = 0, k_kx = 0, k_ky = 0;           // channel plane, filter column, filter row of the current k-block
+            if (a.conv.mode == 6) {
+                const ConvA& cv = a.conv;
+                const int g = r / cv.segw, ox = r - g * cv.segw;
+                if (g < t.nvalid) {
+                    const int b0 = fdiv(t.seg0, cv.rows_per_img);
+                    int oy = t.seg0 - b0 * cv.rows_per_img, run_slot = 0, run_a = oy;
+                    for (int gg = 0; gg < g; ++gg)
+                        if (++oy == cv.rows_per_img) { run_slot += cv.s * (cv.rows_per_img - 1 - run_a) + cv.KH; run_a = 0; oy = 0; }
+                    line0 = (uint32_t)((run_slot + cv.s * (oy - run_a)) * cv.Win + ox * cv.s);
+                }
+                stage6 = smemA_u + (tile_it & 1u) * cv.tile_stage_bytes;
+                mbar_wait(&full_a[tile_it & 1u], (tile_it >> 1) & 1u);
+            }
             for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB), turn = (turn + 1 == kGroups) ? 0 : turn + 1) {
+                if (a.conv.mode == 6 && kb > 0) {       // advance (plane, kx, ky) for EVERY k-block, also the other group's
+                    if (++k_p == a.conv.planes) { k_p = 0; if (++k_kx == a.conv.KW) { k_kx = 0; ++k_ky; } }
+                }
                 if (turn != grp) continue;
                 const uint32_t s = it % kSA;
                 if (q == 0) TCA_TRACE(it, 2);
-                mbar_wait(&full_a[s], (it / kSA) & 1u);
+                if (a.conv.mode != 6) mbar_wait(&full_a[s], (it / kSA) & 1u);
                 if (q == 0) TCA_TRACE(it, 3);
                 const uint32_t sa = smemA_u + s * a_bytes;
                 float x[32];
@@ -626,7 +684,16 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int c = 0; c < 32; ++c) x[c] = __uint_as_float(sa + c);
                 if (sa == 0xffffffffu)
 #endif
-                if (a.conv.mode == 3 && a.conv.raw) {
+                if (a.conv.mode == 6) {
+                    const ConvA& cv = a.conv;
+                    const uint32_t line = (uint32_t)(k_p * cv.nrows_max * cv.Win) + line0 + (uint32_t)(k_ky * cv.Win + k_kx);
+                    const uint32_t la = stage6 + line * 128u;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v = lds128(la + (((uint32_t)c ^ (line & 7u)) << 4));
+                        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+                    }
+                } else if (a.conv.mode == 3 && a.conv.raw) {
                     // raw rows [half][output row][ky][W]: patch element (ky, kx) of pixel slot p sits at row ky, float s*ox_p + kx
                     const ConvA& cv = a.conv;
                     const int OW = cv.spr;
@@ -684,7 +751,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int c = 0; c < 32; ++c) split_tf32(x[c], hi[c], lo[c]);
 #endif
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_a[s]);            // the tile is in registers: slot back to the producer
+                if (lane == 0 && a.conv.mode != 6) mbar_arrive(&empty_a[s]);   // the tile is in registers: slot back to the producer
                 if (q == 0) TCA_TRACE(it, 4);
                 const uint32_t ts = it % kTA;
                 mbar_wait(&ta_empty[ts], ((it / kTA) & 1u) ^ 1u);
@@ -726,6 +793,10 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (lane == 0) mbar_arrive(&ta_full[ts]);
                 if (q == 0) TCA_TRACE(it, 7);
             }
+            if (a.conv.mode == 6) {                    // every read of this warp from the tile's stage is done
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_a[tile_it & 1u]);
+            }
         }
     } else {
         // ================= epilogue: warp w may touch TMEM lanes [32*(w%4), +32); result = main + correction accumulator
@@ -739,7 +810,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int64_t i = t.i0 + q * 32 + lane;
             bool row_ok = i < a.I;
             int64_t crow_off = i * a.ldc + t.j0, mrow_off = i * a.ldm + t.j0;
-            if (a.conv.mode == 1 || a.conv.mode == 2 || a.conv.mode == 4) {
+            if (a.conv.mode == 1 || a.conv.mode == 2 || a.conv.mode == 4 || a.conv.mode == 6) {
                 const ConvA& cv = a.conv;
                 const int r = q * 32 + lane;
                 row_ok = r < t.nvalid * cv.segw;
@@ -918,6 +989,7 @@ int make_map_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, i
     return 0;
 }
 
+int g_conv_resident = 1;      // forward NHWC convolutions stage their input once per tile (ConvA mode 6); 0 = one im2col box per row and k-block (mode 1)
 // N-D fp32 tensor map (dims / strides innermost first; strides in bytes for dims 1..nd-1), OOB elements read as zero.
 static int make_map_nd(CUtensorMap* m, const float* base, int nd, const cuuint64_t* dims, const cuuint64_t* strides,
                        const cuuint32_t* box, CUtensorMapSwizzle swz) {
@@ -933,10 +1005,12 @@ static int make_map_nd(CUtensorMap* m, const float* base, int nd, const cuuint64
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo, Args& a, cudaStream_t s) {
     a.a_mn = 0; a.b_presplit = 1; a.transpose_out = 0; a.accumulate = 0; a.partial = nullptr;
     a.num_m = 1; a.num_n = 1; a.splits = 1; a.kk_per_split = a.KK; a.ldm = a.ldc;
-    int sb_stages = (int)((kSmemBudget - 1024 - (size_t)kSA * BM * BK * 4) / ((size_t)2 * a.bn * BK * 4));
+    const size_t a_region = a.a_region_bytes ? a.a_region_bytes : (size_t)kSA * BM * BK * 4;
+    int sb_stages = (int)((kSmemBudget - 1024 - a_region) / ((size_t)2 * a.bn * BK * 4));
     if (sb_stages > kMaxSB) sb_stages = kMaxSB;
+    PPD_REQUIRE(sb_stages >= 2, "shared memory: no room for the B ring");
     a.sb_stages = sb_stages;
-    const size_t smem = (size_t)kSA * BM * BK * 4 + (size_t)sb_stages * 2 * a.bn * BK * 4 + 1024;
+    const size_t smem = a_region + (size_t)sb_stages * 2 * a.bn * BK * 4 + 1024;
     cudaError_t e = cudaFuncSetAttribute(tca_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
     if (e != cudaSuccess) { set_error("tca conv: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
     const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
@@ -970,6 +1044,21 @@ int conv_forward(const float* x, const ppd_conv_geom* g, int Cout, const float* 
     cv.nkb = g->kh * cv.kpk;
     a.total_items = cv.ntile_class;
     PPD_REQUIRE(cv.nseg <= 32, "output width not supported (too many TMA boxes per tile)");
+    // Tile-resident raw input (mode 6) when two stages of it and a B ring fit: every input element goes through TMA once per tile
+    if (g_conv_resident && g->C % 32 == 0) {
+        const int planes = g->C / 32;
+        const int max_runs = 1 + (cv.nseg - 1 + OH - 1) / OH;
+        const int nrows_max = g->stride * cv.nseg + (g->kh > g->stride ? (g->kh - g->stride) * max_runs : 0) + 1;
+        const size_t stage = (((size_t)planes * nrows_max * g->W * 128) + 1023) & ~(size_t)1023;
+        if (2 * stage + 2 * (size_t)2 * Cout * BK * 4 + 1024 <= kSmemBudget) {
+            cuuint64_t d4[4] = {(cuuint64_t)g->C, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->B};
+            cuuint64_t s4[3] = {(cuuint64_t)g->C * 4, (cuuint64_t)g->W * g->C * 4, (cuuint64_t)g->H * g->W * g->C * 4};
+            cuuint32_t b4[4] = {32, (cuuint32_t)g->W, 1, 1};
+            if ((rc = make_map_nd(&tmA, x, 4, d4, s4, b4, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+            cv.mode = 6; cv.KH = g->kh; cv.planes = planes; cv.nrows_max = nrows_max; cv.tile_stage_bytes = (uint32_t)stage;
+            a.a_region_bytes = (uint32_t)(2 * stage);
+        }
+    }
     return launch_conv(tmA, tmB, tmBlo, a, s);
 }
 

@@ -49,6 +49,12 @@ constexpr uint32_t kTaCol0 = 256;
 //                     y = s*oy + ky as boxes {W floats, 32/kw rows}; the window expansion happens on the way to registers:
 //                     the thread of pixel ox reads floats [s*ox, s*ox + kw) of each row -- consecutive lanes read consecutive
 //                     16-byte words (s = 4), conflict-free, and every input element crosses L2 -> SM once, not kw/s times.
+//   mode 6, forward NHWC with a TILE-RESIDENT raw input: the input rows a tile of output rows needs are staged ONCE per tile
+//                     (plain NHWC boxes {32 channels, Win pixels} per image row and channel plane, 128B-swizzled lines) and every
+//                     k-block (filter tap x channel chunk) reads its shifted window of the same stage: pixel ox of tap (ky, kx)
+//                     is line (row0 + ky) * Win + s*ox + kx.  TMA moves each input element once per tile instead of once per tap
+//                     (4x fewer bytes for the 4x4 stride-2 layer): the implicit convolutions are bound by TMA ingest of the
+//                     expanded tile stream (profiles/r1c_tca_ablation.md).
 struct ConvA {
     int mode;                // 0 = plain GEMM
     int segw, nseg;          // pixels per segment, segments per tile (nseg * segw <= 128)
@@ -66,6 +72,8 @@ struct ConvA {
     int nchunks;             // wgrad: K / 64
     int nchw;                // wgrad: 5-D NCHW view (conv1) instead of the 4-D NHWC view
     int raw;                 // wgrad NCHW: stage raw image rows with 1-D bulk copies, windows expanded on the register read
+    int KH, planes, nrows_max;   // mode 6: filter height, C / 32 channel planes, input rows a stage can hold per plane
+    uint32_t tile_stage_bytes;   // mode 6: bytes of one tile-resident A stage (two of them)
     int C;                   // wgrad NCHW: channels
     int total_kb, kbps;      // wgrad: k-blocks in total / per split
     int total_seg;           // wgrad: B * OH * spr
@@ -83,8 +91,11 @@ struct Args {
     int total_items;
     int sb_stages;
     const float* a_ptr;      // A tensor base (1-D bulk copies of the raw-row wgrad)
+    uint32_t a_region_bytes; // bytes of the A region of shared memory (0 = kSA stages of 16 KB)
     ConvA conv;
 };
+
+extern int g_conv_resident;
 
 struct Plan { int bn, num_m, num_n, splits; int64_t kk_per_split; size_t ws; };
 

@@ -29,6 +29,8 @@ def split(w):
 def main():
     L = _lib.lib()
     st = _lib.stream_ptr()
+    if os.environ.get("PPD_RESIDENT") is not None:
+        L.ppd_tc_gemm_set_option(6 + int(os.environ["PPD_RESIDENT"]))
     only = os.environ.get("PPD_SHAPES")
     obs = torch.randn(B, 3, 84, 84, device=DEV)
     a1 = torch.randn(B, 20, 20, 32, device=DEV)
