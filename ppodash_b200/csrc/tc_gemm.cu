@@ -569,6 +569,7 @@ extern "C" void ppd_tc_gemm_set_option(int v) {
     else if (v == 2 || v == 3) g_a_tmem = v - 2;
     else if (v == 4 || v == 5) g_persistent = v - 4;
     else if (v == 6 || v == 7) ppd::tca::g_conv_resident = v - 6;
+    else if (v == 8 || v == 9) ppd::tca::g_b_resident = v - 8;
     else if (v == 32 || v == 64 || v == 128 || v == 256) g_force_bn = v;
     else if (v == -1) g_force_bn = 0;
 }

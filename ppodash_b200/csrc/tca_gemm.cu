@@ -552,18 +552,23 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else if (warp == 2) {
         // ================= TMA producer, B tiles
-        uint32_t it = 0;
+        // Resident B (convolutions whose weight tiles of ALL k-blocks fit): stage kb holds k-block kb for as long as the tile class
+        // (dgrad: the parity class that selects the filter taps) does not change -- the weights were otherwise re-streamed through
+        // TMA for every tile, as many bytes as the patch stream itself (conv1 forward: 328 MB of weights for 173 MB of pixels).
+        uint32_t it = 0, epoch = 0;
+        int loaded_cls = -1;
         Ring rb;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
             const Item t = decode(a, w);
+            const bool reload = !a.b_resident || t.cls != loaded_cls;
             // dgrad: (channel chunk, dkx, dky) of the k-block as counters, parity class of the tile
             int bk0 = 0, bk1 = 0, bk2 = 0;
             const int bpy = a.conv.mode == 2 ? fdiv(t.cls, a.conv.s) : 0, bpx = a.conv.mode == 2 ? t.cls - bpy * a.conv.s : 0;
             for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB)) {
                 const int kk = (int)(t.kk_begin + (int64_t)kb * BK);
-                const uint32_t s = rb.s;
-                mbar_wait(&empty_b[s], rb.ph ^ 1u);
-                if (elect_one()) {
+                const uint32_t s = a.b_resident ? (uint32_t)kb : rb.s;
+                if (reload) mbar_wait(&empty_b[s], a.b_resident ? ((epoch & 1u) ^ 1u) : (rb.ph ^ 1u));
+                if (reload && elect_one()) {
                     TCA_TRACE1(it, 1);
                     mbar_expect_tx(&full_b[s], a.b_presplit ? 2 * b_bytes : b_bytes);
                     uint8_t* sb = smemB + s * 2 * b_bytes;
@@ -593,6 +598,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (a.conv.mode == 2) { if (++bk0 == a.conv.kpk) { bk0 = 0; if (++bk1 == a.conv.T) { bk1 = 0; ++bk2; } } }
                 __syncwarp();
             }
+            if (a.b_resident && reload) { loaded_cls = t.cls; ++epoch; }
         }
     } else if (warp == 1) {
         // ================= MMA issuer.  Two accumulators per tile: main = A_hi B_hi in columns [0, bn) and the
@@ -603,18 +609,23 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint64_t bdesc0 = a.b_mn ? make_desc(smem_u32(smemB), 4096, 512, kLayoutSw128Base32)
                                        : make_desc(smem_u32(smemB), 0, 1024, kLayoutSw128);
         const uint32_t kstep = a.b_mn ? (1024u >> 4) : (32u >> 4);          // descriptor start-address step per 8 k
-        uint32_t it = 0, tile_it = 0;
+        uint32_t it = 0, tile_it = 0, epoch = 0;
+        int loaded_cls = -1;
         Ring rb;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
             const Item t = decode(a, w);
+            const bool reload = !a.b_resident || t.cls != loaded_cls;
+            // resident B: its stages are released only when this CTA's NEXT tile needs other weights
+            const int wn = w + gridDim.x;
+            const bool release = !a.b_resident || (wn < a.total_items && decode(a, wn).cls != t.cls);
             const uint32_t acc = tile_it & 1u;
             mbar_wait(&acc_empty[acc], ((tile_it >> 1) & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d = tmem_base + kAccCol0 + acc * kAccStride;
             for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB)) {
-                const uint32_t ts = it % kTA, s = rb.s;
+                const uint32_t ts = it % kTA, s = a.b_resident ? (uint32_t)kb : rb.s;
                 mbar_wait(&ta_full[ts], (it / kTA) & 1u);
-                if (a.b_presplit) mbar_wait(&full_b[s], rb.ph);
+                if (a.b_presplit && reload) mbar_wait(&full_b[s], a.b_resident ? (epoch & 1u) : rb.ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     TCA_TRACE1(it, 8);
@@ -630,13 +641,14 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #endif
                     }
                     umma_commit(&ta_empty[ts]);
-                    umma_commit(&empty_b[s]);
+                    if (release) umma_commit(&empty_b[s]);
                     TCA_TRACE1(it, 9);
                 }
                 __syncwarp();
             }
             if (elect_one()) umma_commit(&acc_full[acc]);
             __syncwarp();
+            if (a.b_resident && reload) { loaded_cls = t.cls; ++epoch; }
         }
     } else if (warp == 3) {
         // (second A producer in convolution modes, handled above; idle for plain GEMMs)
@@ -989,6 +1001,7 @@ int make_map_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, i
     return 0;
 }
 
+int g_b_resident = 1;         // convolutions keep the weight tiles of all k-blocks in shared memory when they fit
 int g_conv_resident = 1;      // forward NHWC convolutions stage their input once per tile (ConvA mode 6); 0 = one im2col box per row and k-block (mode 1)
 // N-D fp32 tensor map (dims / strides innermost first; strides in bytes for dims 1..nd-1), OOB elements read as zero.
 static int make_map_nd(CUtensorMap* m, const float* base, int nd, const cuuint64_t* dims, const cuuint64_t* strides,
@@ -1007,7 +1020,9 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     a.num_m = 1; a.num_n = 1; a.splits = 1; a.kk_per_split = a.KK; a.ldm = a.ldc;
     const size_t a_region = a.a_region_bytes ? a.a_region_bytes : (size_t)kSA * BM * BK * 4;
     int sb_stages = (int)((kSmemBudget - 1024 - a_region) / ((size_t)2 * a.bn * BK * 4));
-    if (sb_stages > kMaxSB) sb_stages = kMaxSB;
+    a.b_resident = (g_b_resident && a.conv.nkb >= 2 && a.conv.nkb <= kMaxSB && a.conv.nkb <= sb_stages) ? 1 : 0;      // all weight tiles fit: keep them
+    if (a.b_resident) sb_stages = a.conv.nkb;
+    if (sb_stages > 8 && !a.b_resident) sb_stages = 8;
     PPD_REQUIRE(sb_stages >= 2, "shared memory: no room for the B ring");
     a.sb_stages = sb_stages;
     const size_t smem = a_region + (size_t)sb_stages * 2 * a.bn * BK * 4 + 1024;
@@ -1196,7 +1211,7 @@ int conv_wgrad(const float* x, const ppd_conv_geom* g, int nchw, const float* dy
     a.partial = reinterpret_cast<float*>(workspace);
     a.total_items = num_m * splits;
     int sb_stages = (int)((kSmemBudget - 1024 - (size_t)kSA * BM * BK * 4) / ((size_t)2 * a.bn * BK * 4));
-    if (sb_stages > kMaxSB) sb_stages = kMaxSB;
+    if (sb_stages > 8) sb_stages = 8;
     a.sb_stages = sb_stages;
     const size_t smem = (size_t)kSA * BM * BK * 4 + (size_t)sb_stages * 2 * a.bn * BK * 4 + 1024;
     cudaError_t e = cudaFuncSetAttribute(tca_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
@@ -1260,7 +1275,7 @@ int launch(const ppd_gemm_args* g, int transpose_out, const float* b_lo, void* w
     a.partial = p.splits > 1 ? reinterpret_cast<float*>(workspace) : nullptr;
     a.total_items = p.num_m * p.num_n * p.splits;
     int sb_stages = (int)((kSmemBudget - 1024 - (size_t)kSA * BM * BK * 4) / ((size_t)2 * p.bn * BK * 4));
-    if (sb_stages > kMaxSB) sb_stages = kMaxSB;
+    if (sb_stages > 8) sb_stages = 8;
     a.sb_stages = sb_stages;
     const size_t smem = (size_t)kSA * BM * BK * 4 + (size_t)sb_stages * 2 * p.bn * BK * 4 + 1024;
     static bool attr_set = false;

@@ -10,7 +10,7 @@ namespace tca {
 constexpr int BM = 128;            // UMMA M
 constexpr int BK = 32;             // floats per k-block (one 128-byte row)
 constexpr int kSA = 8;             // shared-memory A stages (128 KB in flight per SM covers the HBM latency)
-constexpr int kMaxSB = 8;          // shared-memory B stages ([hi | lo] each): as many as fit, at most 8
+constexpr int kMaxSB = 18;         // shared-memory B stages ([hi | lo] each): a ring of as many as fit (at most 8), or all k-blocks resident
 constexpr size_t kSmemBudget = 225 * 1024;
 constexpr int kTA = 4;             // tensor-memory A stages (64 columns each: 32 hi + 32 lo)
 #ifndef PPD_GROUPS
@@ -92,10 +92,11 @@ struct Args {
     int sb_stages;
     const float* a_ptr;      // A tensor base (1-D bulk copies of the raw-row wgrad)
     uint32_t a_region_bytes; // bytes of the A region of shared memory (0 = kSA stages of 16 KB)
+    int b_resident;          // convolutions: the B (weight) tiles of ALL k-blocks stay in shared memory; reloaded only when the tile class changes
     ConvA conv;
 };
 
-extern int g_conv_resident;
+extern int g_conv_resident, g_b_resident;
 
 struct Plan { int bn, num_m, num_n, splits; int64_t kk_per_split; size_t ws; };
 

@@ -31,6 +31,8 @@ def main():
     st = _lib.stream_ptr()
     if os.environ.get("PPD_RESIDENT") is not None:
         L.ppd_tc_gemm_set_option(6 + int(os.environ["PPD_RESIDENT"]))
+    if os.environ.get("PPD_BRES") is not None:
+        L.ppd_tc_gemm_set_option(8 + int(os.environ["PPD_BRES"]))
     only = os.environ.get("PPD_SHAPES")
     obs = torch.randn(B, 3, 84, 84, device=DEV)
     a1 = torch.randn(B, 20, 20, 32, device=DEV)
