@@ -302,7 +302,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #endif
     if (threadIdx.x == 0) {
         // convolution stages are filled by TWO producer warps (each arms the barrier for its own boxes)
-        for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], a.conv.mode ? kAProd : 1); mbar_init(&empty_a[s], a.conv.mode == 6 ? kXformWarps : 4); }
+        for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], a.conv.mode ? kAProd : 1); mbar_init(&empty_a[s], (a.conv.mode == 6 || a.conv.mode == 7) ? kXformWarps : 4); }
         for (int s = 0; s < kMaxSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < kTA; ++s) { mbar_init(&ta_full[s], 4); mbar_init(&ta_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
@@ -351,11 +351,14 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const ConvA& cv = a.conv;
         const int pw = warp == 0 ? 0 : (warp == 3 ? 1 : warp - kFirstExtra + 2);       // producer index 0 .. kAProd-1
         uint32_t it = 0;
-        if (cv.mode == 6) {
-            // tile-resident raw input: one stage per TILE (two stages); image rows s*oy_a .. s*oy_b + KH - 1 of every run of output
-            // rows inside one sample, per channel plane, as plain NHWC boxes {32 channels, Win pixels}; rows alternate between the
-            // two producer warps.  Nothing is loaded per k-block.
-            const uint32_t row_bytes = (uint32_t)cv.Win * 128u;
+        if (cv.mode == 6 || cv.mode == 7) {
+            // tile-resident raw input: one stage per TILE (two stages).  Forward (6): image rows s*oy_a .. s*oy_b + KH - 1 of every
+            // run of output rows inside one sample; dgrad (7): dY rows i_a - T + 1 .. i_b of every run of dx rows, T - 1 pixels of
+            // left halo (out-of-bounds rows / pixels read as zero).  Per channel plane, plain NHWC boxes {32 channels, lw pixels};
+            // rows alternate between the two producer warps.  Nothing is loaded per k-block.
+            const bool isd = cv.mode == 7;
+            const int lw = isd ? cv.segw + cv.T - 1 : cv.Win;                 // lines per staged row
+            const uint32_t row_bytes = (uint32_t)lw * 128u;
             uint32_t tile_it = 0;
             for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
                 const Item t = decode(a, w);
@@ -370,7 +373,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         int left = t.nvalid, oy = oy0, slot = 0;
                         while (left > 0) {
                             const int run = min(left, cv.rows_per_img - oy);
-                            const int nr = cv.s * (run - 1) + cv.KH;
+                            const int nr = isd ? run + cv.T - 1 : cv.s * (run - 1) + cv.KH;
                             mine += (nr + ((slot & 1) == pw ? 1 : 0)) >> 1;           // rows with (slot + y) & 1 == pw
                             slot += nr; left -= run; oy = 0;
                         }
@@ -380,11 +383,12 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     int left = t.nvalid, oy = oy0, slot = 0, b = b0;
                     while (left > 0) {
                         const int run = min(left, cv.rows_per_img - oy);
-                        const int nr = cv.s * (run - 1) + cv.KH;
+                        const int nr = isd ? run + cv.T - 1 : cv.s * (run - 1) + cv.KH;
+                        const int y0 = isd ? oy - (cv.T - 1) : cv.s * oy, x0 = isd ? -(cv.T - 1) : 0;
                         for (int y = ((slot & 1) == pw) ? 0 : 1; y < nr; y += 2)
                             for (int p2 = 0; p2 < cv.planes; ++p2)
-                                tma_load_4d(&tmA, &full_a[st], base + (uint32_t)((p2 * cv.nrows_max + slot + y)) * row_bytes, p2 * 32, 0,
-                                            cv.s * oy + y, b);
+                                tma_load_4d(&tmA, &full_a[st], base + (uint32_t)((p2 * cv.nrows_max + slot + y)) * row_bytes, p2 * 32, x0,
+                                            y0 + y, b);
                         slot += nr; left -= run; oy = 0; ++b;
                     }
                 }
@@ -563,7 +567,8 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const bool reload = !a.b_resident || t.cls != loaded_cls;
             // dgrad: (channel chunk, dkx, dky) of the k-block as counters, parity class of the tile
             int bk0 = 0, bk1 = 0, bk2 = 0;
-            const int bpy = a.conv.mode == 2 ? fdiv(t.cls, a.conv.s) : 0, bpx = a.conv.mode == 2 ? t.cls - bpy * a.conv.s : 0;
+            const bool dgrad = a.conv.mode == 2 || a.conv.mode == 7;
+            const int bpy = dgrad ? fdiv(t.cls, a.conv.s) : 0, bpx = dgrad ? t.cls - bpy * a.conv.s : 0;
             for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB)) {
                 const int kk = (int)(t.kk_begin + (int64_t)kb * BK);
                 const uint32_t s = a.b_resident ? (uint32_t)kb : rb.s;
@@ -577,7 +582,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         // pixel belong to the next k-block: finite values that meet the zeroed pad slots of A)
                         const int p0 = (t.kb0 + kb) * a.conv.nseg * a.conv.segw;
                         for (int q = 0; q < bn / 32; ++q) tma_load_2d(&tmB, &full_b[s], sb + q * 4096, 32 * q, p0);
-                    } else if (a.conv.mode == 2) {
+                    } else if (a.conv.mode == 2 || a.conv.mode == 7) {
                         // W [Cout, (ky, kx, c)]: box {32 c, 32 couts} of filter tap (ky, kx) = (py + s dky, px + s dkx)
                         const ConvA& cv = a.conv;
                         const int col = ((bpy + cv.s * bk2) * cv.KW + (bpx + cv.s * bk1)) * cv.Cin;
@@ -595,7 +600,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         }
                     }
                 }
-                if (a.conv.mode == 2) { if (++bk0 == a.conv.kpk) { bk0 = 0; if (++bk1 == a.conv.T) { bk1 = 0; ++bk2; } } }
+                if (dgrad) { if (++bk0 == a.conv.kpk) { bk0 = 0; if (++bk1 == a.conv.T) { bk1 = 0; ++bk2; } } }
                 __syncwarp();
             }
             if (a.b_resident && reload) { loaded_cls = t.cls; ++epoch; }
@@ -668,27 +673,34 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // mode 6 (tile-resident raw input): this thread's pixel is line `line0` of the stage for tap (0, 0); wait for the stage once
             uint32_t line0 = 0, stage6 = 0;
             int k_p = 0, k_kx = 0, k_ky = 0;           // channel plane, filter column, filter row of the current k-block
-            if (a.conv.mode == 6) {
+            const bool res6 = a.conv.mode == 6, res7 = a.conv.mode == 7, resident = res6 || res7;
+            const int lw = res7 ? a.conv.segw + a.conv.T - 1 : a.conv.Win;              // lines per staged row
+            if (resident) {
                 const ConvA& cv = a.conv;
                 const int g = r / cv.segw, ox = r - g * cv.segw;
+                if (res7) line0 = (uint32_t)((cv.T - 1) * lw + cv.T - 1);       // rows past the tile: any in-range line (the dgrad taps subtract)
                 if (g < t.nvalid) {
                     const int b0 = fdiv(t.seg0, cv.rows_per_img);
                     int oy = t.seg0 - b0 * cv.rows_per_img, run_slot = 0, run_a = oy;
                     for (int gg = 0; gg < g; ++gg)
-                        if (++oy == cv.rows_per_img) { run_slot += cv.s * (cv.rows_per_img - 1 - run_a) + cv.KH; run_a = 0; oy = 0; }
-                    line0 = (uint32_t)((run_slot + cv.s * (oy - run_a)) * cv.Win + ox * cv.s);
+                        if (++oy == cv.rows_per_img) {
+                            run_slot += res7 ? (cv.rows_per_img - run_a) + cv.T - 1 : cv.s * (cv.rows_per_img - 1 - run_a) + cv.KH;
+                            run_a = 0; oy = 0;
+                        }
+                    line0 = res7 ? (uint32_t)((run_slot + (oy - run_a) + cv.T - 1) * lw + ox + cv.T - 1)
+                                 : (uint32_t)((run_slot + cv.s * (oy - run_a)) * lw + ox * cv.s);
                 }
                 stage6 = smemA_u + (tile_it & 1u) * cv.tile_stage_bytes;
                 mbar_wait(&full_a[tile_it & 1u], (tile_it >> 1) & 1u);
             }
             for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB), turn = (turn + 1 == kGroups) ? 0 : turn + 1) {
-                if (a.conv.mode == 6 && kb > 0) {       // advance (plane, kx, ky) for EVERY k-block, also the other group's
-                    if (++k_p == a.conv.planes) { k_p = 0; if (++k_kx == a.conv.KW) { k_kx = 0; ++k_ky; } }
+                if (resident && kb > 0) {               // advance (plane, kx, ky) for EVERY k-block, also the other group's
+                    if (++k_p == a.conv.planes) { k_p = 0; if (++k_kx == (res7 ? a.conv.T : a.conv.KW)) { k_kx = 0; ++k_ky; } }
                 }
                 if (turn != grp) continue;
                 const uint32_t s = it % kSA;
                 if (q == 0) TCA_TRACE(it, 2);
-                if (a.conv.mode != 6) mbar_wait(&full_a[s], (it / kSA) & 1u);
+                if (!resident) mbar_wait(&full_a[s], (it / kSA) & 1u);
                 if (q == 0) TCA_TRACE(it, 3);
                 const uint32_t sa = smemA_u + s * a_bytes;
                 float x[32];
@@ -696,9 +708,11 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int c = 0; c < 32; ++c) x[c] = __uint_as_float(sa + c);
                 if (sa == 0xffffffffu)
 #endif
-                if (a.conv.mode == 6) {
+                if (resident) {
+                    // forward: tap (ky, kx) is lw*ky + kx lines further; dgrad: tap (dky, dkx) reads dY row i - dky, pixel j - dkx
                     const ConvA& cv = a.conv;
-                    const uint32_t line = (uint32_t)(k_p * cv.nrows_max * cv.Win) + line0 + (uint32_t)(k_ky * cv.Win + k_kx);
+                    const uint32_t line = (uint32_t)(k_p * cv.nrows_max * lw) + (res7 ? line0 - (uint32_t)(k_ky * lw + k_kx)
+                                                                                      : line0 + (uint32_t)(k_ky * lw + k_kx));
                     const uint32_t la = stage6 + line * 128u;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
@@ -763,7 +777,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int c = 0; c < 32; ++c) split_tf32(x[c], hi[c], lo[c]);
 #endif
                 __syncwarp();
-                if (lane == 0 && a.conv.mode != 6) mbar_arrive(&empty_a[s]);   // the tile is in registers: slot back to the producer
+                if (lane == 0 && !resident) mbar_arrive(&empty_a[s]);          // the tile is in registers: slot back to the producer
                 if (q == 0) TCA_TRACE(it, 4);
                 const uint32_t ts = it % kTA;
                 mbar_wait(&ta_empty[ts], ((it / kTA) & 1u) ^ 1u);
@@ -805,7 +819,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (lane == 0) mbar_arrive(&ta_full[ts]);
                 if (q == 0) TCA_TRACE(it, 7);
             }
-            if (a.conv.mode == 6) {                    // every read of this warp from the tile's stage is done
+            if (resident) {                            // every read of this warp from the tile's stage is done
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_a[tile_it & 1u]);
             }
@@ -822,11 +836,11 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int64_t i = t.i0 + q * 32 + lane;
             bool row_ok = i < a.I;
             int64_t crow_off = i * a.ldc + t.j0, mrow_off = i * a.ldm + t.j0;
-            if (a.conv.mode == 1 || a.conv.mode == 2 || a.conv.mode == 4 || a.conv.mode == 6) {
+            if (a.conv.mode == 1 || a.conv.mode == 2 || a.conv.mode == 4 || a.conv.mode == 6 || a.conv.mode == 7) {
                 const ConvA& cv = a.conv;
                 const int r = q * 32 + lane;
                 row_ok = r < t.nvalid * cv.segw;
-                if (cv.mode != 2) {
+                if (cv.mode != 2 && cv.mode != 7) {
                     crow_off = ((int64_t)t.seg0 * cv.segw + r) * a.ldc;            // output pixels of whole rows are contiguous
                 } else {
                     const int g = r / cv.segw, j = r - g * cv.segw;
@@ -1135,6 +1149,19 @@ int conv_dgrad(const float* dy, const ppd_conv_geom* g, int Cout, const float* w
     cv.nkb = cv.T * cv.T * cv.kpk;
     a.total_items = st * st * cv.ntile_class;
     PPD_REQUIRE(cv.nseg <= 32, "input width not supported (too many TMA boxes per tile)");
+    // Tile-resident dY (mode 7): every dY element goes through TMA once per tile instead of once per tap that reads it
+    if (g_conv_resident) {
+        const int planes = Cout / 32, lw = Wq + cv.T - 1;
+        const int max_runs = 1 + (cv.nseg - 1 + Hq - 1) / Hq;
+        const int nrows_max = cv.nseg + (cv.T - 1) * max_runs + 1;
+        const size_t stage = (((size_t)planes * nrows_max * lw * 128) + 1023) & ~(size_t)1023;
+        if (lw <= 256 && 2 * stage + 2 * (size_t)2 * g->C * BK * 4 + 1024 <= kSmemBudget) {
+            cuuint32_t bx[4] = {32, (cuuint32_t)lw, 1, 1};
+            if ((rc = make_map_nd(&tmA, dy, 4, dims, str, bx, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+            cv.mode = 7; cv.planes = planes; cv.nrows_max = nrows_max; cv.tile_stage_bytes = (uint32_t)stage;
+            a.a_region_bytes = (uint32_t)(2 * stage);
+        }
+    }
     return launch_conv(tmA, tmB, tmBlo, a, s);
 }
 
