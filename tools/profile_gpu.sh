@@ -14,7 +14,7 @@ echo "launch list rc=$? (skipped $SKIP)"
 # (2) DRAM traffic of the dominant kernel family over 64 consecutive launches (= 2 minibatches of 32 tca launches)
 $CMD > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:tca_gemm_kernel -s 200 -c 64 --csv --log-file $OUT/tca_traffic_$TAG.csv $CMD > $OUT/ncu_t_$TAG.log 2>&1
 echo "tca traffic rc=$?"
-# (3) full captures of the top kernels
+# (3) full captures of the top kernels (the 20th tca launch is a convolution)
 for K in tca_gemm_kernel gru_fwd_cluster512 gru_bwd_cluster512; do
   $CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:$K -s 20 -c 1 -o $OUT/prof_${K}_$TAG -f $CMD > $OUT/ncu_${K}_$TAG.log 2>&1
   echo "$K rc=$?"
