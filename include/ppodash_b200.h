@@ -238,8 +238,11 @@ int ppd_conv_wgrad(const float* x, const ppd_conv_geom* geom, int nchw, const fl
 int ppd_tc_gemm_col2im(const ppd_gemm_args* g, const ppd_conv_geom* geom, int flags, void* stream);
 /* x[i] = act[i] > 0 ? x[i] : 0 */
 int ppd_relu_mask(float* x, const float* act, int64_t n, void* stream);
-/* Tuning switch (default 1): narrow tiles run as two co-resident CTAs with a 2-deep ring each. */
-void ppd_tc_gemm_set_option(int two_ctas);
+/* Tuning / A-B switches (defaults in brackets): 0 / [1] two co-resident CTAs for the narrow tiles of the non-persistent kernel;
+ * 32 / 64 / 128 / 256 / [-1] force its tile width; 2 / [3] its TMEM-A mode; 4 / [5] non-persistent / persistent kernel for 3xTF32;
+ * 6 / [7] implicit convolutions with one im2col box per row and k-block / with the input staged once per tile; 8 / [9] streamed /
+ * shared-memory-resident weight tiles in the convolutions. */
+void ppd_tc_gemm_set_option(int option);
 /* out[j] (+)= sum_i X[i*ld + j]  (bias gradients) */
 size_t ppd_colsum_workspace(int64_t I, int64_t J);
 int ppd_colsum(const float* X, int64_t ld, int64_t I, int64_t J, float* out, int accumulate,

@@ -331,9 +331,22 @@ def test_split_tf32_is_exact_and_tf32():
     assert torch.all(err <= x.abs().double() * 2.0 ** -21)          # hi + lo carries >= 21 mantissa bits of x
 
 
+@pytest.fixture(params=[(1, 1), (0, 0), (1, 0)], ids=["resident", "per_kblock_boxes", "resident_input_streamed_weights"])
+def conv_variant(request):
+    """The implicit convolutions have two staging schemes each (ppd_tc_gemm_set_option 6/7: tile-resident raw input vs one im2col
+    box per row and k-block; 8/9: resident vs streamed weight tiles); both must give the same results."""
+    L = _lib.lib()
+    res, bres = request.param
+    L.ppd_tc_gemm_set_option(6 + res)
+    L.ppd_tc_gemm_set_option(8 + bres)
+    yield request.param
+    L.ppd_tc_gemm_set_option(7)
+    L.ppd_tc_gemm_set_option(9)
+
+
 @pytest.mark.parametrize("B,H,C,k,s,Cout", [(7, 20, 32, 4, 2, 64), (5, 9, 64, 3, 1, 32), (300, 20, 32, 4, 2, 64), (333, 9, 64, 3, 1, 32),
                                             (3, 12, 32, 2, 2, 32)])
-def test_conv_fwd_nhwc_implicit_gemm(B, H, C, k, s, Cout):
+def test_conv_fwd_nhwc_implicit_gemm(B, H, C, k, s, Cout, conv_variant):
     """ppd_conv_fwd_nhwc == ReLU(conv2d + bias) (PKG/model.py:177-178), NHWC in / out, weights (o, ky, kx, c)."""
     from ppodash_b200._lib import ConvGeom
     L = _lib.lib()
@@ -357,7 +370,7 @@ def test_conv_fwd_nhwc_implicit_gemm(B, H, C, k, s, Cout):
 
 @pytest.mark.parametrize("B,H,C,k,s,Cout", [(7, 9, 64, 3, 1, 32), (5, 20, 32, 4, 2, 64), (300, 20, 32, 4, 2, 64), (333, 9, 64, 3, 1, 32),
                                             (3, 12, 32, 2, 2, 32)])
-def test_conv_dgrad_nhwc_gather_form(B, H, C, k, s, Cout):
+def test_conv_dgrad_nhwc_gather_form(B, H, C, k, s, Cout, conv_variant):
     """ppd_conv_dgrad_nhwc == ReLU'(act) * conv_transpose2d(dy): every dx element written exactly once."""
     from ppodash_b200._lib import ConvGeom
     L = _lib.lib()
@@ -412,7 +425,7 @@ def test_conv_wgrad_implicit_gemm(B, H, C, k, s, Cout, nchw):
 
 
 @pytest.mark.parametrize("B,C,Cout", [(3, 3, 32), (40, 3, 32), (2, 1, 32), (5, 4, 32), (3, 12, 32)])
-def test_conv_fwd_nchw_observations(B, C, Cout):
+def test_conv_fwd_nchw_observations(B, C, Cout, conv_variant):
     """ppd_conv_fwd_nchw == ReLU(Conv2d(C, 32, 8, stride 4)(obs)) with NCHW observations and NHWC output."""
     from ppodash_b200._lib import ConvGeom
     L = _lib.lib()
