@@ -428,6 +428,11 @@ def run_b200(args, cfg):
 
     if not args.no_cpu_baseline and world == 1 and not big:
         line["cpu_baseline"] = cpu_reference(cfg, minibatches=2, warm=1)
+        # the reference's own setting is ONE thread (run.py:55 torch.set_num_threads(1)); SURVEY.md 8d asks for both
+        one = cpu_reference(cfg, minibatches=1, warm=0, threads=1)
+        line["cpu_baseline"]["single_thread"] = dict(value=one["value"], unit="env-steps/s", cores=1, sample=one["sample"],
+                                                     sec_per_minibatch=one["sec_per_minibatch"])
+        torch.set_num_threads(os.cpu_count() or 1)
         # second comparison row: the reference algorithm on the SAME GPU through stock PyTorch (not an optimisation
         # target either; it separates "GPU vs CPU" from "hand-written sm_100a kernels vs stock PyTorch")
         del st, host
