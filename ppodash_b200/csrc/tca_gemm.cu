@@ -156,10 +156,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 // hi = x rounded to TF32 (10 mantissa bits, round half away in magnitude), lo = (x - hi) rounded likewise.
 // Integer rounding on the bit pattern: 5 instructions per element (cvt.rna.tf32.f32 expands to ~8 on sm_100a).
 // x - hi is exact; Inf stays Inf, the largest finite values round to Inf as round-to-nearest does.
+// Used for the B operand (weights, split once per forward by split_tf32_kernel).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
     const float r = x - __uint_as_float(hi);
     lo = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+}
+// The A operand is split by the transform warps once per k-block and tile -- 32 elements per thread, and the transform
+// warps' instruction issue is what bounds the kernel (ncu: 163 of ~350 instructions per warp and k-block were the 5-instruction
+// split).  Two instructions: hi = x with the low 13 mantissa bits cleared (exactly representable in TF32), lo = x - hi, exact,
+// stored with all its bits -- the tensor core reads the TF32 part of it.  |x - hi - tf32(lo)| <= 2^-20 |x| (2^-22 with the
+// rounding split): still far below the 1e-5 gate, and the [hi | lo] pair never meets the rounding split of B in one product term.
+__device__ __forceinline__ void split_a(float x, uint32_t& hi, uint32_t& lo) {
+#ifdef PPD_SPLIT_ROUND
+    split_tf32(x, hi, lo);
+#else
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+#endif
 }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor)
@@ -215,10 +229,12 @@ __device__ long long* g_trace = nullptr;
 #define TCA_TRACE1(it_, slot_) do { } while (0)
 #endif
 
+template <int MODE>
 __device__ __forceinline__ Item decode(const Args& a, int w) {
+    constexpr int mode = MODE == 5 ? 3 : MODE;
     Item it;
     it.kb0 = 0;
-    if (a.conv.mode == 3) {
+    if (mode == 3) {
         it.z = fdiv(w, a.num_m);
         const int mt = w - it.z * a.num_m;
         it.i0 = (int64_t)mt * BM; it.j0 = 0; it.kk_begin = 0;
@@ -227,7 +243,7 @@ __device__ __forceinline__ Item decode(const Args& a, int w) {
         it.cls = mt; it.seg0 = 0; it.nvalid = 0;
         return it;
     }
-    if (a.conv.mode) {
+    if (mode) {
         it.cls = fdiv(w, a.conv.ntile_class);
         it.seg0 = (w - it.cls * a.conv.ntile_class) * a.conv.nseg;
         it.nvalid = min(a.conv.nseg, a.conv.nseg_class - it.seg0);
@@ -277,13 +293,17 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
 // whole warp with one ELECTED lane issuing the TMA / MMA / commit instructions.  That keeps tensor-map coordinates,
 // descriptors and barrier addresses in uniform registers: issued from a divergent `lane == 0` branch, each
 // tcgen05.mma cost ~185 clocks (seven R2UR moves per instruction) instead of ~33 (measured, tools/probes/mma_probe.cu).
+template <int MODE>       // ConvA::mode, as a compile-time constant (5 = mode 3 with raw rows): one lean kernel per operand layout
 __global__ void __launch_bounds__(kThreads, 1)
 tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmBlo, const Args a) {
+    constexpr int mode = MODE == 5 ? 3 : MODE;
+    constexpr bool raw = MODE == 5;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_a[kSA], empty_a[kSA], full_b[kMaxSB], empty_b[kMaxSB];
     __shared__ __align__(8) uint64_t ta_full[kTA], ta_empty[kTA], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ int tap_line[kMaxTaps];                  // modes 6 / 7: line offset of k-block kb inside the tile's stage
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int bn = a.bn;
@@ -298,11 +318,11 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (threadIdx.x == 0 && blockIdx.x == 0)
         printf("tca_gemm barriers: full_a %u empty_a %u full_b %u empty_b %u ta_full %u ta_empty %u acc_full %u acc_empty %u | mode %d items %d\n",
                smem_u32(full_a), smem_u32(empty_a), smem_u32(full_b), smem_u32(empty_b), smem_u32(ta_full), smem_u32(ta_empty),
-               smem_u32(acc_full), smem_u32(acc_empty), a.conv.mode, a.total_items);
+               smem_u32(acc_full), smem_u32(acc_empty), mode, a.total_items);
 #endif
     if (threadIdx.x == 0) {
         // convolution stages are filled by TWO producer warps (each arms the barrier for its own boxes)
-        for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], a.conv.mode ? kAProd : 1); mbar_init(&empty_a[s], (a.conv.mode == 6 || a.conv.mode == 7) ? kXformWarps : 4); }
+        for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], mode ? kAProd : 1); mbar_init(&empty_a[s], (mode == 6 || mode == 7) ? kXformWarps : 4); }
         for (int s = 0; s < kMaxSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < kTA; ++s) { mbar_init(&ta_full[s], 4); mbar_init(&ta_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
@@ -310,6 +330,15 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         if (a.b_presplit) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+    }
+    if ((mode == 6 || mode == 7) && (int)threadIdx.x >= 64 && (int)threadIdx.x - 64 < a.conv.nkb) {
+        // k-block kb = (channel plane, filter column, filter row), planes fastest.  Forward: tap (ky, kx) is lw*ky + kx lines
+        // further; dgrad: tap (dky, dkx) reads dY row i - dky, pixel j - dkx.
+        const ConvA& cv = a.conv;
+        const int kb = (int)threadIdx.x - 64, fw = mode == 7 ? cv.T : cv.KW;
+        const int lw = mode == 7 ? cv.segw + cv.T - 1 : cv.Win;
+        const int k_p = kb % cv.planes, tap = kb / cv.planes, k_kx = tap % fw, k_ky = tap / fw;
+        tap_line[kb] = k_p * cv.nrows_max * lw + (mode == 7 ? -(k_ky * lw + k_kx) : (k_ky * lw + k_kx));
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
@@ -322,11 +351,11 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
 
-    if (warp == 0 && a.conv.mode == 0) {
+    if (warp == 0 && mode == 0) {
         // ================= TMA producer, A tiles of a plain GEMM: one box per stage
         uint32_t it = 0;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
-            const Item t = decode(a, w);
+            const Item t = decode<MODE>(a, w);
             for (int kb = 0; kb < t.nkb; ++kb, ++it) {
                 const int kk = (int)(t.kk_begin + (int64_t)kb * BK);
                 const uint32_t s = it % kSA;
@@ -341,7 +370,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 __syncwarp();
             }
         }
-    } else if ((warp == 0 || warp == 3 || warp >= kFirstExtra) && a.conv.mode) {
+    } else if ((warp == 0 || warp == 3 || warp >= kFirstExtra) && mode) {
         // ================= TMA producers of a convolution: a stage is several boxes, shared between warp 0 and warp 3, each
         // walking its boxes from one elected thread (~55 clocks per box in a uniform-datapath loop; every lane issuing its
         // own box costs ~200: the compiler serialises them through R2UR broadcasts).  The k loop carries NO division: the
@@ -351,17 +380,17 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const ConvA& cv = a.conv;
         const int pw = warp == 0 ? 0 : (warp == 3 ? 1 : warp - kFirstExtra + 2);       // producer index 0 .. kAProd-1
         uint32_t it = 0;
-        if (cv.mode == 6 || cv.mode == 7) {
+        if (mode == 6 || mode == 7) {
             // tile-resident raw input: one stage per TILE (two stages).  Forward (6): image rows s*oy_a .. s*oy_b + KH - 1 of every
             // run of output rows inside one sample; dgrad (7): dY rows i_a - T + 1 .. i_b of every run of dx rows, T - 1 pixels of
             // left halo (out-of-bounds rows / pixels read as zero).  Per channel plane, plain NHWC boxes {32 channels, lw pixels};
             // rows alternate between the two producer warps.  Nothing is loaded per k-block.
-            const bool isd = cv.mode == 7;
+            const bool isd = mode == 7;
             const int lw = isd ? cv.segw + cv.T - 1 : cv.Win;                 // lines per staged row
             const uint32_t row_bytes = (uint32_t)lw * 128u;
             uint32_t tile_it = 0;
             for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
-                const Item t = decode(a, w);
+                const Item t = decode<MODE>(a, w);
                 const uint32_t st = tile_it & 1u;
                 mbar_wait(&empty_a[st], ((tile_it >> 1) & 1u) ^ 1u);
                 const int b0 = fdiv(t.seg0, cv.rows_per_img);
@@ -394,7 +423,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 __syncwarp();
             }
-        } else if (cv.mode == 3 && cv.raw) {
+        } else if (mode == 3 && raw) {
             // weight gradient over NCHW observations, raw rows: a k-block is 32 consecutive pixels of the flattened (b, oy, ox)
             // grid = at most 3 output rows; output row (b, oy) of channel c needs image rows s*oy .. s*oy + kh - 1, one
             // CONTIGUOUS range -> one 1-D bulk copy per (output row, channel).  (The 5-D im2col view of the same data is 80 runs
@@ -402,7 +431,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t row_bytes = (uint32_t)(cv.KW * cv.Win) * 4u;          // kh == kw image rows
             const int OW = cv.spr;                                                // pixels per output row
             for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
-                const Item t = decode(a, w);
+                const Item t = decode<MODE>(a, w);
                 const int ch0 = 2 * t.cls;
                 const int nhalf = min(2, cv.nchunks - ch0);
                 if (pw >= nhalf) {                                                 // nothing to load: only arrive
@@ -442,10 +471,10 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     __syncwarp();
                 }
             }
-        } else if (cv.mode == 3) {
+        } else if (mode == 3) {
             const uint32_t seg_bytes = (uint32_t)cv.segw * 256u;
             for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
-                const Item t = decode(a, w);
+                const Item t = decode<MODE>(a, w);
                 const int ch0 = 2 * t.cls;
                 const int nhalf = min(2, cv.nchunks - ch0);
                 // two chunk halves: producers (pw & 1) take one half each, and with four producers (pw >> 1) splits the segments;
@@ -498,10 +527,10 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         } else {
             const int kyg = 32 / max(cv.KW, 1);
-            const uint32_t seg_bytes = cv.mode == 4 ? (uint32_t)(kyg * cv.Win) * 4u : (uint32_t)cv.segw * 128u;
+            const uint32_t seg_bytes = mode == 4 ? (uint32_t)(kyg * cv.Win) * 4u : (uint32_t)cv.segw * 128u;
             const uint32_t seg_pitch = seg_bytes;
             for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
-                const Item t = decode(a, w);
+                const Item t = decode<MODE>(a, w);
                 // modes 1, 2, 4: the segments of a tile are consecutive rows (b, row); the two producer warps take half each
                 const int per = (t.nvalid + kAProd - 1) / kAProd;
                 const int lo_op = min(t.nvalid, pw * per), hi_op = min(t.nvalid, lo_op + per);
@@ -520,7 +549,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         uint32_t dst = smem_u32(smemA + s * a_bytes) + lo_op * seg_pitch;
                         int row = row0, b = b0;
                         // one tight loop per mode: c = the coordinate that moves with the row, the rest is fixed for the stage
-                        if (cv.mode == 1) {
+                        if (mode == 1) {
                             const int c0 = k0 * 32;
                             int y = row * cv.s + k1;
                             for (int g = lo_op; g < hi_op; ++g, dst += seg_pitch) {
@@ -528,7 +557,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 y += cv.s;
                                 if (++row == cv.rows_per_img) { row = 0; ++b; y = k1; }
                             }
-                        } else if (cv.mode == 2) {
+                        } else if (mode == 2) {
                             const int c0 = k0 * 32, x0 = -k1;
                             int y = row - k2;
                             for (int g = lo_op; g < hi_op; ++g, dst += seg_pitch) {
@@ -548,7 +577,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             }
                         }
                     }
-                    if (cv.mode == 2) { if (++k0 == cv.kpk) { k0 = 0; if (++k1 == cv.T) { k1 = 0; ++k2; } } }
+                    if (mode == 2) { if (++k0 == cv.kpk) { k0 = 0; if (++k1 == cv.T) { k1 = 0; ++k2; } } }
                     else              { if (++k0 == cv.kpk) { k0 = 0; ++k1; } }
                     __syncwarp();
                 }
@@ -563,11 +592,11 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int loaded_cls = -1;
         Ring rb;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
-            const Item t = decode(a, w);
+            const Item t = decode<MODE>(a, w);
             const bool reload = !a.b_resident || t.cls != loaded_cls;
             // dgrad: (channel chunk, dkx, dky) of the k-block as counters, parity class of the tile
             int bk0 = 0, bk1 = 0, bk2 = 0;
-            const bool dgrad = a.conv.mode == 2 || a.conv.mode == 7;
+            const bool dgrad = mode == 2 || mode == 7;
             const int bpy = dgrad ? fdiv(t.cls, a.conv.s) : 0, bpx = dgrad ? t.cls - bpy * a.conv.s : 0;
             for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB)) {
                 const int kk = (int)(t.kk_begin + (int64_t)kb * BK);
@@ -577,12 +606,12 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     TCA_TRACE1(it, 1);
                     mbar_expect_tx(&full_b[s], a.b_presplit ? 2 * b_bytes : b_bytes);
                     uint8_t* sb = smemB + s * 2 * b_bytes;
-                    if (a.conv.mode == 3) {
+                    if (mode == 3) {
                         // dY [pixels, Cout]: the 32 pixel rows starting at the k-block's first pixel (rows past its last valid
                         // pixel belong to the next k-block: finite values that meet the zeroed pad slots of A)
                         const int p0 = (t.kb0 + kb) * a.conv.nseg * a.conv.segw;
                         for (int q = 0; q < bn / 32; ++q) tma_load_2d(&tmB, &full_b[s], sb + q * 4096, 32 * q, p0);
-                    } else if (a.conv.mode == 2 || a.conv.mode == 7) {
+                    } else if (mode == 2 || mode == 7) {
                         // W [Cout, (ky, kx, c)]: box {32 c, 32 couts} of filter tap (ky, kx) = (py + s dky, px + s dkx)
                         const ConvA& cv = a.conv;
                         const int col = ((bpy + cv.s * bk2) * cv.KW + (bpx + cv.s * bk1)) * cv.Cin;
@@ -618,11 +647,11 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int loaded_cls = -1;
         Ring rb;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
-            const Item t = decode(a, w);
+            const Item t = decode<MODE>(a, w);
             const bool reload = !a.b_resident || t.cls != loaded_cls;
             // resident B: its stages are released only when this CTA's NEXT tile needs other weights
             const int wn = w + gridDim.x;
-            const bool release = !a.b_resident || (wn < a.total_items && decode(a, wn).cls != t.cls);
+            const bool release = !a.b_resident || (wn < a.total_items && decode<MODE>(a, wn).cls != t.cls);
             const uint32_t acc = tile_it & 1u;
             mbar_wait(&acc_empty[acc], ((tile_it >> 1) & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -668,16 +697,20 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t it = 0, tile_it = 0;
         int turn = 0;                                  // it % kGroups
         Ring rb;
+        // per-thread constants of the convolution modes (row r of the tile = pixel ox of tile row g): no division in the loops
+        const int g_r = mode ? r / max(a.conv.segw, 1) : 0, ox_r = mode ? r - g_r * a.conv.segw : 0;
+        const uint32_t row4 = (uint32_t)a.conv.Win * 4u;
+        const uint32_t off4 = mode == 4 ? (uint32_t)(g_r * (32 / max(a.conv.KW, 1)) * a.conv.Win + ox_r * a.conv.s) * 4u : 0u;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
-            const Item t = decode(a, w);
+            const Item t = decode<MODE>(a, w);
+            const bool ok4 = g_r < t.nvalid;
             // mode 6 (tile-resident raw input): this thread's pixel is line `line0` of the stage for tap (0, 0); wait for the stage once
             uint32_t line0 = 0, stage6 = 0;
-            int k_p = 0, k_kx = 0, k_ky = 0;           // channel plane, filter column, filter row of the current k-block
-            const bool res6 = a.conv.mode == 6, res7 = a.conv.mode == 7, resident = res6 || res7;
+            const bool res6 = mode == 6, res7 = mode == 7, resident = res6 || res7;
             const int lw = res7 ? a.conv.segw + a.conv.T - 1 : a.conv.Win;              // lines per staged row
             if (resident) {
                 const ConvA& cv = a.conv;
-                const int g = r / cv.segw, ox = r - g * cv.segw;
+                const int g = g_r, ox = ox_r;
                 if (res7) line0 = (uint32_t)((cv.T - 1) * lw + cv.T - 1);       // rows past the tile: any in-range line (the dgrad taps subtract)
                 if (g < t.nvalid) {
                     const int b0 = fdiv(t.seg0, cv.rows_per_img);
@@ -694,9 +727,6 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 mbar_wait(&full_a[tile_it & 1u], (tile_it >> 1) & 1u);
             }
             for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB), turn = (turn + 1 == kGroups) ? 0 : turn + 1) {
-                if (resident && kb > 0) {               // advance (plane, kx, ky) for EVERY k-block, also the other group's
-                    if (++k_p == a.conv.planes) { k_p = 0; if (++k_kx == (res7 ? a.conv.T : a.conv.KW)) { k_kx = 0; ++k_ky; } }
-                }
                 if (turn != grp) continue;
                 const uint32_t s = it % kSA;
                 if (q == 0) TCA_TRACE(it, 2);
@@ -710,16 +740,14 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #endif
                 if (resident) {
                     // forward: tap (ky, kx) is lw*ky + kx lines further; dgrad: tap (dky, dkx) reads dY row i - dky, pixel j - dkx
-                    const ConvA& cv = a.conv;
-                    const uint32_t line = (uint32_t)(k_p * cv.nrows_max * lw) + (res7 ? line0 - (uint32_t)(k_ky * lw + k_kx)
-                                                                                      : line0 + (uint32_t)(k_ky * lw + k_kx));
+                    const uint32_t line = line0 + (uint32_t)tap_line[kb];
                     const uint32_t la = stage6 + line * 128u;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const float4 v = lds128(la + (((uint32_t)c ^ (line & 7u)) << 4));
                         x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
                     }
-                } else if (a.conv.mode == 3 && a.conv.raw) {
+                } else if (mode == 3 && raw) {
                     // raw rows [half][output row][ky][W]: patch element (ky, kx) of pixel slot p sits at row ky, float s*ox_p + kx
                     const ConvA& cv = a.conv;
                     const int OW = cv.spr;
@@ -736,7 +764,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         off += (uint32_t)cv.s * 4u;
                         if (++ox == OW) { ox = 0; rowoff += row_bytes; off = rowoff; }
                     }
-                } else if (a.conv.mode == 3) {
+                } else if (mode == 3) {
                     // [half][pixel slot][64 patch floats]; slots past the valid pixels and chunks past K are zero
                     const ConvA& cv = a.conv;
                     const int seg0 = (t.kb0 + kb) * cv.nseg;
@@ -745,17 +773,14 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t base = sa + (uint32_t)(r >> 6) * 8192u + (uint32_t)(r & 63) * 4u;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) x[c] = (chunk_ok && c < npx) ? lds32(base + c * 256) : 0.f;
-                } else if (a.conv.mode == 4) {
-                    const ConvA& cv = a.conv;
-                    const int g = r / cv.segw, ox = r - g * cv.segw;
-                    const int kyg = 32 / cv.KW;                                  // 4 rows of 8 floats
-                    const uint32_t base = sa + (uint32_t)(g * kyg * cv.Win + ox * cv.s) * 4u;
-                    const bool ok = g < min(cv.nseg, cv.nseg_class - t.seg0);
+                } else if (mode == 4) {
+                    // stage = [output row g][kyg = 4 image rows][W]; this thread's pixel starts at float off4 of the stage
+                    const uint32_t base = sa + off4;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         // float4 index c: filter row c / 2 (kw = 8: two float4 per row)
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ok) v = lds128(base + (uint32_t)((c >> 1) * cv.Win) * 4u + (uint32_t)(c & 1) * 16u);
+                        if (ok4) v = lds128(base + (uint32_t)(c >> 1) * row4 + (uint32_t)(c & 1) * 16u);
                         x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
                     }
                 } else if (!a.a_mn) {
@@ -774,7 +799,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #ifdef PPD_ABL_NOSPLIT
                 for (int c = 0; c < 32; ++c) { hi[c] = __float_as_uint(x[c]); lo[c] = 0u; }
 #else
-                for (int c = 0; c < 32; ++c) split_tf32(x[c], hi[c], lo[c]);
+                for (int c = 0; c < 32; ++c) split_a(x[c], hi[c], lo[c]);
 #endif
                 __syncwarp();
                 if (lane == 0 && !resident) mbar_arrive(&empty_a[s]);          // the tile is in registers: slot back to the producer
@@ -829,18 +854,18 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int q = warp & 3;
         uint32_t tile_it = 0;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
-            const Item t = decode(a, w);
+            const Item t = decode<MODE>(a, w);
             const uint32_t acc = tile_it & 1u;
             mbar_wait(&acc_full[acc], (tile_it >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t i = t.i0 + q * 32 + lane;
             bool row_ok = i < a.I;
             int64_t crow_off = i * a.ldc + t.j0, mrow_off = i * a.ldm + t.j0;
-            if (a.conv.mode == 1 || a.conv.mode == 2 || a.conv.mode == 4 || a.conv.mode == 6 || a.conv.mode == 7) {
+            if (mode == 1 || mode == 2 || mode == 4 || mode == 6 || mode == 7) {
                 const ConvA& cv = a.conv;
                 const int r = q * 32 + lane;
                 row_ok = r < t.nvalid * cv.segw;
-                if (cv.mode != 2 && cv.mode != 7) {
+                if (mode != 2 && mode != 7) {
                     crow_off = ((int64_t)t.seg0 * cv.segw + r) * a.ldc;            // output pixels of whole rows are contiguous
                 } else {
                     const int g = r / cv.segw, j = r - g * cv.segw;
@@ -953,6 +978,34 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+// One instantiation per operand layout (ConvA::mode; 5 = weight gradient over raw rows).
+template <int MODE>
+cudaError_t launch_mode(int grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
+                        const Args& a) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tca_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    tca_gemm_kernel<MODE><<<grid, kThreads, smem, s>>>(tmA, tmB, tmBlo, a);
+    return cudaSuccess;
+}
+cudaError_t launch_kernel(int grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
+                          const Args& a) {
+    switch (a.conv.mode == 3 && a.conv.raw ? 5 : a.conv.mode) {
+        case 0: return launch_mode<0>(grid, smem, s, tmA, tmB, tmBlo, a);
+        case 1: return launch_mode<1>(grid, smem, s, tmA, tmB, tmBlo, a);
+        case 2: return launch_mode<2>(grid, smem, s, tmA, tmB, tmBlo, a);
+        case 3: return launch_mode<3>(grid, smem, s, tmA, tmB, tmBlo, a);
+        case 4: return launch_mode<4>(grid, smem, s, tmA, tmB, tmBlo, a);
+        case 5: return launch_mode<5>(grid, smem, s, tmA, tmB, tmBlo, a);
+        case 6: return launch_mode<6>(grid, smem, s, tmA, tmB, tmBlo, a);
+        case 7: return launch_mode<7>(grid, smem, s, tmA, tmB, tmBlo, a);
+    }
+    return cudaErrorInvalidValue;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1040,10 +1093,9 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     PPD_REQUIRE(sb_stages >= 2, "shared memory: no room for the B ring");
     a.sb_stages = sb_stages;
     const size_t smem = a_region + (size_t)sb_stages * 2 * a.bn * BK * 4 + 1024;
-    cudaError_t e = cudaFuncSetAttribute(tca_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-    if (e != cudaSuccess) { set_error("tca conv: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
     const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
-    tca_gemm_kernel<<<grid, kThreads, smem, s>>>(tmA, tmB, tmBlo, a);
+    cudaError_t e = launch_kernel(grid, smem, s, tmA, tmB, tmBlo, a);
+    if (e != cudaSuccess) { set_error("tca conv: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
     return launch_status("tca_gemm_kernel(conv)");
 }
 
@@ -1079,7 +1131,7 @@ int conv_forward(const float* x, const ppd_conv_geom* g, int Cout, const float* 
         const int max_runs = 1 + (cv.nseg - 1 + OH - 1) / OH;
         const int nrows_max = g->stride * cv.nseg + (g->kh > g->stride ? (g->kh - g->stride) * max_runs : 0) + 1;
         const size_t stage = (((size_t)planes * nrows_max * g->W * 128) + 1023) & ~(size_t)1023;
-        if (2 * stage + 2 * (size_t)2 * Cout * BK * 4 + 1024 <= kSmemBudget) {
+        if (cv.nkb <= kMaxTaps && 2 * stage + 2 * (size_t)2 * Cout * BK * 4 + 1024 <= kSmemBudget) {
             cuuint64_t d4[4] = {(cuuint64_t)g->C, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->B};
             cuuint64_t s4[3] = {(cuuint64_t)g->C * 4, (cuuint64_t)g->W * g->C * 4, (cuuint64_t)g->H * g->W * g->C * 4};
             cuuint32_t b4[4] = {32, (cuuint32_t)g->W, 1, 1};
@@ -1155,7 +1207,7 @@ int conv_dgrad(const float* dy, const ppd_conv_geom* g, int Cout, const float* w
         const int max_runs = 1 + (cv.nseg - 1 + Hq - 1) / Hq;
         const int nrows_max = cv.nseg + (cv.T - 1) * max_runs + 1;
         const size_t stage = (((size_t)planes * nrows_max * lw * 128) + 1023) & ~(size_t)1023;
-        if (lw <= 256 && 2 * stage + 2 * (size_t)2 * g->C * BK * 4 + 1024 <= kSmemBudget) {
+        if (lw <= 256 && cv.nkb <= kMaxTaps && 2 * stage + 2 * (size_t)2 * g->C * BK * 4 + 1024 <= kSmemBudget) {
             cuuint32_t bx[4] = {32, (cuuint32_t)lw, 1, 1};
             if ((rc = make_map_nd(&tmA, dy, 4, dims, str, bx, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
             cv.mode = 7; cv.planes = planes; cv.nrows_max = nrows_max; cv.tile_stage_bytes = (uint32_t)stage;
@@ -1241,10 +1293,9 @@ int conv_wgrad(const float* x, const ppd_conv_geom* g, int nchw, const float* dy
     if (sb_stages > 8) sb_stages = 8;
     a.sb_stages = sb_stages;
     const size_t smem = (size_t)kSA * BM * BK * 4 + (size_t)sb_stages * 2 * a.bn * BK * 4 + 1024;
-    cudaError_t e = cudaFuncSetAttribute(tca_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-    if (e != cudaSuccess) { set_error("tca conv: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
     const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
-    tca_gemm_kernel<<<grid, kThreads, smem, s>>>(tmA, tmB, tmB, a);
+    cudaError_t e = launch_kernel(grid, smem, s, tmA, tmB, tmB, a);
+    if (e != cudaSuccess) { set_error("tca conv: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
     if (splits_out) *splits_out = splits;
     (void)accumulate; (void)dW;
     return launch_status("tca_gemm_kernel(wgrad)");
@@ -1305,14 +1356,11 @@ int launch(const ppd_gemm_args* g, int transpose_out, const float* b_lo, void* w
     if (sb_stages > 8) sb_stages = 8;
     a.sb_stages = sb_stages;
     const size_t smem = (size_t)kSA * BM * BK * 4 + (size_t)sb_stages * 2 * p.bn * BK * 4 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tca_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
-        if (e != cudaSuccess) { set_error("tca_gemm: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
-        attr_set = true;
-    }
     const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
-    tca_gemm_kernel<<<grid, kThreads, smem, s>>>(tmA, tmB, tmBlo, a);
+    {
+        cudaError_t e = launch_kernel(grid, smem, s, tmA, tmB, tmBlo, a);
+        if (e != cudaSuccess) { set_error("tca_gemm: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
+    }
     if (plan_out) *plan_out = p;
     return launch_status("tca_gemm_kernel");
 }
