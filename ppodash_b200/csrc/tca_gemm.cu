@@ -756,13 +756,24 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const bool chunk_ok = 2 * t.cls + (r >> 6) < cv.nchunks;
                     const uint32_t row_bytes = (uint32_t)(cv.KW * cv.Win) * 4u;
                     const uint32_t base = sa + (uint32_t)(r >> 6) * 3u * row_bytes + (uint32_t)(((r >> 3) & 7) * cv.Win + (r & 7)) * 4u;
-                    int ox = P0 - fdiv(P0, OW) * OW;
-                    uint32_t rowoff = 0, off = (uint32_t)(ox * cv.s) * 4u;
+                    const int ox0 = P0 - fdiv(P0, OW) * OW;
+                    // Offset of pixel slot c inside the stage (the same for every thread): lane c computes it once, the
+                    // unrolled loop below fetches it with one shuffle -- 3 instructions per element instead of ~10 of a
+                    // running (ox, row) counter (20 % of the kernel's instructions, ncu).  A k-block is at most 3 output rows.
+                    const int p = ox0 + lane, prow = (p >= OW ? 1 : 0) + (p >= 2 * OW ? 1 : 0);
+                    const uint32_t myoff = (uint32_t)prow * row_bytes + (uint32_t)((p - prow * OW) * cv.s) * 4u;
+                    if (!chunk_ok) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        x[c] = (chunk_ok && c < npx) ? lds32(base + off) : 0.f;
-                        off += (uint32_t)cv.s * 4u;
-                        if (++ox == OW) { ox = 0; rowoff += row_bytes; off = rowoff; }
+                        for (int c = 0; c < 32; ++c) x[c] = 0.f;
+                    } else if (npx == 32) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) x[c] = lds32(base + __shfl_sync(0xffffffffu, myoff, c));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const uint32_t o = __shfl_sync(0xffffffffu, myoff, c);
+                            x[c] = c < npx ? lds32(base + o) : 0.f;
+                        }
                     }
                 } else if (mode == 3) {
                     // [half][pixel slot][64 patch floats]; slots past the valid pixels and chunks past K are zero
@@ -771,8 +782,13 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int npx = min(cv.nseg, cv.total_seg - seg0) * cv.segw;
                     const bool chunk_ok = 2 * t.cls + (r >> 6) < cv.nchunks;
                     const uint32_t base = sa + (uint32_t)(r >> 6) * 8192u + (uint32_t)(r & 63) * 4u;
+                    if (chunk_ok && npx >= 32) {             // the common case: no predicates
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) x[c] = (chunk_ok && c < npx) ? lds32(base + c * 256) : 0.f;
+                        for (int c = 0; c < 32; ++c) x[c] = lds32(base + c * 256);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) x[c] = (chunk_ok && c < npx) ? lds32(base + c * 256) : 0.f;
+                    }
                 } else if (mode == 4) {
                     // stage = [output row g][kyg = 4 image rows][W]; this thread's pixel starts at float off4 of the stage
                     const uint32_t base = sa + off4;
@@ -829,10 +845,10 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int v = gt; v < nvec; v += 128) {
                         const float4 xb = lds128(src + (v << 4));
                         uint4 hb, rb;
-                        split_tf32(xb.x, hb.x, rb.x);
-                        split_tf32(xb.y, hb.y, rb.y);
-                        split_tf32(xb.z, hb.z, rb.z);
-                        split_tf32(xb.w, hb.w, rb.w);
+                        split_a(xb.x, hb.x, rb.x);
+                        split_a(xb.y, hb.y, rb.y);
+                        split_a(xb.z, hb.z, rb.z);
+                        split_a(xb.w, hb.w, rb.w);
                         sts128(src + (v << 4), hb);
                         sts128(src + b_bytes + (v << 4), rb);
                     }
