@@ -445,33 +445,44 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
                 const int ch = ch0 + pw;
                 int P0 = t.kb0 * 32;
-                int R = fdiv(P0, OW), ox0 = P0 - R * OW;                          // first output row (flattened b*OH + oy) and pixel
-                int b = fdiv(R, cv.rows_per_img), oy = R - b * cv.rows_per_img;
+                const int R = fdiv(P0, OW);                                       // first output row (flattened b*OH + oy) and pixel
+                int ox0 = P0 - R * OW;
+                const int b = fdiv(R, cv.rows_per_img);
+                int oy = R - b * cv.rows_per_img;
+                // image rows of output row (b, oy), channel ch: a running pointer, no multiplications in the k loop
+                const int row_step = cv.s * cv.Win;
+                const size_t wrap = (size_t)cv.C * cv.Hin * cv.Win - (size_t)cv.rows_per_img * row_step;
+                const float* src0 = a.a_ptr + ((size_t)(b * cv.C + ch) * cv.Hin + (size_t)oy * cv.s) * cv.Win;
+                const bool leader = elect_one();
                 for (int kb = 0; kb < t.nkb; ++kb, ++it) {
                     const uint32_t s = it % kSA;
                     mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
-                    const int npx = min(32, cv.total_seg - P0);
-                    const int nrows = (ox0 + npx + OW - 1) / OW;                  // 1..3 (small constant divisor path: OW is run-time, but
-                                                                                  // this is one division per k-block on the vector pipe)
-                    if (elect_one()) {
+                    const int e = ox0 + min(32, cv.total_seg - P0);
+                    const int nrows = 1 + (e > OW ? 1 : 0) + (e > 2 * OW ? 1 : 0);      // a k-block is at most 3 output rows
+                    if (leader) {
                         TCA_TRACE1(it, pw ? 10 : 0);
                         mbar_expect_tx(&full_a[s], (uint32_t)nrows * row_bytes);
                         uint32_t dst = smem_u32(smemA + s * a_bytes) + (uint32_t)pw * 3u * row_bytes;
-                        int b2 = b, oy2 = oy;
+                        const float* src = src0;
+                        int oy2 = oy;
                         for (int r = 0; r < nrows; ++r, dst += row_bytes) {
-                            const float* src = a.a_ptr + ((size_t)(b2 * cv.C + ch) * cv.Hin + (size_t)oy2 * cv.s) * cv.Win;
                             bulk_load_1d(src, &full_a[s], dst, row_bytes);
-                            if (++oy2 == cv.rows_per_img) { oy2 = 0; ++b2; }
+                            src += row_step;
+                            if (++oy2 == cv.rows_per_img) { oy2 = 0; src += wrap; }
                         }
                     }
                     // advance 32 pixels
                     P0 += 32;
                     ox0 += 32;
-                    while (ox0 >= OW) { ox0 -= OW; if (++oy == cv.rows_per_img) { oy = 0; ++b; } }
+                    while (ox0 >= OW) { ox0 -= OW; src0 += row_step; if (++oy == cv.rows_per_img) { oy = 0; src0 += wrap; } }
                     __syncwarp();
                 }
             }
         } else if (mode == 3) {
+            // One walk over the segments of a k-block per producer: every lane advances the running position (sample b, output
+            // row oy, row segment sub) in uniform registers, the elected lane issues the boxes that are this producer's.  (A
+            // separate skip / issue / catch-up walk cost ~245 uniform-datapath instructions per k-block: the A producers, not
+            // TMA or the transform warps, bounded the weight-gradient kernels.)
             const uint32_t seg_bytes = (uint32_t)cv.segw * 256u;
             for (int w = blockIdx.x; w < a.total_items; w += gridDim.x) {
                 const Item t = decode<MODE>(a, w);
@@ -484,43 +495,35 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int ch = ch0 + hh;
                 const int ky = cv.nchw ? 0 : fdiv(ch, cv.cpr);
                 const int j0 = (ch - ky * cv.cpr) * 64;
-                // running position of the next segment of this item: (sample b, output row oy, row segment sub)
                 int seg = t.kb0 * cv.nseg;
                 const int rowidx0 = fdiv(seg, cv.spr);
                 int b = fdiv(rowidx0, cv.rows_per_img);
                 int oy = rowidx0 - b * cv.rows_per_img, sub = seg - rowidx0 * cv.spr;
+                int x = sub * cv.segw, y = oy * cv.s + ky, cb = b * cv.C + ch;
+                const bool leader = elect_one();
                 for (int kb = 0; kb < t.nkb; ++kb, ++it) {
                     const uint32_t s = it % kSA;
                     mbar_wait(&empty_a[s], ((it / kSA) & 1u) ^ 1u);
                     const int nvalid = min(cv.nseg, cv.total_seg - seg);
-                    const int per = (nvalid + nparts - 1) / nparts;
+                    const int per = nparts == 1 ? nvalid : (nparts == 2 ? (nvalid + 1) >> 1 : (nvalid + 3) >> 2);
                     const int g_lo = min(nvalid, part * per), g_hi = min(nvalid, g_lo + per);
-                    // skip the segments of the other producer warp (single-half tiles only), then walk this warp's boxes
-                    for (int g = 0; g < g_lo; ++g)
-                        if (++sub == cv.spr) { sub = 0; if (++oy == cv.rows_per_img) { oy = 0; ++b; } }
-                    if (elect_one()) {
+                    if (leader) {
                         TCA_TRACE1(it, pw ? 10 : 0);
                         mbar_expect_tx(&full_a[s], (uint32_t)(g_hi - g_lo) * seg_bytes);
-                        uint32_t dst = smem_u32(smemA + s * a_bytes) + hh * 8192u + g_lo * seg_bytes;
-                        int sb2 = sub, oy2 = oy, b2 = b;
-                        if (cv.nchw) {
-                            int x = sb2 * cv.segw, cb = b2 * cv.C + ch;
-                            for (int g = g_lo; g < g_hi; ++g, dst += seg_bytes) {
-                                tma_load_5d(&tmA, &full_a[s], dst, 0, 0, x, oy2, cb);
-                                x += cv.segw;
-                                if (++sb2 == cv.spr) { sb2 = 0; x = 0; if (++oy2 == cv.rows_per_img) { oy2 = 0; cb += cv.C; } }
-                            }
-                        } else {
-                            int x = sb2 * cv.segw, y = oy2 * cv.s + ky;
-                            for (int g = g_lo; g < g_hi; ++g, dst += seg_bytes) {
-                                tma_load_4d(&tmA, &full_a[s], dst, j0, x, y, b2);
-                                x += cv.segw;
-                                if (++sb2 == cv.spr) { sb2 = 0; x = 0; y += cv.s; if (++oy2 == cv.rows_per_img) { oy2 = 0; y = ky; ++b2; } }
-                            }
+                    }
+                    uint32_t dst = smem_u32(smemA + s * a_bytes) + hh * 8192u + g_lo * seg_bytes;
+                    for (int g = 0; g < nvalid; ++g) {
+                        if (leader && g >= g_lo && g < g_hi) {
+                            if (cv.nchw) tma_load_5d(&tmA, &full_a[s], dst, 0, 0, x, oy, cb);
+                            else         tma_load_4d(&tmA, &full_a[s], dst, j0, x, y, b);
+                            dst += seg_bytes;
+                        }
+                        x += cv.segw;
+                        if (++sub == cv.spr) {
+                            sub = 0; x = 0; y += cv.s;
+                            if (++oy == cv.rows_per_img) { oy = 0; y = ky; ++b; cb += cv.C; }
                         }
                     }
-                    for (int g = g_lo; g < nvalid; ++g)            // every lane keeps the running position
-                        if (++sub == cv.spr) { sub = 0; if (++oy == cv.rows_per_img) { oy = 0; ++b; } }
                     seg += nvalid;
                     __syncwarp();
                 }
@@ -1144,10 +1147,19 @@ int conv_forward(const float* x, const ppd_conv_geom* g, int Cout, const float* 
     // Tile-resident raw input (mode 6) when two stages of it and a B ring fit: every input element goes through TMA once per tile
     if (g_conv_resident && g->C % 32 == 0) {
         const int planes = g->C / 32;
-        const int max_runs = 1 + (cv.nseg - 1 + OH - 1) / OH;
-        const int nrows_max = g->stride * cv.nseg + (g->kh > g->stride ? (g->kh - g->stride) * max_runs : 0) + 1;
-        const size_t stage = (((size_t)planes * nrows_max * g->W * 128) + 1023) & ~(size_t)1023;
-        if (cv.nkb <= kMaxTaps && 2 * stage + 2 * (size_t)2 * Cout * BK * 4 + 1024 <= kSmemBudget) {
+        // two stages of the rows of a tile + a B ring of at least two stages must fit: a tile may give up to two of its output rows for that
+        int nseg = cv.nseg, max_runs = 0, nrows_max = 0;
+        size_t stage = 0;
+        for (; nseg >= 1 && nseg >= cv.nseg - 2; --nseg) {
+            max_runs = 1 + (nseg - 1 + OH - 1) / OH;
+            nrows_max = g->stride * nseg + (g->kh > g->stride ? (g->kh - g->stride) * max_runs : 0) + 1;
+            stage = (((size_t)planes * nrows_max * g->W * 128) + 1023) & ~(size_t)1023;
+            if (2 * stage + 2 * (size_t)2 * Cout * BK * 4 + 1024 <= kSmemBudget) break;
+        }
+        if (cv.nkb <= kMaxTaps && nseg >= 1 && nseg >= cv.nseg - 2) {
+            cv.nseg = nseg;
+            cv.ntile_class = (cv.nseg_class + cv.nseg - 1) / cv.nseg;
+            a.total_items = cv.ntile_class;
             cuuint64_t d4[4] = {(cuuint64_t)g->C, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->B};
             cuuint64_t s4[3] = {(cuuint64_t)g->C * 4, (cuuint64_t)g->W * g->C * 4, (cuuint64_t)g->H * g->W * g->C * 4};
             cuuint32_t b4[4] = {32, (cuuint32_t)g->W, 1, 1};
