@@ -3,6 +3,7 @@
 
   python tools/ncu_summary.py launches gpurun_out/launches.csv profiles/r1_launches.md "command line"
   python tools/ncu_summary.py full gpurun_out/prof.ncu-rep profiles/r1_kernel.md
+  python tools/ncu_summary.py traffic gpurun_out/tca_traffic.csv profiles/r1_tca_traffic "command line"     (writes .md and .json)
 """
 import collections
 import csv
@@ -67,8 +68,39 @@ def full(src, dst):
     print("wrote", dst)
 
 
+def traffic(src, dst, cmd):
+    """DRAM bytes and device time of consecutive launches of one kernel family (3 metrics per launch)."""
+    import json
+    lines = [l for l in open(src) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        d = per.setdefault(int(row["ID"]), {"grid": row["Grid Size"], "kernel": short(row["Kernel Name"])})
+        v = float(row["Metric Value"].replace(",", ""))
+        if row["Metric Name"].startswith("gpu__time"):
+            u = row["Metric Unit"]
+            d["us"] = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
+        else:
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[row["Metric Unit"]]
+            d["read" if "read" in row["Metric Name"] else "write"] = v * mult
+    n = len(per)
+    rd, wr, us = (sum(d[k] for d in per.values()) for k in ("read", "write", "us"))
+    rec = {"kernel": "tca_gemm_kernel", "launches": n, "dram_bytes_read": rd, "dram_bytes_written": wr,
+           "avg_dram_bytes_per_launch": (rd + wr) / n, "total_us": us, "command": cmd}
+    json.dump(rec, open(dst + ".json", "w"), indent=1)
+    with open(dst + ".md", "w") as f:
+        f.write(f"# DRAM traffic of `tca_gemm_kernel` over {n} consecutive launches of the bench step\n\n`{cmd}`\n\n")
+        f.write(f"{n} launches, {us:.1f} us of kernel time (serialised, cold cache), DRAM read {rd / 1e6:.1f} MB, written {wr / 1e6:.1f} MB "
+                f"-> {(rd + wr) / n / 1e6:.1f} MB per launch.\n\n")
+        f.write("| # | kernel | grid | us | DRAM read MB | DRAM write MB |\n|---:|---|---|---:|---:|---:|\n")
+        for i, d in per.items():
+            f.write(f"| {i} | `{d['kernel'][-22:]}` | {d['grid']} | {d['us']:.1f} | {d['read'] / 1e6:.2f} | {d['write'] / 1e6:.2f} |\n")
+    print("wrote", dst + ".md", dst + ".json")
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
     else:
         full(sys.argv[2], sys.argv[3])
