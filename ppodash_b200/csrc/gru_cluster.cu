@@ -28,6 +28,13 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// Gate non-linearities of the register kernels: the gate phase is one warp's dependent chain inside every recurrence step (all
+// other warps wait at the barrier), so its length is step latency.  ex2.approx (2^-22 relative) and rcp.approx (1 ulp) keep the
+// absolute error of both functions below 2e-7 -- under the fp32 rounding noise of the 512-term dot products feeding them.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - 2.f * rcp_approx(1.f + ex2_approx(2.8853900817779268f * x)); }
 
 // ---- DSMEM push with completion: st.async writes a value into a peer CTA's shared memory and
 // performs complete_tx on that CTA's mbarrier, so data and "it has arrived" travel together and the
@@ -396,9 +403,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(cons
         const size_t row = (size_t)t * E + env;
         if (gate_thread) {
             const float ghr = gh[tid] + bh_r, ghz = gh[kHU + tid] + bh_z, ghn = gh[2 * kHU + tid] + bh_n;
+#ifdef PPD_GRU_EXACT_GATES
             const float rg = sigmoidf_(gi_r + ghr);
             const float z = sigmoidf_(gi_z + ghz);
             const float n = tanhf(gi_n + rg * ghn);
+#else
+            const float rg = fast_sigmoid(gi_r + ghr);
+            const float z = fast_sigmoid(gi_z + ghz);
+            const float n = fast_tanh(gi_n + rg * ghn);
+#endif
             const float hm = hcur[hpad(ju)];
             const float hn = n + z * (hm - n);
             stage[tid] = hn * m_next;
