@@ -233,8 +233,8 @@ def run_b200(args, cfg):
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values()) + nv_host.numel() * 4
 
     def upload():
-        for k, t in host.items():
-            getattr(st, k).copy_(t, non_blocking=True)
+        # public API: small fields at once, observations per env on a copy stream in the order the first epoch consumes them
+        st.upload_from(host)
         nv_dev.copy_(nv_host, non_blocking=True)
 
     def step(with_upload):

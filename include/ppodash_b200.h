@@ -35,6 +35,11 @@ const char* ppd_last_error(void);
 /* Number of this library's kernels launched by the calling thread since the last reset. */
 int64_t ppd_launch_count(void);
 void ppd_reset_launch_count(void);
+/* Strided host->device upload on `stream`: `rows` rows of `row_bytes` bytes, source pitch `src_pitch`, destination pitch `dst_pitch`
+ * (cudaMemcpy2DAsync).  Used by RolloutStorage.upload_from to move ONE env's observations -- rows of a [T+1, N, ...] tensor, N rows
+ * apart -- from pinned host memory, so that the upload of a rollout can be ordered by the first epoch's env permutation and overlap
+ * the update (the reference's `rollouts.to(device)`, PKG/storage.py:34-46, is one blocking copy of everything). */
+int ppd_upload_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Returns / GAE                          replaces RolloutStorage.compute_returns, PKG/storage.py:82-121

@@ -64,6 +64,7 @@ _PROTOTYPES = {
     "ppd_last_error": (c_char_p, []),
     "ppd_launch_count": (c_int64, []),
     "ppd_reset_launch_count": (None, []),
+    "ppd_upload_rows": (c_int, [_P, c_size_t, _P, c_size_t, c_size_t, c_size_t, _P]),
     "ppd_compute_returns_workspace": (c_size_t, [c_int, c_int]),
     "ppd_compute_returns_set_tuning": (None, [c_int, c_int]),
     "ppd_compute_returns": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_double, c_double, c_int, c_int,

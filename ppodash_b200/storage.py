@@ -63,8 +63,86 @@ class RolloutStorage(object):
                "action_log_probs", "actions", "masks", "bad_masks")
 
     def to(self, device):
+        self.finish_upload()
         for name in self._FIELDS:
             setattr(self, name, getattr(self, name).to(device, non_blocking=True))
+
+    # ------------------------------------------------------------------ staged upload of a host rollout
+    def upload_from(self, host, staged=True):
+        """Fill this (device) storage from `host`: another RolloutStorage or a dict of CPU tensors with the same fields
+        (the job of the reference's `rollouts.to(device)`, storage.py:34-46, for a rollout collected on the host).
+
+        Every field but `obs` is a few MB and is copied at once on the current stream.  The observations -- 99 % of the
+        bytes -- are uploaded PER ENV on a copy stream when `host["obs"]` is pinned and `staged` is true: the copies are
+        queued when the first minibatch generator draws its env permutation, in that order, and a minibatch waits only for
+        the envs it gathers, so the upload overlaps compute_returns and the first epoch of `PPO.update` instead of
+        preceding them.  `finish_upload()` (called by everything else that touches `obs`) waits for all of it."""
+        self.finish_upload()
+        get = (lambda k: getattr(host, k)) if not isinstance(host, dict) else (lambda k: host[k])
+        dev = self.obs.device
+        if dev.type != "cuda":
+            raise _lib.PpdError("upload_from needs the storage on a CUDA device (rollouts.to(device))")
+        for k in self._FIELDS:
+            src = get(k)
+            if tuple(src.shape) != tuple(getattr(self, k).shape):
+                raise ValueError("upload_from: field {} has shape {}, expected {}".format(k, tuple(src.shape), tuple(getattr(self, k).shape)))
+        for k in self._FIELDS:
+            if k != "obs":
+                getattr(self, k).copy_(get(k), non_blocking=True)
+        obs = get("obs")
+        if staged and obs.device.type == "cpu" and obs.is_pinned() and obs.is_contiguous() and obs.dtype == self.obs.dtype \
+                and self.obs.is_contiguous():
+            self._pending = {"host": obs, "events": None}
+        else:
+            self.obs.copy_(obs, non_blocking=True)
+
+    def _issue_upload(self, order=None):
+        """Queue the per-env observation copies (env order `order`, default natural) on the copy stream; one event per env."""
+        p = getattr(self, "_pending", None)
+        if p is None or p["events"] is not None:
+            return
+        dev = self.obs.device
+        N = self.obs.size(1)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        cs.wait_stream(torch.cuda.current_stream(dev))          # earlier readers / writers of obs on the main stream
+        row = self.obs[0, 0].numel() * self.obs.element_size()
+        rows = self.obs.size(0)
+        order = list(range(N)) if order is None else [int(e) for e in order]
+        seen = set(order)
+        order += [e for e in range(N) if e not in seen]
+        events = [None] * N
+        for e in order:
+            check(lib().ppd_upload_rows(self.obs.data_ptr() + e * row, N * row, p["host"].data_ptr() + e * row, N * row,
+                                        row, rows, cs.cuda_stream), "upload_rows")
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            events[e] = ev
+        p["events"] = events
+
+    def _wait_envs(self, envs=None):
+        """Make the current stream wait for the uploads of `envs` (all when None)."""
+        p = getattr(self, "_pending", None)
+        if p is None:
+            return
+        if p["events"] is None:
+            self._issue_upload()
+        cur = torch.cuda.current_stream(self.obs.device)
+        left = False
+        for e, ev in enumerate(p["events"]):
+            if ev is None:
+                continue
+            if envs is None or e in envs:
+                cur.wait_event(ev)
+                p["events"][e] = None
+            else:
+                left = True
+        if not left:
+            self._pending = None
+
+    def finish_upload(self):
+        self._wait_envs(None)
 
     def half(self):
         # The reference's experimental --half_precision path (storage.py:48-58) also casts the int64
@@ -74,6 +152,7 @@ class RolloutStorage(object):
     def insert(self, obs, vector_obs, recurrent_hidden_states, actions, action_log_probs,
                value_preds, rewards, masks, bad_masks):
         s = self.step
+        self.finish_upload()
         self.obs[s + 1].copy_(obs, non_blocking=True)
         self.vector_obs[s + 1].copy_(vector_obs, non_blocking=True)
         self.recurrent_hidden_states[s + 1].copy_(recurrent_hidden_states, non_blocking=True)
@@ -86,6 +165,7 @@ class RolloutStorage(object):
         self.step = (self.step + 1) % self.num_steps
 
     def after_update(self):
+        self.finish_upload()
         self.obs[0].copy_(self.obs[-1])
         self.vector_obs[0].copy_(self.vector_obs[-1])
         self.recurrent_hidden_states[0].copy_(self.recurrent_hidden_states[-1])
@@ -180,6 +260,7 @@ class RolloutStorage(object):
         # with drop_last=True then cuts it into consecutive blocks (storage.py:138-142).
         perm = torch.randperm(batch_size)
         perm_dev = self._perm_to_device(perm, self.obs.device)
+        self.finish_upload()                                       # a feed-forward minibatch samples every env
         for k in range(batch_size // mini_batch_size):
             yield self._gather("ff", perm_dev, k * mini_batch_size, mini_batch_size, 0, advantages)
 
@@ -193,9 +274,14 @@ class RolloutStorage(object):
         perm = torch.randperm(num_processes)                       # storage.py:169
         perm_dev = self._perm_to_device(perm, self.obs.device)
         T = self.num_steps
+        pending = getattr(self, "_pending", None) is not None
+        if pending:
+            self._issue_upload(perm.tolist())                      # a staged upload follows this epoch's env order
         for start_ind in range(0, num_processes, num_envs_per_batch):
             if start_ind + num_envs_per_batch > num_processes:
                 # the reference runs off the end of `perm` here (storage.py:182)
                 raise IndexError("index {} is out of bounds for dimension 0 with size {}".format(
                     num_processes, num_processes))
+            if pending:
+                self._wait_envs(set(perm[start_ind:start_ind + num_envs_per_batch].tolist()))
             yield self._gather("rec", perm_dev, start_ind, T * num_envs_per_batch, num_envs_per_batch, advantages)

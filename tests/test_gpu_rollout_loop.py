@@ -82,3 +82,45 @@ def test_rollout_loop_sampling_is_consistent():
     agent = ppd.algo.PPO(pol, 0.1, 1, 2, 0.5, 0.001, lr=1e-4, eps=1e-5, max_grad_norm=0.5)
     out = agent.update(st)
     assert all(np.isfinite(x) for x in out)
+
+
+@pytest.mark.gpu
+def test_staged_upload_matches_direct_copy():
+    """RolloutStorage.upload_from with pinned observations (per-env copies on a copy stream, ordered by the first epoch's
+    permutation, minibatches waiting only for their envs) gives the same update as a plain copy of every field."""
+    from ppodash_b200 import algo, synthetic
+    from ppodash_b200.model import Policy
+    from ppodash_b200.storage import RolloutStorage
+
+    class Discrete:
+        def __init__(self, n):
+            self.n = n
+            self.shape = ()
+    cfg = synthetic.RolloutConfig("staged", 16, 8, 3, 15, 8, True, 2, 4, 1e-4, 0.001)
+    roll = synthetic.make_rollout(cfg, seed=3, reset_prob=0.05)
+    results = []
+    for staged in (False, True):
+        torch.manual_seed(0)
+        pol = Policy((3, 84, 84), Discrete(8), base_kwargs={"recurrent": True}, vector_obs_len=15).to("cuda:0")
+        st = RolloutStorage(cfg.num_steps, cfg.num_envs, (3, 84, 84), [15], Discrete(8), 512)
+        st.to("cuda:0")
+        host = {k: roll[k].clone().pin_memory() for k in RolloutStorage._FIELDS}
+        if staged:
+            st.upload_from(host)
+            assert getattr(st, "_pending", None) is not None
+        else:
+            for k in RolloutStorage._FIELDS:
+                getattr(st, k).copy_(host[k])
+        st.compute_returns(roll["next_value"].to("cuda:0"), True, cfg.gamma, cfg.gae_lambda, False)
+        agent = algo.PPO(pol, cfg.clip_param, cfg.ppo_epoch, cfg.num_mini_batch, cfg.value_loss_coef, cfg.entropy_coef,
+                         lr=cfg.lr, eps=cfg.eps, max_grad_norm=cfg.max_grad_norm)
+        torch.manual_seed(11)
+        out = agent.update(st)
+        assert getattr(st, "_pending", None) is None
+        torch.cuda.synchronize()
+        results.append((out, st.obs.clone(), {k: v.clone() for k, v in pol.state_dict().items()}))
+    assert results[0][0] == results[1][0]
+    assert torch.equal(results[0][1], results[1][1])
+    assert torch.equal(results[1][1].cpu(), roll["obs"])
+    for k in results[0][2]:
+        assert torch.equal(results[0][2][k], results[1][2][k]), k
