@@ -471,8 +471,18 @@ tc_splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t I
                         int relu, int accumulate, int transpose_out) {
     const int64_t n = I * J;
     for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
-        float v = 0.f;
-        for (int z = 0; z < splits; ++z) v += partial[(int64_t)z * n + e];
+        // four independent accumulators, eight loads in flight: the kernel is a latency chain over `splits` (dozens), not bandwidth;
+        // the order of the sum is fixed (deterministic), only its association differs from a serial sum
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* p = partial + e;
+        int z = 0;
+#pragma unroll 2
+        for (; z + 4 <= splits; z += 4) {
+            a0 += __ldg(p + (int64_t)z * n); a1 += __ldg(p + (int64_t)(z + 1) * n);
+            a2 += __ldg(p + (int64_t)(z + 2) * n); a3 += __ldg(p + (int64_t)(z + 3) * n);
+        }
+        for (; z < splits; ++z) a0 += __ldg(p + (int64_t)z * n);
+        float v = (a0 + a1) + (a2 + a3);
         const int64_t i = e / J, j = e - i * J;
         if (bias) v += __ldg(bias + j);
         if (relu) v = fmaxf(v, 0.f);
