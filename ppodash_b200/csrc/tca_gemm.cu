@@ -1342,9 +1342,10 @@ Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_avail, bool limit) {
         if (splits > nkb / 4) splits = nkb / 4;
         if (splits < 1) splits = 1;
     }
-    // tcgen05 accumulates with truncation: a chain of KK/8 x 3 accumulate steps loses ~1e-5 (relative) at KK ~ 1500.
-    // Where the output is small enough for the partials to be cheap, keep every chain at <= 24 k-blocks (768).
-    if (KK > 1024 && tiles <= 2 * kNumSMs && splits < (nkb + 23) / 24) splits = (nkb + 23) / 24;
+    // tcgen05 accumulates with truncation: with ONE accumulator a chain of KK/8 x 3 accumulate steps lost ~1.2e-5 (relative) at
+    // KK ~ 1500.  The main / correction accumulator pair sees a third of the steps per accumulator (4e-6 at KK = 1568, inside the
+    // 1e-5 gate), so chains are only cut beyond 64 k-blocks (2048), where the output is small enough for the partials to be cheap.
+    if (KK > 2048 && tiles <= 2 * kNumSMs && splits < (nkb + 63) / 64) splits = (nkb + 63) / 64;
     if (limit) {
         while (splits > 1 && (size_t)splits * I * J * sizeof(float) > ws_avail) --splits;
     }
