@@ -346,10 +346,10 @@ def run_b200(args, cfg):
         fwd = 2.0 * (819200 * C + 2654208 + 903168 + 802816 + ((3 * H * (H + V)) if rec else 0))
         tf = 3.0 * fwd * Bm * cfg.ppo_epoch * cfg.num_mini_batch / (top_ms * 1e-3) / 1e12
         try:        # DRAM bytes of the same kernel from the committed ncu pass (profiles/), scaled to the launches of one step
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1e_tca_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1f_tca_traffic.json")))
             roof["traffic"] = tr["avg_dram_bytes_per_launch"] * top_calls
             roof["traffic_note"] = (f"dram__bytes_read+write.sum averaged over {tr['launches']} consecutive launches (ncu, profiles/"
-                                    f"r1e_tca_traffic.md) x {top_calls} launches per step; algorithmic bytes per step {bytes_step:.4g}")
+                                    f"r1f_tca_traffic.md) x {top_calls} launches per step; algorithmic bytes per step {bytes_step:.4g}")
         except Exception:
             pass
         roof.update(bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"], tflops=tf,
