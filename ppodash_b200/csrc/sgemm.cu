@@ -222,7 +222,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t I, i
 //   tid % J, so loads are fully coalesced and the per-column fold happens once per block in shared memory;
 //   wide matrices: one thread per column over a slab of rows.
 constexpr int kColRows = 64;     // rows per partial block (wide path)
-constexpr int kNarrowElems = 256 * 64;   // elements per partial block (narrow path)
+constexpr int kNarrowElems = 256 * 256;  // elements per partial block (narrow path): few partials -- the final stage is a latency chain over them
 __global__ void __launch_bounds__(kThreads)
 colsum_partial_kernel(const float* __restrict__ X, int64_t ld, int64_t I, int64_t J, float* __restrict__ partial) {
     const int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -326,13 +326,18 @@ __global__ void __launch_bounds__(kThreads) colsum_multi_final_kernel(const Mult
     const int G = kThreads / cols;
     const int g = threadIdx.x / cols, c = threadIdx.x - g * cols;
     const float* partial = ws + m.part_off[s] + jb + c;
-    float s0 = 0.f, s1 = 0.f;
+    // four accumulators, eight loads in flight: the walk over the partials is a latency chain (L2 round trips), not bandwidth
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (g < G) {
         int64_t p = g;
-        for (; p + G < m.parts[s]; p += 2 * G) { s0 += partial[p * J]; s1 += partial[(p + G) * J]; }
-        if (p < m.parts[s]) s0 += partial[p * J];
+        const int64_t P = m.parts[s];
+#pragma unroll 2
+        for (; p + 3 * G < P; p += 4 * G) {
+            s0 += partial[p * J]; s1 += partial[(p + G) * J]; s2 += partial[(p + 2 * G) * J]; s3 += partial[(p + 3 * G) * J];
+        }
+        for (; p < P; p += G) s0 += partial[p * J];
     }
-    sm[threadIdx.x] = s0 + s1;
+    sm[threadIdx.x] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (g == 0) {
         float t = 0.f;
