@@ -42,6 +42,10 @@ def test_no_cpu_fallback():
         st.compute_returns(torch.zeros(2, 1), True, 0.99, 0.95, False)
     with pytest.raises(_lib.PpdError):
         next(st.feed_forward_generator(None, 2))
+    with pytest.raises(_lib.PpdError):                      # a staged upload targets device storage
+        st.upload_from({k: getattr(st, k) for k in RolloutStorage._FIELDS})
+    rc = _lib.lib().ppd_upload_rows(None, 0, None, 0, 0, 0, None)
+    assert rc == -1 and b"upload_rows" in _lib.lib().ppd_last_error()
 
 
 def test_bad_arguments_return_error_codes():
