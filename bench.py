@@ -417,13 +417,14 @@ def run_b200(args, cfg):
         g = mb.bench_gae(2048, 4096)
         line["gae_steps_per_sec"] = g["steps_per_s"]
         ks = [dict(kernel="returns_scan", config="4096 envs x 2048 steps", bound="hbm", achieved=g["gbs"], peak=pk["hbm"],
-                   unit="GB/s", frac=g["gbs"] / pk["hbm"], ms=g["ms"])]
+                   unit="GB/s", frac=g["gbs"] / pk["hbm"], ms=g["ms"], ms_single_flushed=g["ms_single_flushed"], timing=g["timing"])]
         gg = mb.bench_gather(512, 256, 3, 15, True, 8)
         ks.append(dict(kernel="gather_recurrent", config="256 envs x 512 steps, 3x84x84", bound="hbm", achieved=gg["gbs"],
                        peak=pk["hbm"], unit="GB/s", frac=gg["gbs"] / pk["hbm"], ms_epoch=gg["ms_epoch"]))
         ad = mb.bench_adam(pol.engine().n_params)
         ks.append(dict(kernel="clip_adam", config=f"{pol.engine().n_params} params", bound="hbm", achieved=ad["gbs"],
-                       peak=pk["hbm"], unit="GB/s", frac=ad["gbs"] / pk["hbm"], ms=ad["ms"]))
+                       peak=pk["hbm"], unit="GB/s", frac=ad["gbs"] / pk["hbm"], ms=ad["ms"], ms_single_flushed=ad["ms_single_flushed"],
+                       timing=ad["timing"]))
         line["kernels"] = ks
 
     if not args.no_cpu_baseline and world == 1 and not big:
