@@ -845,6 +845,9 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_wait(&full_b[sbs], rb.ph);
                     const uint32_t src = smemB_u + sbs * 2 * b_bytes;
                     const int nvec = (int)(b_bytes >> 4);
+#ifdef PPD_ABL_NOBSPLIT
+                    if (nvec < 0)
+#endif
                     for (int v = gt; v < nvec; v += 128) {
                         const float4 xb = lds128(src + (v << 4));
                         uint4 hb, rb;
