@@ -299,9 +299,14 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmBlo, const Args a) {
     constexpr int mode = MODE == 5 ? 3 : MODE;
     constexpr bool raw = MODE == 5;
+    // Weight gradients (modes 3 / 5) of the N = 32 layers: the activation B tile is split into [hi | lo] by the four EPILOGUE warps,
+    // which otherwise idle for the ~170-350 k-blocks of a work item; everywhere else a non-pre-split B is split by the transform warps.
+    constexpr bool epi_splits_b = (MODE == 3 || MODE == 5);
+    const bool esb = epi_splits_b && !a.b_presplit && a.bn <= 32;      // measured: -13 % for the N = 32 layers, +2 % at N = 64
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_a[kSA], empty_a[kSA], full_b[kMaxSB], empty_b[kMaxSB];
     __shared__ __align__(8) uint64_t ta_full[kTA], ta_empty[kTA], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t bs_full[kMaxSB];   // weight gradients: B stage split into [hi | lo] by the epilogue warps
     __shared__ uint32_t tmem_base_slot;
     __shared__ int tap_line[kMaxTaps];                  // modes 6 / 7: line offset of k-block kb inside the tile's stage
 
@@ -323,7 +328,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (threadIdx.x == 0) {
         // convolution stages are filled by TWO producer warps (each arms the barrier for its own boxes)
         for (int s = 0; s < kSA; ++s) { mbar_init(&full_a[s], mode ? kAProd : 1); mbar_init(&empty_a[s], (mode == 6 || mode == 7) ? kXformWarps : 4); }
-        for (int s = 0; s < kMaxSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < kMaxSB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); mbar_init(&bs_full[s], kEpiWarps); }
         for (int s = 0; s < kTA; ++s) { mbar_init(&ta_full[s], 4); mbar_init(&ta_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -663,6 +668,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const uint32_t ts = it % kTA, s = a.b_resident ? (uint32_t)kb : rb.s;
                 mbar_wait(&ta_full[ts], (it / kTA) & 1u);
                 if (a.b_presplit && reload) mbar_wait(&full_b[s], a.b_resident ? (epoch & 1u) : rb.ph);
+                if (esb) mbar_wait(&bs_full[s], rb.ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     TCA_TRACE1(it, 8);
@@ -840,7 +846,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tmem_st16(ta + 48u, lo + 16);
 #endif
                 if (q == 0) TCA_TRACE(it, 6);
-                if (!a.b_presplit) {
+                if (!a.b_presplit && !esb) {
                     const uint32_t sbs = rb.s;
                     mbar_wait(&full_b[sbs], rb.ph);
                     const uint32_t src = smemB_u + sbs * 2 * b_bytes;
@@ -875,9 +881,31 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ================= epilogue: warp w may touch TMEM lanes [32*(w%4), +32); result = main + correction accumulator
         const int q = warp & 3;
         uint32_t tile_it = 0;
+        Ring rbs;                                       // B ring position (weight gradients: these warps split the B stages)
+        const uint32_t smemB_e = smem_u32(smemB);
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
             const Item t = decode<MODE>(a, w);
             const uint32_t acc = tile_it & 1u;
+            if (esb) {
+                const int nvec = (int)(b_bytes >> 4);
+                for (int kb = 0; kb < t.nkb; ++kb, rbs.next(kSB)) {
+                    mbar_wait(&full_b[rbs.s], rbs.ph);
+                    const uint32_t src = smemB_e + rbs.s * 2 * b_bytes;
+                    for (int v = q * 32 + lane; v < nvec; v += 32 * kEpiWarps) {
+                        const float4 xb = lds128(src + (v << 4));
+                        uint4 hb, lb;
+                        split_a(xb.x, hb.x, lb.x);
+                        split_a(xb.y, hb.y, lb.y);
+                        split_a(xb.z, hb.z, lb.z);
+                        split_a(xb.w, hb.w, lb.w);
+                        sts128(src + (v << 4), hb);
+                        sts128(src + b_bytes + (v << 4), lb);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bs_full[rbs.s]);
+                }
+            }
             mbar_wait(&acc_full[acc], (tile_it >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t i = t.i0 + q * 32 + lane;
