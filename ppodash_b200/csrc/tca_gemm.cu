@@ -1178,16 +1178,19 @@ int conv_forward(const float* x, const ppd_conv_geom* g, int Cout, const float* 
     // Tile-resident raw input (mode 6) when two stages of it and a B ring fit: every input element goes through TMA once per tile
     if (g_conv_resident && g->C % 32 == 0) {
         const int planes = g->C / 32;
-        // two stages of the rows of a tile + a B ring of at least two stages must fit: a tile may give up to two of its output rows for that
+        // two stages of the rows of a tile + a B ring must fit (a smaller tile is not worth it: more tiles, each with all its k-blocks)
         int nseg = cv.nseg, max_runs = 0, nrows_max = 0;
         size_t stage = 0;
-        for (; nseg >= 1 && nseg >= cv.nseg - 2; --nseg) {
+        for (; nseg >= 1 && nseg >= cv.nseg; --nseg) {
             max_runs = 1 + (nseg - 1 + OH - 1) / OH;
             nrows_max = g->stride * nseg + (g->kh > g->stride ? (g->kh - g->stride) * max_runs : 0) + 1;
             stage = (((size_t)planes * nrows_max * g->W * 128) + 1023) & ~(size_t)1023;
-            if (2 * stage + 2 * (size_t)2 * Cout * BK * 4 + 1024 <= kSmemBudget) break;
+            // ... with room for a B ring of at least four stages (or all k-blocks): with the two left over for the 4x4x32 -> 64
+            // layer the weight loads sit on the critical path and the per-k-block boxes of mode 1 are faster (76 vs 82 us, same-box A/B)
+            const size_t b_stages_wanted = cv.nkb < 4 ? cv.nkb : 4;
+            if (2 * stage + b_stages_wanted * (size_t)2 * Cout * BK * 4 + 1024 <= kSmemBudget) break;
         }
-        if (cv.nkb <= kMaxTaps && nseg >= 1 && nseg >= cv.nseg - 2) {
+        if (cv.nkb <= kMaxTaps && nseg >= 1 && nseg >= cv.nseg) {
             cv.nseg = nseg;
             cv.ntile_class = (cv.nseg_class + cv.nseg - 1) / cv.nseg;
             a.total_items = cv.ntile_class;
