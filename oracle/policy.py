@@ -65,13 +65,22 @@ def init_params(num_inputs, num_actions, vector_obs_len=0, recurrent=False, hidd
     return p
 
 
-def trunk(p, visual):
-    """conv-relu x3, flatten (NCHW order), linear-relu  (model.py:176-180,194; no /255)."""
-    x = F.relu(F.conv2d(visual, p["base.main.0.weight"], p["base.main.0.bias"], stride=4))
-    x = F.relu(F.conv2d(x, p["base.main.2.weight"], p["base.main.2.bias"], stride=2))
-    x = F.relu(F.conv2d(x, p["base.main.4.weight"], p["base.main.4.bias"], stride=1))
+def trunk(p, visual, relu_masks=None, pre_out=None):
+    """conv-relu x3, flatten (NCHW order), linear-relu  (model.py:176-180,194; no /255).
+
+    Test instruments (never used by the reference path): ``relu_masks`` -- a list of four 0/1 tensors (NCHW for the three
+    convolutions, [B,H] for the FC layer) that REPLACE the sign test of each ReLU (x * mask instead of relu(x)); the parity tests
+    pass the masks the CUDA path used, to show that its gradient outliers come only from units whose pre-activation sits at
+    rounding distance from zero.  ``pre_out`` -- a list that receives the four pre-activations."""
+    def act(x, i):
+        if pre_out is not None:
+            pre_out.append(x.detach())
+        return F.relu(x) if relu_masks is None else x * relu_masks[i]
+    x = act(F.conv2d(visual, p["base.main.0.weight"], p["base.main.0.bias"], stride=4), 0)
+    x = act(F.conv2d(x, p["base.main.2.weight"], p["base.main.2.bias"], stride=2), 1)
+    x = act(F.conv2d(x, p["base.main.4.weight"], p["base.main.4.bias"], stride=1), 2)
     x = x.reshape(x.shape[0], -1)
-    return F.relu(F.linear(x, p["base.main.7.weight"], p["base.main.7.bias"]))
+    return act(F.linear(x, p["base.main.7.weight"], p["base.main.7.bias"]), 3)
 
 
 def _gru_run(p, x_seq, h):
@@ -103,9 +112,9 @@ def gru_with_resets(p, x, hxs, masks):
     return torch.cat(outs, 0).reshape(T * E, -1), h
 
 
-def base_forward(p, visual, vector, hxs, masks, recurrent, concat_vector=True):
+def base_forward(p, visual, vector, hxs, masks, recurrent, concat_vector=True, relu_masks=None, pre_out=None):
     """(value [B,1], features [B,F], hxs) -- CNNBase.forward, model.py:192-199."""
-    x = trunk(p, visual)
+    x = trunk(p, visual, relu_masks, pre_out)
     if concat_vector:
         x = torch.cat((x, vector), dim=1)
     if recurrent:
@@ -119,9 +128,9 @@ def categorical(p, feats):
     return torch.distributions.Categorical(logits=logits)
 
 
-def evaluate_actions(p, visual, vector, hxs, masks, action, recurrent, concat_vector=True):
+def evaluate_actions(p, visual, vector, hxs, masks, action, recurrent, concat_vector=True, relu_masks=None, pre_out=None):
     """model.py:72-79 -> (value [B,1], log_prob [B,1], mean entropy, hxs)."""
-    value, feats, hxs = base_forward(p, visual, vector, hxs, masks, recurrent, concat_vector)
+    value, feats, hxs = base_forward(p, visual, vector, hxs, masks, recurrent, concat_vector, relu_masks, pre_out)
     d = categorical(p, feats)
     logp = d.log_prob(action.squeeze(-1)).reshape(action.shape[0], -1).sum(-1).unsqueeze(-1)
     return value, logp, d.entropy().mean(), hxs

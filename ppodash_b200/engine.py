@@ -256,6 +256,31 @@ class PolicyEngine:
             torch.cuda.current_stream(self.device).wait_event(ev)
 
     # ------------------------------------------------------------------ scratch
+    class _Scratch:
+        """Context manager: route `buf()` to a caller-owned dict.  A captured CUDA graph bakes the addresses of its scratch
+        buffers in; giving the capture (and nothing else) its own dict keeps those buffers alive and un-shared for as long as
+        the owner holds the dict, whatever sizes later eager / training calls ask the engine's own grow-only pool for."""
+
+        def __init__(self, eng, bufs):
+            self.eng, self.bufs = eng, bufs
+
+        def __enter__(self):
+            self.saved, self.eng._buffers = self.eng._buffers, self.bufs
+            return self
+
+        def __exit__(self, *exc):
+            self.eng._buffers = self.saved
+            return False
+
+    def scratch(self, bufs):
+        return self._Scratch(self, bufs)
+
+    def signature(self):
+        """Everything a captured forward pass depends on besides its inputs: the flat parameter buffers (re-created by bind()
+        after .to() / load), their TF32 hi / lo copies and the precision mode."""
+        self.bind()
+        return (self.flat.data_ptr(), self.flat_hi.data_ptr(), self.flat_lo.data_ptr(), self.precision, str(self.device))
+
     def buf(self, name, *shape, dtype=torch.float32):
         n = 1
         for d in shape:

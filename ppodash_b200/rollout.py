@@ -47,6 +47,8 @@ class RolloutLoop:
                         h=torch.zeros_like(rollouts.recurrent_hidden_states[0]), m=torch.ones_like(rollouts.masks[0]))
         self._out = None
         self._graph = None
+        self._sig = None
+        self._bufs = {}               # scratch of the captured forward pass: owned here, never shared with eager / training calls
         # pinned staging
         pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory()
         self._h_obs = pin(*rollouts.obs.shape[1:])
@@ -60,10 +62,16 @@ class RolloutLoop:
     # ------------------------------------------------------------------ act
     def _forward(self):
         i = self._in
-        with torch.no_grad():
+        with torch.no_grad(), self.policy.engine().scratch(self._bufs):
             return self.policy.act(i["obs"], i["vobs"], i["h"], i["m"], deterministic=self.deterministic)
 
     def _capture(self):
+        # The graph bakes in device addresses: its scratch buffers live in self._bufs (PolicyEngine.scratch), so PPO.update or an
+        # eager act() at another batch size cannot free or reuse them, and `_sig` records what else it depends on (flat parameter
+        # buffers, precision); act() re-captures when that changes (engine.bind() after .to() / load_state_dict on a new module).
+        self._graph, self._out = None, None
+        self._bufs.clear()
+        self._sig = self.policy.engine().signature()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):                          # warm-up: workspaces, lazy binds, tensor maps
@@ -84,7 +92,7 @@ class RolloutLoop:
         i["obs"].copy_(r.obs[s]); i["vobs"].copy_(r.vector_obs[s])
         i["h"].copy_(r.recurrent_hidden_states[s]); i["m"].copy_(r.masks[s])
         if self.use_cuda_graph:
-            if self._graph is None:
+            if self._graph is None or self._sig != self.policy.engine().signature():
                 self._capture()
             self._graph.replay()
             out = self._out

@@ -1,0 +1,335 @@
+"""GPU parity at PRODUCTION size (BASELINE.json configs C1-C4), through the C ABI, against the oracle.
+
+The other GPU test files check every kernel on shapes the CPU oracle finishes instantly; this file repeats the
+checks at the sizes the bench actually runs:
+
+  * one full C2 minibatch -- 2048 rows = 512 steps x 4 envs, H = 512, reference initialisation -- losses, values,
+    rnn_hxs and EVERY gradient tensor against oracle autograd, in `fp32` and `tf32x3`, elementwise to 1e-5 of the
+    tensor's scale, with the ReLU decisions of the CUDA path forced on the oracle and every flipped unit shown to sit at
+    rounding distance from zero;
+  * the three convolutions (forward / input gradient / weight gradient) at B = 2048 against float64;
+  * the GRU pair at T = 512 for E = 4 (C2) and E = 128 (C5);
+  * compute_returns at 4096 envs x 2048 steps (C4) directly against the numpy oracle;
+  * one minibatch and one full PPO.update of C1, C3 and C3-12ch (feed-forward, A = 8 / 54 / 54) against the oracle.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import policy as o_pol  # noqa: E402
+from oracle import ppo_update as o_upd  # noqa: E402
+from oracle import returns as o_ret  # noqa: E402
+import ppodash_b200 as ppd  # noqa: E402
+from ppodash_b200 import _lib, synthetic  # noqa: E402
+from ppodash_b200._lib import ConvGeom  # noqa: E402
+
+DEV = "cuda:0"
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = n
+        self.shape = ()
+
+
+# --------------------------------------------------------------------------- C2: one full minibatch, every gradient
+def _gpu_relu_masks(eng, B, H):
+    """0/1 masks of the four ReLUs as the CUDA path decided them, in the oracle's layouts (NCHW; [B,H])."""
+    b = eng._buffers
+    s1, s2, s3 = eng.sp
+    a1 = b["a1"][:B * s1 * s1 * 32].view(B, s1, s1, 32).permute(0, 3, 1, 2)
+    a2 = b["a2"][:B * s2 * s2 * 64].view(B, s2, s2, 64).permute(0, 3, 1, 2)
+    a3 = b["a3t"][:B * eng.flat_dim].view(B, 32, s3, s3)
+    if eng.recurrent:
+        fc = b["t_xcat"][:B * eng.Ipad].view(B, eng.Ipad)[:, :H]
+    else:
+        fc = b["t_feat"][:B * H].view(B, H)
+    return [(t > 0).float().cpu().contiguous() for t in (a1, a2, a3, fc)]
+
+
+def _compare_minibatch(pol, p_cpu, sample_cpu, recurrent, clip, vcoef, ecoef, precision, concat_vector):
+    """Runs one train_minibatch on the GPU and the oracle twice on the CPU (natural ReLUs; ReLU decisions forced to the GPU's).
+    Stated tolerances (fp32 and tf32x3 alike): outputs and losses 1e-5 relative (+ 1e-5 of the output scale near zero);
+    gradients elementwise |got - ref| <= 1e-4 |ref| + 1e-5 max|ref| against the forced-mask oracle, no outlier allowance."""
+    eng = pol.engine(precision)
+    obs, vobs, h0, actions, old_v, ret, masks, old_logp, adv = sample_cpu
+    dd = lambda t: t.to(DEV)
+    out = eng.train_minibatch(tuple(dd(t) for t in sample_cpu), clip, vcoef, ecoef)
+    torch.cuda.synchronize()
+    B = obs.shape[0]
+    gmasks = _gpu_relu_masks(eng, B, eng.H)
+
+    def run_oracle(relu_masks, pre_out):
+        pr = {k: v.clone().requires_grad_(True) for k, v in p_cpu.items()}
+        v, lp, ent, hx = o_pol.evaluate_actions(pr, obs, vobs, h0, masks, actions, recurrent, concat_vector,
+                                                relu_masks=relu_masks, pre_out=pre_out)
+        vl, al = o_upd.ppo_losses(v, lp, ent, old_v, ret, old_logp, adv, clip)
+        (vl * vcoef + al - ent * ecoef).backward()
+        return pr, v.detach(), hx.detach(), (vl.item(), al.item(), ent.item())
+
+    pre = []
+    _, v_nat, hx_nat, loss_nat = run_oracle(None, pre)
+    # --- the flipped units sit at rounding distance from zero
+    flips = 0
+    for name, p_, gm in zip(("conv1", "conv2", "conv3", "fc"), pre, gmasks):
+        nat = (p_ > 0).float()
+        diff = nat != gm
+        n = int(diff.sum())
+        flips += n
+        if n:
+            worst = float(p_[diff].abs().max())
+            assert worst <= 1e-5 * float(p_.abs().max()), (name, n, worst)
+    # --- outputs against the natural oracle
+    vs = float(v_nat.abs().max())
+    np.testing.assert_allclose(out["value"].cpu().numpy(), v_nat.numpy(), rtol=1e-5, atol=1e-5 * vs)
+    if recurrent:
+        np.testing.assert_allclose(out["rnn_hxs"].cpu().numpy(), hx_nat.numpy(), rtol=1e-5, atol=1e-5)
+    loss = eng.flat_grad[eng.loss_off:eng.loss_off + 3].cpu().numpy()
+    np.testing.assert_allclose(loss, loss_nat, rtol=1e-5, atol=1e-7)
+    # --- every gradient tensor against the oracle that takes the same ReLU decisions
+    pr, _, _, loss_forced = run_oracle(gmasks, None)
+    np.testing.assert_allclose(loss, loss_forced, rtol=1e-5, atol=1e-7)
+    worst = {}
+    for name, p in pol.named_parameters():
+        ref = pr[name].grad.numpy()
+        got = p.grad.cpu().numpy()
+        scale = max(1e-12, float(np.abs(ref).max()))
+        worst[name] = float(np.abs(got - ref).max()) / scale
+        np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5 * scale, err_msg=f"{name} ({precision}, {flips} ReLU flips)")
+    return flips, worst
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_c2_full_minibatch_every_gradient_vs_oracle(precision):
+    """BASELINE config 2 minibatch: T = 512 steps x E = 4 envs = 2048 rows, C = 3, V = 15, A = 8, H = 512 (PKG/algo/ppo.py:57-81)."""
+    T, E = 512, 4
+    torch.manual_seed(0)
+    pol = ppd.Policy((3, 84, 84), Discrete(8), base_kwargs={"recurrent": True}, vector_obs_len=15)
+    p_cpu = {k: v.clone() for k, v in pol.state_dict().items()}
+    pol = pol.to(DEV)
+    cfg = synthetic.RolloutConfig("c2mb", T, E, 3, 15, 8, True, 1, 1, 1e-4, 0.001)
+    roll = synthetic.make_rollout(cfg, seed=21)                     # ~1/500 resets per (step, env), as in the bench
+    B = T * E
+    obs = roll["obs"][:T].reshape(B, 3, 84, 84)
+    vobs = roll["vector_obs"][:T].reshape(B, 15)
+    h0 = roll["recurrent_hidden_states"][0]
+    masks = roll["masks"][:T].reshape(B, 1)
+    actions = roll["actions"].reshape(B, 1)
+    gen = torch.Generator().manual_seed(5)
+    old_v = 0.1 * torch.randn(B, 1, generator=gen)
+    ret = 0.3 * torch.randn(B, 1, generator=gen)
+    adv = torch.randn(B, 1, generator=gen)
+    with torch.no_grad():
+        _, lp0, _, _ = o_pol.evaluate_actions(p_cpu, obs, vobs, h0, masks, actions, True, True)
+    old_logp = lp0 + 0.05 * torch.randn(B, 1, generator=gen)
+    flips, worst = _compare_minibatch(pol, p_cpu, (obs, vobs, h0, actions, old_v, ret, masks, old_logp, adv), True,
+                                      0.1, 0.5, 0.001, precision, True)
+    print(f"c2 minibatch {precision}: {flips} ReLU flips at rounding distance; worst gradient error / scale per tensor: "
+          + ", ".join(f"{k} {v:.1e}" for k, v in worst.items()))
+
+
+# --------------------------------------------------------------------------- C1 / C3 / C3-12ch
+FF_CONFIGS = ["c1", "c3", "c3_12"]
+
+
+def _ff_policy(cfg):
+    torch.manual_seed(0)
+    pol = ppd.Policy((cfg.channels, 84, 84), Discrete(cfg.num_actions), base_kwargs={"recurrent": False})
+    p_cpu = {k: v.clone() for k, v in pol.state_dict().items()}
+    return pol.to(DEV), p_cpu
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("name", FF_CONFIGS)
+def test_feed_forward_config_minibatch_vs_oracle(name, precision):
+    """One minibatch at the config's own shape: C1 256 rows (C = 1, A = 8), C3 1024 rows (C = 4, A = 54), C3-12ch (C = 12)."""
+    cfg = synthetic.CONFIGS[name]
+    pol, p_cpu = _ff_policy(cfg)
+    B = cfg.num_steps * cfg.num_envs // cfg.num_mini_batch
+    gen = torch.Generator().manual_seed(17)
+    obs = torch.randn(B, cfg.channels, 84, 84, generator=gen)
+    vobs = torch.zeros(B, 0)
+    h0 = torch.zeros(B, 1)
+    masks = torch.ones(B, 1)
+    actions = torch.randint(0, cfg.num_actions, (B, 1), generator=gen)
+    old_v = 0.1 * torch.randn(B, 1, generator=gen)
+    ret = 0.3 * torch.randn(B, 1, generator=gen)
+    adv = torch.randn(B, 1, generator=gen)
+    with torch.no_grad():
+        _, lp0, _, _ = o_pol.evaluate_actions(p_cpu, obs, vobs, h0, masks, actions, False, False)
+    old_logp = lp0 + 0.05 * torch.randn(B, 1, generator=gen)
+    flips, worst = _compare_minibatch(pol, p_cpu, (obs, vobs, h0, actions, old_v, ret, masks, old_logp, adv), False,
+                                      cfg.clip_param, cfg.value_loss_coef, cfg.entropy_coef, precision, False)
+    print(f"{name} minibatch {precision}: {flips} ReLU flips; worst: " + ", ".join(f"{k} {v:.1e}" for k, v in worst.items()))
+
+
+@pytest.mark.parametrize("name", FF_CONFIGS)
+def test_feed_forward_config_full_update_vs_oracle(name):
+    """compute_returns + one full PPO.update (4 epochs x 4 minibatches, feed_forward_generator with the reference's randperm
+    stream) at the config's own size against the oracle: returns, losses, first-minibatch gradients, final parameters."""
+    cfg = synthetic.CONFIGS[name]
+    pol, p_cpu = _ff_policy(cfg)
+    roll = synthetic.make_rollout(cfg, seed=1234)
+    st = ppd.RolloutStorage(cfg.num_steps, cfg.num_envs, (cfg.channels, 84, 84), [0], Discrete(cfg.num_actions), 1)
+    for k in ppd.RolloutStorage._FIELDS:
+        getattr(st, k).copy_(roll[k])
+    st.to(DEV)
+    st.compute_returns(roll["next_value"].to(DEV), True, cfg.gamma, cfg.gae_lambda, False)
+    want_ret, want_v = o_ret.returns_recurrence(roll["rewards"].numpy(), roll["value_preds"].numpy(), roll["masks"].numpy(),
+                                                roll["bad_masks"].numpy(), roll["next_value"].numpy(), True, cfg.gamma,
+                                                cfg.gae_lambda, False)
+    np.testing.assert_allclose(st.returns.cpu().numpy()[:-1], want_ret[:-1], rtol=1e-5, atol=1e-5)
+    agent = ppd.algo.PPO(pol, cfg.clip_param, cfg.ppo_epoch, cfg.num_mini_batch, cfg.value_loss_coef, cfg.entropy_coef,
+                         lr=cfg.lr, eps=cfg.eps, max_grad_norm=cfg.max_grad_norm)
+    first = {}
+    step0 = agent.optimizer.step
+
+    def spy(*a, **kw):
+        if not first:
+            first.update({n: p.grad.clone() for n, p in pol.named_parameters()})
+        return step0(*a, **kw)
+    agent.optimizer.step = spy
+    torch.manual_seed(11)
+    got = agent.update(st)
+
+    cpu_roll = dict(roll)
+    cpu_roll["returns"] = torch.from_numpy(want_ret)
+    cpu_roll["value_preds"] = torch.from_numpy(want_v)
+    state = o_upd.UpdateState(p_cpu, lr=cfg.lr, eps=cfg.eps)
+    ref_first = {}
+
+    def on_mb(k, info):
+        if k == 0:
+            coef = min(1.0, cfg.max_grad_norm / (info["grad_norm"] + 1e-6))     # the oracle reports gradients after clipping
+            ref_first.update({n: g / coef for n, g in info["grads"].items()})
+    torch.manual_seed(11)
+    want = o_upd.ppo_update(state, cpu_roll, recurrent=False, clip_param=cfg.clip_param, ppo_epoch=cfg.ppo_epoch,
+                            num_mini_batch=cfg.num_mini_batch, value_loss_coef=cfg.value_loss_coef,
+                            entropy_coef=cfg.entropy_coef, max_grad_norm=cfg.max_grad_norm, concat_vector=False,
+                            on_minibatch=on_mb)
+    np.testing.assert_allclose(np.array(got), np.array(want), rtol=1e-4, atol=1e-6)
+    for n, g in first.items():
+        ref = ref_first[n].numpy()
+        scale = max(1e-12, float(np.abs(ref).max()))
+        err = np.abs(g.cpu().numpy() - ref)
+        # natural ReLUs on both sides here (the forced-mask comparison is the minibatch test above): a unit that flips moves its
+        # fan-in by O(1/rows), so >= 99 % of the entries meet the 1e-5 gate and nothing is off by more than 5e-4 of the scale
+        ok = err <= 1e-4 * np.abs(ref) + 1e-5 * scale
+        assert ok.mean() >= 0.99 and float(err.max()) <= 5e-4 * scale, (n, float(ok.mean()), float(err.max()) / scale)
+    # parameters after 16 Adam steps: Adam's lr * m / (sqrt(v) + eps) turns a 1e-6 gradient difference on an entry whose gradient
+    # is ~eps into a visible fraction of lr, so: >= 98 % of every tensor within 5 % of ONE step, nothing further than one step
+    for k, v in pol.state_dict().items():
+        err = np.abs(v.cpu().numpy() - state.params[k].detach().numpy())
+        assert (err <= 0.05 * cfg.lr).mean() >= 0.98 and err.max() <= 1.0 * cfg.lr, (k, float((err <= 0.05 * cfg.lr).mean()), float(err.max()))
+
+
+# --------------------------------------------------------------------------- convolutions at B = 2048
+def _split(w):
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _lib.check(_lib.lib().ppd_split_tf32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), _lib.stream_ptr()))
+    return hi, lo
+
+
+LAYERS = [  # B, H, C, k, s, Cout, nchw
+    pytest.param(2048, 84, 3, 8, 4, 32, 1, id="conv1_c2_B2048"),
+    pytest.param(1024, 84, 4, 8, 4, 32, 1, id="conv1_c3_B1024"),
+    pytest.param(1024, 84, 12, 8, 4, 32, 1, id="conv1_c3_12ch_B1024"),
+    pytest.param(256, 84, 1, 8, 4, 32, 1, id="conv1_c1_B256"),
+    pytest.param(2048, 20, 32, 4, 2, 64, 0, id="conv2_B2048"),
+    pytest.param(2048, 9, 64, 3, 1, 32, 0, id="conv3_B2048"),
+]
+
+
+@pytest.mark.parametrize("B,H,C,k,s,Cout,nchw", LAYERS)
+def test_convolutions_at_minibatch_size_vs_float64(B, H, C, k, s, Cout, nchw):
+    """Forward, input gradient (NHWC layers) and weight gradient of PKG/model.py:176-178 at the minibatch sizes of the configs
+    (weight gradient of conv1 at B = 2048: an 819 200-pixel contraction with split-K partials) against float64 torch ops.
+    Stated tolerance: 1e-5 of the result's scale (weight gradients 2e-5), as in the small-shape tests."""
+    L = _lib.lib()
+    g0 = torch.Generator(device=DEV).manual_seed(B + H + C)
+    OH = (H - k) // s + 1
+    x = torch.randn(B, C, H, H, generator=g0, device=DEV)                         # NCHW reference layout
+    w = torch.randn(Cout, C, k, k, generator=g0, device=DEV) / np.sqrt(C * k * k)
+    b = torch.randn(Cout, generator=g0, device=DEV)
+    dy = torch.randn(B, OH, OH, Cout, generator=g0, device=DEV) / np.sqrt(B * OH * OH)
+    x64, w64 = x.double(), w.double()
+    geom = ConvGeom(B, H, H, C, k, k, s)
+    # ---- forward
+    want = torch.relu(F.conv2d(x64, w64, b.double(), stride=s)).permute(0, 2, 3, 1)
+    out = torch.full((B * OH * OH + 3, Cout), -7.0, device=DEV)
+    if nchw:
+        hi, lo = _split(w.contiguous())
+        _lib.check(L.ppd_conv_fwd_nchw(x.data_ptr(), ctypes.byref(geom), Cout, hi.data_ptr(), lo.data_ptr(), b.data_ptr(), 1,
+                                       out.data_ptr(), _lib.stream_ptr()))
+        xk = x
+        wk = w
+    else:
+        xk = x.permute(0, 2, 3, 1).contiguous()
+        wk = w.permute(0, 2, 3, 1).contiguous()                                    # (o, ky, kx, c)
+        hi, lo = _split(wk)
+        _lib.check(L.ppd_conv_fwd_nhwc(xk.data_ptr(), ctypes.byref(geom), Cout, hi.data_ptr(), lo.data_ptr(), b.data_ptr(), 1,
+                                       out.data_ptr(), _lib.stream_ptr()))
+    got = out[:B * OH * OH].view(B, OH, OH, Cout).double()
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    assert torch.all(out[B * OH * OH:] == -7.0)
+    # ---- weight gradient (accumulating and overwriting)
+    dy_nchw = dy.permute(0, 3, 1, 2).double().contiguous()
+    dw = torch.nn.grad.conv2d_weight(x64, w.shape, dy_nchw, stride=s)              # [Cout, C, k, k]
+    if not nchw:
+        dw = dw.permute(0, 2, 3, 1)
+    dw = dw.reshape(Cout, -1)
+    dW0 = torch.randn(Cout, C * k * k, generator=g0, device=DEV)
+    ws = _lib.workspace(L.ppd_conv_wgrad_workspace(ctypes.byref(geom), Cout), DEV, "wgrad_test")
+    for acc in (0, 1):
+        dW = dW0.clone()
+        _lib.check(L.ppd_conv_wgrad(xk.data_ptr(), ctypes.byref(geom), nchw, dy.data_ptr(), Cout, dW.data_ptr(), acc,
+                                    ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        wantw = dw + (dW0.double() if acc else 0)
+        assert float((dW.double() - wantw).abs().max()) <= 2e-5 * float(dw.abs().max())
+    # ---- input gradient (the NHWC layers; conv1 needs none)
+    if not nchw:
+        act = torch.randn(B, H, H, C, generator=g0, device=DEV)
+        full = F.conv_transpose2d(dy_nchw, w64, stride=s)
+        wantx = torch.zeros(B, C, H, H, dtype=torch.float64, device=DEV)
+        wantx[:, :, :full.shape[2], :full.shape[3]] = full
+        wantx = wantx.permute(0, 2, 3, 1) * (act > 0)
+        dx = torch.full((B, H, H, C), 9.0, device=DEV)
+        _lib.check(L.ppd_conv_dgrad_nhwc(dy.data_ptr(), ctypes.byref(geom), Cout, hi.data_ptr(), lo.data_ptr(), act.data_ptr(),
+                                         dx.data_ptr(), _lib.stream_ptr()))
+        assert float((dx.double() - wantx).abs().max()) <= 1e-5 * float(wantx.abs().max())
+
+
+# --------------------------------------------------------------------------- GRU at T = 512
+@pytest.mark.parametrize("T,E", [(512, 4), (512, 128)])
+def test_gru_pair_at_rollout_length(T, E):
+    """PKG/model.py:111-166 over the full rollout length: E = 4 (C2 minibatch) and E = 128 (C5 minibatch), H = 512, I = 527,
+    20 % resets per (step, env); same tolerances as the short-sequence cases."""
+    from test_gpu_network_kernels import _gru_case
+    _gru_case(T, E, 512, 527)
+
+
+# --------------------------------------------------------------------------- C4 returns, directly against the oracle
+@pytest.mark.parametrize("use_gae,proper", [(True, False), (True, True)])
+def test_returns_c4_full_size_vs_oracle(use_gae, proper):
+    """BASELINE config 4: 4096 envs x 2048 steps, every element against oracle.returns (PKG/storage.py:89-116).
+    Stated tolerance: rtol 1e-5, atol 1e-5 (128-step chunks are combined affinely, i.e. re-associated)."""
+    T, N = 2048, 4096
+    gen = torch.Generator().manual_seed(40)
+    f = synthetic.scalar_fields(gen, T, N, 8, reset_prob=1.0 / 500, bad_prob=0.005 if proper else 0.0)
+    want, want_v = o_ret.returns_recurrence(f["rewards"].numpy(), f["value_preds"].numpy(), f["masks"].numpy(),
+                                            f["bad_masks"].numpy(), f["next_value"].numpy(), use_gae, 0.99, 0.95, proper)
+    L = _lib.lib()
+    d = {k: f[k].to(DEV).contiguous() for k in ("rewards", "value_preds", "masks", "bad_masks", "next_value")}
+    ret = torch.zeros(T + 1, N, 1, device=DEV)
+    w = _lib.workspace(L.ppd_compute_returns_workspace(T, N), DEV, "returns", zero=True)
+    for _ in range(2):            # twice: the look-back workspace re-arms itself between launches
+        _lib.check(L.ppd_compute_returns(d["rewards"].data_ptr(), d["value_preds"].data_ptr(), d["masks"].data_ptr(),
+                                         d["bad_masks"].data_ptr(), ret.data_ptr(), d["next_value"].data_ptr(), T, N,
+                                         0.99, 0.95, int(use_gae), int(proper), w.data_ptr(), w.numel(), _lib.stream_ptr()))
+    np.testing.assert_allclose(ret.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    assert np.array_equal(d["value_preds"].cpu().numpy(), want_v)
