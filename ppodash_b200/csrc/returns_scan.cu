@@ -385,6 +385,8 @@ returns_scan_tma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_co
         }
         sP[w][lane] = P;
         sQ[w][lane] = Q;
+        // generic-proxy reads of the stage above, async-proxy (TMA) refill below: write-after-read across proxies needs this fence
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();       // every warp has copied its rows out of the stage; sP/sQ/lP/lQ are complete
         if (threadIdx.x == 0) issue(k + S);                // refill this ring slot
         if (w == 0 && seg + 1 < nseg) {

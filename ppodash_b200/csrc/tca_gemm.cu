@@ -826,6 +826,11 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #else
                 for (int c = 0; c < 32; ++c) split_a(x[c], hi[c], lo[c]);
 #endif
+                // The stage was read through the generic proxy (ld.shared) and will be re-written through the async proxy (TMA / bulk
+                // copy): that write-after-read needs a proxy fence before the release.  Without it the 1-D bulk copies of the NCHW
+                // forward overtook in-flight reads once a CTA re-used a stage (second tile onwards): ~1e-3 of the tiles of a
+                // 2048-sample conv1 came out wrong, non-deterministically (found by tests/test_gpu_production_size.py).
+                if (!resident) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // (resident stages: once per tile, below)
                 __syncwarp();
                 if (lane == 0 && !resident) mbar_arrive(&empty_a[s]);          // the tile is in registers: slot back to the producer
                 if (q == 0) TCA_TRACE(it, 4);
@@ -873,6 +878,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (q == 0) TCA_TRACE(it, 7);
             }
             if (resident) {                            // every read of this warp from the tile's stage is done
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic reads before the async-proxy refill
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_a[tile_it & 1u]);
             }
@@ -1303,6 +1309,15 @@ static void wgrad_plan(const ppd_conv_geom* g, int Cout, int nchw, ConvA& cv, in
     splits = kNumSMs / num_m;
     if (splits > cv.total_kb / 8) splits = cv.total_kb / 8;
     if (splits < 1) splits = 1;
+    // tcgen05 accumulates with truncation, so the error of an accumulator grows with the length of its chain: a 2048-sample
+    // conv1 (819 200 pixels = 25 600 k-blocks over 74 splits = 346 k-blocks per chain) was 2.7e-5 of the gradient's scale off on
+    // random-sign data (gate 2e-5; 4e-5 at C = 12).  Chains are cut at kMaxChainKb k-blocks: whole multiples of the one-wave split count,
+    // so that the SMs stay evenly loaded; the extra partial tiles are a few MB.
+    {
+        const int chain = (cv.total_kb + splits - 1) / splits;
+        const int k = (chain + kMaxChainKb - 1) / kMaxChainKb;
+        if (k > 1) splits *= k;
+    }
     cv.kbps = (cv.total_kb + splits - 1) / splits;
     splits = (cv.total_kb + cv.kbps - 1) / cv.kbps;
     (void)Cout;

@@ -13,6 +13,7 @@ constexpr int kSA = 8;             // shared-memory A stages (128 KB in flight p
 constexpr int kMaxTaps = 64;       // k-blocks of a tile-resident convolution (modes 6 / 7): per-k-block line offsets live in shared memory
 constexpr int kMaxSB = 18;         // shared-memory B stages ([hi | lo] each): a ring of as many as fit (at most 8), or all k-blocks resident
 constexpr size_t kSmemBudget = 225 * 1024;
+constexpr int kMaxChainKb = 176;   // weight gradients: k-blocks accumulated into one TMEM accumulator before the partial tile is flushed
 constexpr int kTA = 4;             // tensor-memory A stages (64 columns each: 32 hi + 32 lo)
 #ifndef PPD_GROUPS
 #define PPD_GROUPS 2
