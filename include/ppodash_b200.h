@@ -111,6 +111,44 @@ int ppd_gather_recurrent(const ppd_gather_desc* d, const int64_t* env_perm, int6
                          int E, int T, int N, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * uint8 observation frames: normalise-on-read, device frame stack, minibatch gather      
+ * replaces, bit-exactly, the env-side float pipeline of the reference:
+ *   NormalizeWrapper.observation   ppo-dash-study/013_.../sohojoe_wrappers.py:871-885   (obs - mean) / std  or  obs / 255, float64
+ *   TransposeImage.observation     ppo-dash-training/.../make_env.py:155-160            HWC -> CHW
+ *   VecPyTorch.step_wait           make_env.py:105-113                                  torch.from_numpy(obs).float()
+ *   VecPyTorchFrameStack.step_wait make_env.py:39-46                                    shift, zero on episode end, append
+ * followed by the obs part of the minibatch generators (PKG/storage.py:144-146,171-197).
+ * The storage keeps every frame ONCE as uint8, CHW:  frames [T + nstack, N, C, H*W]; storage slot t's newest frame is frame
+ * t + nstack - 1, so slot t's stack entry j (oldest first) is frame t + j.  age [T+1, N] (uint8) = number of earlier frames of the
+ * same episode, saturating at nstack - 1 (NULL: always nstack - 1, i.e. no episode boundaries).  Output element:
+ *     out = float32( (float64(u8) - mean[c,y,x]) / divisor )    IEEE float64, one rounding to float32 (= numpy, then .float())
+ * or 0.0f for a stack entry that predates the episode.  mean: float64 [C, H*W] (the reference's (H,W,C) file transposed) or NULL
+ * (= 0: obs / 255 with divisor 255; raw values with divisor 1).  C*H*W must be a multiple of 16; frames, mean, out 16-byte aligned.
+ *   expand                 out [N, nstack*C, H*W]       <- storage slot t           (what Policy.act / get_value are fed)
+ *   gather_feed_forward    out row i                    <- (t, n) = divmod(perm[mb_start + i], N)
+ *   gather_recurrent       out row t*E + j              <- (t, env_perm[env_start + j])
+ */
+typedef struct ppd_obs_u8_desc {
+    const uint8_t* frames;
+    const uint8_t* age;
+    const double* mean;
+    double divisor;
+    int C;
+    int64_t HW;
+    int nstack;
+    int multiply_exact;      /* 1: (u8 - mean) * (1 / divisor) was certified bit-identical to the division for this (mean, divisor) */
+} ppd_obs_u8_desc;
+/* bad[0] (device int) = 0 if float32((u - mean[p]) * (1 / divisor)) == float32((u - mean[p]) / divisor) for ALL u in 0..255 and all
+ * n pixels p (mean NULL: m = 0), else 1.  Run once per (mean, divisor); a certified pair lets the kernels below replace the float64
+ * division of every element by one multiply without giving up bit-exactness. */
+int ppd_obs_u8_certify(const double* mean, int64_t n, double divisor, int* bad, void* stream);
+int ppd_obs_u8_expand(const ppd_obs_u8_desc* d, int64_t t, int N, float* out, void* stream);
+int ppd_gather_obs_u8_feed_forward(const ppd_obs_u8_desc* d, const int64_t* perm, int64_t mb_start, int64_t rows, int T, int N,
+                                   float* out, void* stream);
+int ppd_gather_obs_u8_recurrent(const ppd_obs_u8_desc* d, const int64_t* env_perm, int64_t env_start, int E, int T, int N,
+                                float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused PPO loss, forward + backward      replaces PKG/algo/ppo.py:61-81 and the Categorical
  *                                         log-prob / entropy of PKG/distributions.py:23-25,66-68
  * z [B, ldz]: columns 0..A-1 = action logits, column A = value prediction (the heads GEMM

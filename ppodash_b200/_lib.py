@@ -35,6 +35,12 @@ class GatherDesc(Structure):
     ]
 
 
+class ObsU8Desc(Structure):
+    """Mirror of ``ppd_obs_u8_desc``."""
+    _fields_ = [("frames", c_void_p), ("age", c_void_p), ("mean", c_void_p), ("divisor", c_double), ("C", c_int), ("HW", c_int64),
+                ("nstack", c_int), ("multiply_exact", c_int)]
+
+
 class GemmArgs(Structure):
     """Mirror of ``ppd_gemm_args``."""
     _fields_ = [
@@ -75,6 +81,10 @@ _PROTOTYPES = {
     "ppd_advantage_normalize": (c_int, [_P, _P, c_int64, _P, _P, _P]),
     "ppd_gather_feed_forward": (c_int, [POINTER(GatherDesc), _P, c_int64, c_int64, c_int, c_int, _P]),
     "ppd_gather_recurrent": (c_int, [POINTER(GatherDesc), _P, c_int64, c_int, c_int, c_int, _P]),
+    "ppd_obs_u8_certify": (c_int, [_P, c_int64, c_double, _P, _P]),
+    "ppd_obs_u8_expand": (c_int, [POINTER(ObsU8Desc), c_int64, c_int, _P, _P]),
+    "ppd_gather_obs_u8_feed_forward": (c_int, [POINTER(ObsU8Desc), _P, c_int64, c_int64, c_int, c_int, _P, _P]),
+    "ppd_gather_obs_u8_recurrent": (c_int, [POINTER(ObsU8Desc), _P, c_int64, c_int, c_int, c_int, _P, _P]),
     "ppd_ppo_loss_workspace": (c_size_t, [c_int64]),
     "ppd_ppo_loss_fwd_bwd": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, c_int64, c_int64, c_float, c_float,
                                      c_float, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),

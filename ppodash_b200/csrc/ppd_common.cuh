@@ -62,6 +62,11 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
                  : "l"(p));
     return r;
 }
+__device__ __forceinline__ unsigned ldg_stream_u32(const unsigned* p) {
+    unsigned r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
                  "f"(v.z), "f"(v.w)

@@ -43,7 +43,9 @@ class RolloutLoop:
         N = rollouts.obs.shape[1]
         self.N = N
         # static inputs / outputs of the captured graph
-        self._in = dict(obs=torch.zeros_like(rollouts.obs[0]), vobs=torch.zeros_like(rollouts.vector_obs[0]),
+        u8 = getattr(rollouts, "obs_u8", False)          # uint8 frame storage: the policy input is expanded from it on the device
+        obs_in = torch.zeros((N,) + rollouts.policy_obs_shape, device=dev) if u8 else torch.zeros_like(rollouts.obs[0])
+        self._in = dict(obs=obs_in, vobs=torch.zeros_like(rollouts.vector_obs[0]),
                         h=torch.zeros_like(rollouts.recurrent_hidden_states[0]), m=torch.ones_like(rollouts.masks[0]))
         self._out = None
         self._graph = None
@@ -51,7 +53,7 @@ class RolloutLoop:
         self._bufs = {}               # scratch of the captured forward pass: owned here, never shared with eager / training calls
         # pinned staging
         pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory()
-        self._h_obs = pin(*rollouts.obs.shape[1:])
+        self._h_obs = pin(*rollouts.obs.shape[1:], dtype=rollouts.obs.dtype)
         self._h_vobs = pin(*rollouts.vector_obs.shape[1:])
         self._h_rew = pin(N, 1)
         self._h_flags = pin(2, N, 1)                          # done, bad_transition as 0/1 floats
@@ -89,7 +91,8 @@ class RolloutLoop:
         (valid after this call returns: it waits for the copy)."""
         r, s = self.rollouts, self.rollouts.step
         i = self._in
-        i["obs"].copy_(r.obs[s]); i["vobs"].copy_(r.vector_obs[s])
+        r.obs_at(s, out=i["obs"]) if getattr(r, "obs_u8", False) else i["obs"].copy_(r.obs[s])
+        i["vobs"].copy_(r.vector_obs[s])
         i["h"].copy_(r.recurrent_hidden_states[s]); i["m"].copy_(r.masks[s])
         if self.use_cuda_graph:
             if self._graph is None or self._sig != self.policy.engine().signature():
@@ -109,7 +112,8 @@ class RolloutLoop:
         if isinstance(src, torch.Tensor):
             dst.copy_(src.reshape(dst.shape))
         else:
-            dst.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32)).reshape(dst.shape))
+            np_dtype = np.uint8 if dst.dtype == torch.uint8 else np.float32
+            dst.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np_dtype)).reshape(dst.shape))
 
     def observe(self, obs, vector_obs, reward, done, bad_transition=None):
         """The environment's answer to the last `act()`: new observations, rewards, `done` flags and (optionally) the
@@ -121,7 +125,7 @@ class RolloutLoop:
 
         def up(pinned, x):
             if isinstance(x, torch.Tensor) and x.is_cuda:
-                return x.to(torch.float32).reshape(pinned.shape)
+                return x.to(pinned.dtype).reshape(pinned.shape)
             self._stage(pinned, x)
             return pinned.to(dev, non_blocking=True)
 

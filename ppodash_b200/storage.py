@@ -20,7 +20,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import GatherDesc, check, lib, ptr, stream_ptr
+from ._lib import GatherDesc, ObsU8Desc, check, lib, ptr, stream_ptr
 
 
 class FusedAdvantages:
@@ -37,9 +37,42 @@ def _flatten_helper(T, N, _tensor):
 
 
 class RolloutStorage(object):
+    """Reference constructor (PKG/storage.py:10-11) plus one opt-in extension:
+
+    ``obs_dtype=torch.uint8`` keeps the observations as the uint8 frames the environment emits -- each frame ONCE, CHW -- and
+    moves the env-side float pipeline of the reference onto the device: ``(frame - obs_mean) / obs_std`` (or ``frame / 255``) in
+    float64 rounded once to float32 (NormalizeWrapper + VecPyTorch's ``.float()``), and the ``frame_stack``-deep stack of
+    VecPyTorchFrameStack with its zeroing at episode starts.  The float32 values the policy sees are bit-identical to the
+    reference's; they are produced when a frame is read (``obs_at(step)`` for act / get_value, the generators for training).
+    ``obs_shape`` stays the shape the POLICY sees, ``(frame_stack * C, H, W)``; ``rollouts.obs[t]`` is the newest uint8 frame
+    ``[N, C, H, W]`` of slot t and ``insert`` takes the new frame.  ``obs_mean``: float64 ``[C, H, W]`` (the reference's (H, W, C)
+    mean file transposed) or None; ``obs_std``: the divisor (None: 255 without a mean -- the reference's ``obs / 255`` -- else 1).
+    4x (no stack) to 16x (4-stack) fewer observation bytes in HBM and over PCIe."""
+
     def __init__(self, num_steps, num_processes, obs_shape, vector_obs_shape, action_space,
-                 recurrent_hidden_state_size):
-        self.obs = torch.zeros(num_steps + 1, num_processes, *obs_shape)
+                 recurrent_hidden_state_size, obs_dtype=None, frame_stack=1, obs_mean=None, obs_std=None):
+        self.obs_u8 = obs_dtype == torch.uint8
+        if obs_dtype not in (None, torch.float32, torch.uint8):
+            raise ValueError("obs_dtype must be None / torch.float32 (reference layout) or torch.uint8")
+        if self.obs_u8:
+            if len(obs_shape) != 3 or obs_shape[0] % int(frame_stack) != 0 or frame_stack < 1:
+                raise ValueError("uint8 storage needs obs_shape = (frame_stack * C, H, W)")
+            self.frame_stack = int(frame_stack)
+            c = obs_shape[0] // self.frame_stack
+            # frames [T + nstack, N, C, H, W]; slot t's newest frame is frame t + nstack - 1 = self.obs[t]
+            self._frames = torch.zeros(num_steps + self.frame_stack, num_processes, c, *obs_shape[1:], dtype=torch.uint8)
+            self.obs = self._frames[self.frame_stack - 1:]
+            self.obs_age = torch.zeros(num_steps + 1, num_processes, dtype=torch.uint8)     # earlier frames of the same episode
+            self.obs_mean = None
+            if obs_mean is not None:
+                self.obs_mean = torch.as_tensor(obs_mean, dtype=torch.float64).reshape(c, *obs_shape[1:]).contiguous().clone()
+            self.obs_div = float(obs_std) if obs_std is not None else (255.0 if obs_mean is None else 1.0)
+            self.policy_obs_shape = tuple(obs_shape)
+            self._mul_exact = None
+        else:
+            if frame_stack != 1 or obs_mean is not None or obs_std is not None:
+                raise ValueError("frame_stack / obs_mean / obs_std need obs_dtype=torch.uint8")
+            self.obs = torch.zeros(num_steps + 1, num_processes, *obs_shape)
         self.vector_obs = torch.zeros(num_steps + 1, num_processes, *vector_obs_shape)
         self.recurrent_hidden_states = torch.zeros(num_steps + 1, num_processes, recurrent_hidden_state_size)
         self.rewards = torch.zeros(num_steps, num_processes, 1)
@@ -65,7 +98,45 @@ class RolloutStorage(object):
     def to(self, device):
         self.finish_upload()
         for name in self._FIELDS:
+            if name == "obs" and self.obs_u8:
+                continue
             setattr(self, name, getattr(self, name).to(device, non_blocking=True))
+        if self.obs_u8:
+            self._frames = self._frames.to(device, non_blocking=True)
+            self.obs = self._frames[self.frame_stack - 1:]             # keep `obs` a view of the frame ring
+            self.obs_age = self.obs_age.to(device, non_blocking=True)
+            if self.obs_mean is not None:
+                self.obs_mean = self.obs_mean.to(device, non_blocking=True)
+
+    # ------------------------------------------------------------------ uint8 frames
+    def _u8_desc(self):
+        d = ObsU8Desc()
+        d.frames, d.age = ptr(self._frames, torch.uint8), ptr(self.obs_age, torch.uint8)
+        d.mean = ptr(self.obs_mean, torch.float64) if self.obs_mean is not None else None
+        d.divisor = self.obs_div
+        d.C, d.HW, d.nstack = self._frames.size(2), self._frames[0, 0, 0].numel(), self.frame_stack
+        if self._mul_exact is None:
+            # once per (mean, divisor): may the kernels multiply by 1/divisor instead of dividing?  (all 256 x C*H*W cases checked)
+            bad = torch.ones(1, dtype=torch.int32, device=self._frames.device)
+            check(lib().ppd_obs_u8_certify(d.mean, d.C * d.HW, d.divisor, ptr(bad, torch.int32), stream_ptr(self._frames.device)),
+                  "obs_u8_certify")
+            self._mul_exact = int(bad.item()) == 0
+        d.multiply_exact = 1 if self._mul_exact else 0
+        return d
+
+    def obs_at(self, step, out=None):
+        """float32 ``[N, frame_stack * C, H, W]`` observation of storage slot `step` -- what the reference keeps in
+        ``rollouts.obs[step]`` and feeds to ``actor_critic.act`` (run.py:172-175).  For the reference layout this is ``obs[step]``."""
+        if not self.obs_u8:
+            return self.obs[step]
+        self.finish_upload()
+        N = self.rewards.size(1)
+        step = int(step) % (self.num_steps + 1)
+        if out is None:
+            out = torch.empty((N,) + self.policy_obs_shape, dtype=torch.float32, device=self._frames.device)
+        d = self._u8_desc()
+        check(lib().ppd_obs_u8_expand(ctypes.byref(d), step, N, ptr(out, torch.float32), stream_ptr(self._frames.device)), "obs_u8_expand")
+        return out
 
     # ------------------------------------------------------------------ staged upload of a host rollout
     def upload_from(self, host, staged=True):
@@ -90,6 +161,15 @@ class RolloutStorage(object):
             if k != "obs":
                 getattr(self, k).copy_(get(k), non_blocking=True)
         obs = get("obs")
+        if self.obs_u8:
+            if obs.dtype != torch.uint8:
+                raise TypeError("upload_from: uint8 storage takes uint8 frames")
+            # the stack depth of every slot (and, for frame_stack > 1, the nstack - 1 frames before slot 0)
+            has = (lambda k: k in host) if isinstance(host, dict) else (lambda k: hasattr(host, k))
+            if has("obs_age"):
+                self.obs_age.copy_(get("obs_age"), non_blocking=True)
+            if self.frame_stack > 1 and has("_frames"):
+                self._frames[:self.frame_stack - 1].copy_(get("_frames")[:self.frame_stack - 1], non_blocking=True)
         if staged and obs.device.type == "cpu" and obs.is_pinned() and obs.is_contiguous() and obs.dtype == self.obs.dtype \
                 and self.obs.is_contiguous():
             self._pending = {"host": obs, "events": None}
@@ -153,6 +233,11 @@ class RolloutStorage(object):
                value_preds, rewards, masks, bad_masks):
         s = self.step
         self.finish_upload()
+        if self.obs_u8:
+            if obs.dtype != torch.uint8:
+                raise TypeError("uint8 storage: insert() takes the new uint8 frame [N, C, H, W] (normalisation and stacking happen on the device)")
+            if tuple(obs.shape[1:]) != tuple(self.obs.shape[2:]):
+                raise ValueError("uint8 storage: insert() takes ONE new frame per env, shape {}".format(tuple(self.obs.shape[2:])))
         self.obs[s + 1].copy_(obs, non_blocking=True)
         self.vector_obs[s + 1].copy_(vector_obs, non_blocking=True)
         self.recurrent_hidden_states[s + 1].copy_(recurrent_hidden_states, non_blocking=True)
@@ -162,11 +247,20 @@ class RolloutStorage(object):
         self.rewards[s].copy_(rewards, non_blocking=True)
         self.masks[s + 1].copy_(masks, non_blocking=True)
         self.bad_masks[s + 1].copy_(bad_masks, non_blocking=True)
+        if self.obs_u8:
+            # VecPyTorchFrameStack.step_wait (make_env.py:39-46): an env whose episode just ended starts a fresh stack
+            grown = torch.clamp(self.obs_age[s].to(torch.int16) + 1, max=self.frame_stack - 1)
+            self.obs_age[s + 1] = torch.where(self.masks[s + 1].reshape(-1) == 0, torch.zeros_like(grown), grown).to(torch.uint8)
         self.step = (self.step + 1) % self.num_steps
 
     def after_update(self):
         self.finish_upload()
-        self.obs[0].copy_(self.obs[-1])
+        if self.obs_u8:
+            ns = self.frame_stack
+            self._frames[:ns].copy_(self._frames[-ns:].clone() if ns > 1 else self._frames[-ns:])    # slot T's whole stack -> slot 0
+            self.obs_age[0].copy_(self.obs_age[-1])
+        else:
+            self.obs[0].copy_(self.obs[-1])
         self.vector_obs[0].copy_(self.vector_obs[-1])
         self.recurrent_hidden_states[0].copy_(self.recurrent_hidden_states[-1])
         self.masks[0].copy_(self.masks[-1])
@@ -196,7 +290,10 @@ class RolloutStorage(object):
         T, N = self.rewards.size(0), self.rewards.size(1)
         dev = self.obs.device
         o = out or {}
-        obs_b = o.get("obs") if "obs" in o else self._out(rows, self.obs)
+        if self.obs_u8:
+            obs_b = o.get("obs") if "obs" in o else torch.empty((rows,) + self.policy_obs_shape, dtype=torch.float32, device=dev)
+        else:
+            obs_b = o.get("obs") if "obs" in o else self._out(rows, self.obs)
         vobs_b = o.get("vector_obs") if "vector_obs" in o else self._out(rows, self.vector_obs)
         hrows = rows if mode == "ff" else E
         hxs_b = o.get("hxs") if "hxs" in o else self._out(hrows, self.recurrent_hidden_states)
@@ -206,8 +303,18 @@ class RolloutStorage(object):
         msk_b = self._out(rows, self.masks)
         lp_b = self._out(rows, self.action_log_probs)
         d = GatherDesc()
-        obs_row = self.obs[0, 0].numel()
-        d.obs, d.obs_out, d.obs_row = ptr(self.obs, torch.float32), ptr(obs_b), obs_row
+        if self.obs_u8:
+            # observations: uint8 frames -> normalised, stacked float32 rows (ppd_gather_obs_u8_*); the small fields follow below
+            u = self._u8_desc()
+            if mode == "ff":
+                check(lib().ppd_gather_obs_u8_feed_forward(ctypes.byref(u), ptr(perm_dev, torch.int64), start, rows, T, N,
+                                                           ptr(obs_b, torch.float32), stream_ptr(dev)), "gather_obs_u8")
+            else:
+                check(lib().ppd_gather_obs_u8_recurrent(ctypes.byref(u), ptr(perm_dev, torch.int64), start, E, T, N,
+                                                        ptr(obs_b, torch.float32), stream_ptr(dev)), "gather_obs_u8")
+        else:
+            obs_row = self.obs[0, 0].numel()
+            d.obs, d.obs_out, d.obs_row = ptr(self.obs, torch.float32), ptr(obs_b), obs_row
         vrow = self.vector_obs[0, 0].numel()
         if vrow > 0:
             d.vobs, d.vobs_out, d.vobs_row = ptr(self.vector_obs, torch.float32), vobs_b.data_ptr(), vrow

@@ -75,3 +75,44 @@ def test_storage_host_semantics():
     assert st.masks[1:].eq(0).all() and st.masks[0].eq(1).all()
     st.after_update()
     assert st.obs[0].eq(3).all() and st.masks[0].eq(0).all() and st.recurrent_hidden_states[0].eq(3).all()
+
+
+def test_uint8_storage_bookkeeping_on_cpu():
+    """Host logic of the uint8 storage (no kernel): frame ring / `obs` view aliasing, stack-depth (`age`) bookkeeping of insert
+    against VecPyTorchFrameStack's zeroing rule (make_env.py:39-46), after_update carry, and the loud failure without a GPU."""
+    import numpy as np
+    import torch
+    from ppodash_b200 import _lib
+    from ppodash_b200.storage import RolloutStorage
+
+    class Discrete:
+        def __init__(self, n):
+            self.n = n
+            self.shape = ()
+    T, N, ns = 6, 3, 4
+    st = RolloutStorage(T, N, (ns * 3, 84, 84), [0], Discrete(4), 1, obs_dtype=torch.uint8, frame_stack=ns)
+    assert st.obs.dtype == torch.uint8 and tuple(st.obs.shape) == (T + 1, N, 3, 84, 84) and tuple(st._frames.shape) == (T + ns, N, 3, 84, 84)
+    assert st.obs.data_ptr() == st._frames[ns - 1].data_ptr() and st.obs_div == 255.0
+    rng = np.random.RandomState(0)
+    dones = rng.rand(T, N) < 0.4
+    z = lambda *s: torch.zeros(*s)
+    for t in range(T):
+        frame = torch.full((N, 3, 84, 84), t + 1, dtype=torch.uint8)
+        masks = torch.FloatTensor([[0.0] if d else [1.0] for d in dones[t]])
+        st.insert(frame, z(N, 0), z(N, 1), torch.zeros(N, 1, dtype=torch.int64), z(N, 1), z(N, 1), z(N, 1), masks, torch.ones(N, 1))
+        assert int(st.obs[t + 1].max()) == t + 1
+    # age[t, n] = steps since the last episode start, capped at ns - 1
+    want = np.zeros((T + 1, N), np.int64)
+    for t in range(T):
+        want[t + 1] = np.where(dones[t], 0, np.minimum(want[t] + 1, ns - 1))
+    assert np.array_equal(st.obs_age.numpy(), want)
+    import pytest
+    with pytest.raises(TypeError):
+        st.insert(torch.zeros(N, 3, 84, 84), z(N, 0), z(N, 1), torch.zeros(N, 1, dtype=torch.int64), z(N, 1), z(N, 1), z(N, 1), torch.ones(N, 1), torch.ones(N, 1))
+    last_frames, last_age = st._frames[-ns:].clone(), st.obs_age[-1].clone()
+    st.after_update()
+    assert torch.equal(st._frames[:ns], last_frames) and torch.equal(st.obs_age[0], last_age)
+    with pytest.raises(_lib.PpdError):
+        st.obs_at(0)                      # expanding needs the CUDA kernel: no CPU fallback
+    with pytest.raises(ValueError):
+        RolloutStorage(T, N, (3, 84, 84), [0], Discrete(4), 1, frame_stack=4)

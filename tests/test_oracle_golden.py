@@ -177,3 +177,33 @@ def test_running_moments_pooled_property():
     assert np.isclose(rms.count, n + w)
     out = running_mean_std.obs_filter(rms, chunks[0], clipob=1.0, update=False)
     assert out.min() >= -1.0 and out.max() <= 1.0
+
+
+# --------------------------------------------------------------------------- uint8 observation pipeline
+def _obs_pipeline_inputs(g):
+    T, N, H, W, C, nstack = (int(x) for x in g["shape"])
+    rng = np.random.RandomState(int(g["seed"]))
+    frames = rng.randint(0, 256, size=(T + 1, N, H, W, C), dtype=np.uint8)
+    dones = rng.rand(T, N) < 0.3
+    dones[1, 0] = True
+    assert np.array_equal(dones, g["dones"])
+    return frames, dones, nstack
+
+
+def test_obs_pipeline_oracle_is_bit_exact_with_reference_wrappers(golden):
+    """oracle/obs_pipeline.py against the outputs of the reference's NormalizeWrapper / TransposeImage / VecPyTorch cast /
+    VecPyTorchFrameStack (tests/golden/make_golden_obs.py): sha256 of the float32 bytes, and the stored slots element for element."""
+    import hashlib
+    from oracle import obs_pipeline as o_obs
+    g = golden("obs_pipeline")
+    frames, dones, nstack = _obs_pipeline_inputs(g)
+    sha = lambda t: hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+    norm = o_obs.rollout_observations(frames, dones, 1, g["mean"], g["std"])
+    assert np.array_equal(norm[:1].numpy(), g["head_norm"])
+    assert sha(norm) == str(g["sha_norm"])
+    div = o_obs.rollout_observations(frames, dones, 1)
+    assert np.array_equal(div[:1].numpy(), g["head_div255"])
+    assert sha(div) == str(g["sha_div255"])
+    st = o_obs.rollout_observations(frames, dones, nstack, g["mean"], g["std"])
+    assert np.array_equal(st[2, :1].numpy(), g["head_stack"])
+    assert sha(st) == str(g["sha_stack"])

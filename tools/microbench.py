@@ -123,6 +123,31 @@ def bench_gather(T, N, C, V, recurrent, nmb):
                 ms_best=best, samples_per_s=samples / (med * 1e-3), gbs=bytes_ / (med * 1e-3) / 1e9)
 
 
+def bench_gather_u8(T, N, C, V, nmb, nstack=1, with_mean=True):
+    """Recurrent gather from the uint8 frame storage (normalise-on-gather): algorithmic bytes = C*HW read (+ V, scalars) and
+    nstack*C*HW*4 written per sample."""
+    import numpy as np
+    mean = np.random.RandomState(0).rand(C, 84, 84) * 255 if with_mean else None
+    st = RolloutStorage(T, N, (nstack * C, 84, 84), [V], Discrete(8), 512, obs_dtype=torch.uint8, frame_stack=nstack, obs_mean=mean,
+                        obs_std=36.3 if with_mean else None)
+    st.to(DEV)
+    st._frames.random_(0, 256)
+    st.obs_age.fill_(nstack - 1)
+    stats = torch.tensor([0.0, 1.0], device=DEV)
+    frame = C * 84 * 84
+    row = frame + nstack * frame * 4 + 2 * (V * 4 + 8 + 5 * 4)
+    out = {}
+
+    def fn():
+        for mb in st.recurrent_generator(FusedAdvantages(stats), nmb):
+            out["x"] = mb
+    med, best = time_kernel(fn, iters=5, warmup=2)
+    samples = T * (N // nmb) * nmb
+    bytes_ = row * samples + (N // nmb) * nmb * 512 * 8
+    return dict(kernel="gather_recurrent_u8", T=T, N=N, C=C, nstack=nstack, nmb=nmb, ms_epoch=med, ms_best=best,
+                samples_per_s=samples / (med * 1e-3), gbs=bytes_ / (med * 1e-3) / 1e9)
+
+
 def bench_adam(n, sets=8):
     L = _lib.lib()
     ws = torch.empty(L.ppd_clip_adam_workspace(n), dtype=torch.uint8, device=DEV)
@@ -161,6 +186,9 @@ def main():
         res.append(bench_gather(128, 32, 4, 0, False, 4))
         res.append(bench_gather(512, 256, 3, 15, True, 8))
         res.append(bench_gather(512, 256, 3, 15, False, 8))
+        res.append(bench_gather_u8(512, 256, 3, 15, 8))
+        res.append(bench_gather_u8(512, 256, 3, 15, 8, with_mean=False))
+        res.append(bench_gather_u8(512, 256, 3, 15, 8, nstack=4))
     if only in ("all", "adam"):
         res.append(bench_adam(2464393))
         res.append(bench_adam(1 << 26))
