@@ -28,8 +28,19 @@ def ppo_losses(values, logp, entropy, old_values, returns, old_logp, adv, clip, 
 class UpdateState:
     """Parameters (leaf tensors keyed by state_dict name) + their Adam optimiser."""
 
-    def __init__(self, params, lr, eps):
+    def __init__(self, params, lr, eps, flat_gru=False):
         self.params = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+        gru = ["base.gru.weight_ih_l0", "base.gru.weight_hh_l0", "base.gru.bias_ih_l0", "base.gru.bias_hh_l0"]
+        if flat_gru and all(k in self.params for k in gru):
+            # nn.GRU keeps its four tensors in ONE buffer (flatten_parameters) so that cuDNN need not compact them on every call;
+            # the stock-PyTorch-CUDA comparison row of bench.py gets the same layout: leaf tensors that are views of one buffer
+            flat = torch.cat([self.params[k].detach().reshape(-1) for k in gru])
+            off = 0
+            for k in gru:
+                n = self.params[k].numel()
+                self.params[k] = flat[off:off + n].view(self.params[k].shape).detach().requires_grad_(True)
+                off += n
+            self._flat_gru = flat
         self.optimizer = torch.optim.Adam(list(self.params.values()), lr=lr, eps=eps)
 
 

@@ -124,6 +124,8 @@ _PROTOTYPES = {
     "ppd_gru_set_mode": (None, [c_int]),
 }
 
+_HOST_ONLY = {"ppd_tc_gemm_supported"}      # predicates evaluated on the host: no kernel behind them, nothing to time
+
 _lib = None
 
 
@@ -210,7 +212,7 @@ class _Profile:
         for name in _PROTOTYPES:
             fn = getattr(handle, name)
             restype, argtypes = _PROTOTYPES[name]
-            if restype is not c_int or not argtypes:
+            if restype is not c_int or not argtypes or name in _HOST_ONLY:
                 continue
             self._saved[name] = fn
 
