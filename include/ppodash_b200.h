@@ -168,6 +168,13 @@ int ppd_ppo_loss_fwd_bwd(const float* z, int ldz, int A, const int64_t* actions,
                          int use_clipped_value_loss,
                          float* dz, float* logp_out, float* entropy_out, float* loss_out,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* A2C loss, forward + backward          replaces PKG/algo/a2c_acktr.py:49-52,71-72
+ *   advantages = returns - values; value_loss = mean(adv^2); action_loss = -mean(adv.detach() * log_prob);
+ *   dz = gradient of value_loss*value_coef + action_loss - entropy*entropy_coef; loss_out[3] = { value_loss, action_loss,
+ *   dist_entropy } contributions of these B rows (means over global_rows).  Same z layout and workspace as the PPO loss. */
+int ppd_a2c_loss_fwd_bwd(const float* z, int ldz, int A, const int64_t* actions, const float* returns, int64_t B,
+                         int64_t global_rows, float value_coef, float entropy_coef, float* dz, float* loss_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
 /* Forward only: log-prob of `actions`, per-row entropy and (if mode_out) the arg-max action.
  * Used by Policy.act / evaluate_actions (PKG/model.py:54-79). */
 int ppd_categorical_eval(const float* z, int ldz, int A, const int64_t* actions, int64_t B,
@@ -191,6 +198,12 @@ int ppd_clip_adam_step(float* params, const float* grads, float* exp_avg, float*
                        int64_t n, int64_t step, double lr, double beta1, double beta2, double eps,
                        double max_norm, float* grad_norm_out, const float* loss_in, float* loss_acc,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* Gradient-norm clip + RMSprop step          replaces nn.utils.clip_grad_norm_ + optim.RMSprop.step of PKG/algo/a2c_acktr.py:30-31,
+ * 74-78 (centered = False, momentum = 0, weight_decay = 0): square_avg = alpha*square_avg + (1-alpha)*g*g;
+ * p -= lr * g / (sqrt(square_avg) + eps), g already scaled by min(1, max_norm / (||g|| + 1e-6)).  Workspace as for Adam. */
+int ppd_clip_rmsprop_step(float* params, const float* grads, float* square_avg, int64_t n, double lr, double alpha, double eps,
+                          double max_norm, float* grad_norm_out, void* workspace, size_t workspace_bytes, void* stream);
+
 
 /* ---------------------------------------------------------------------------------------
  * Running observation normalisation     replaces VecNormalize._obfilt (PKG/envs.py:208-217) +

@@ -88,6 +88,8 @@ _PROTOTYPES = {
     "ppd_ppo_loss_workspace": (c_size_t, [c_int64]),
     "ppd_ppo_loss_fwd_bwd": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, c_int64, c_int64, c_float, c_float,
                                      c_float, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "ppd_a2c_loss_fwd_bwd": (c_int, [_P, c_int, c_int, _P, _P, c_int64, c_int64, c_float, c_float, _P, _P, _P, c_size_t, _P]),
+    "ppd_clip_rmsprop_step": (c_int, [_P, _P, _P, c_int64, c_double, c_double, c_double, c_double, _P, _P, c_size_t, _P]),
     "ppd_categorical_eval": (c_int, [_P, c_int, c_int, _P, c_int64, _P, _P, _P, _P, _P]),
     "ppd_clip_adam_workspace": (c_size_t, [c_int64]),
     "ppd_clip_adam_set_fused": (None, [c_int]),

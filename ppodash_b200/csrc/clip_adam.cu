@@ -163,6 +163,37 @@ clip_adam_fused_kernel(float* __restrict__ p, const float* __restrict__ g, float
         for (int64_t i = nvec * kVec + threadIdx.x; i < n; i += kThreads) adam_one(p[i], g[i], m[i], v[i], coef, c);
 }
 
+// RMSprop (torch.optim.RMSprop, centered=False, momentum=0, weight_decay=0 -- what PKG/algo/a2c_acktr.py:30-31 constructs):
+//   square_avg.mul_(alpha).addcmul_(grad, grad, value=1 - alpha); avg = square_avg.sqrt().add_(eps); param.addcdiv_(grad, avg, value=-lr)
+__device__ __forceinline__ void rmsprop_one(float& p, float g, float& sq, float coef, float alpha, float one_minus_alpha, float eps, float neg_lr) {
+    g = g * coef;
+    sq = sq * alpha;
+    sq = sq + (one_minus_alpha * g) * g;
+    const float avg = sqrtf(sq) + eps;
+    p = p + neg_lr * __fdiv_rn(g, avg);
+}
+
+__global__ void __launch_bounds__(kThreads)
+rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq, int64_t n, const Scalars* __restrict__ sc,
+               float alpha, float one_minus_alpha, float eps, float neg_lr) {
+    const float coef = sc->clip_coef;
+    const int64_t nvec = n / kVec;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* s4 = reinterpret_cast<float4*>(sq);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * kThreads) {
+        float4 pp = p4[i], ss = s4[i];
+        const float4 gg = __ldg(g4 + i);
+        rmsprop_one(pp.x, gg.x, ss.x, coef, alpha, one_minus_alpha, eps, neg_lr);
+        rmsprop_one(pp.y, gg.y, ss.y, coef, alpha, one_minus_alpha, eps, neg_lr);
+        rmsprop_one(pp.z, gg.z, ss.z, coef, alpha, one_minus_alpha, eps, neg_lr);
+        rmsprop_one(pp.w, gg.w, ss.w, coef, alpha, one_minus_alpha, eps, neg_lr);
+        p4[i] = pp; s4[i] = ss;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = nvec * kVec + threadIdx.x; i < n; i += kThreads) rmsprop_one(p[i], g[i], sq[i], coef, alpha, one_minus_alpha, eps, neg_lr);
+}
+
 constexpr int64_t kFusedMaxParams = 4 << 20;     // 4 arrays x 16 MB stay L2-resident
 int g_fused = 1;
 
@@ -235,4 +266,31 @@ extern "C" int ppd_clip_adam_step(float* params, const float* grads, float* exp_
     if (blocks > 8 * ppd::kNumSMs) blocks = 8 * ppd::kNumSMs;
     adam_kernel<<<(int)blocks, kThreads, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, sc, c);
     return ppd::launch_status("adam_kernel");
+}
+
+extern "C" int ppd_clip_rmsprop_step(float* params, const float* grads, float* square_avg, int64_t n, double lr, double alpha,
+                                     double eps, double max_norm, float* grad_norm_out, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    PPD_REQUIRE(params && grads && square_avg && workspace, "null pointer");
+    PPD_REQUIRE(n > 0, "n must be positive");
+    PPD_REQUIRE(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)square_avg) % 16 == 0, "buffers must be 16-byte aligned");
+    if (workspace_bytes < ws_bytes(n)) {
+        ppd::set_error("ppd_clip_rmsprop_step: workspace too small");
+        return PPD_EWORKSPACE;
+    }
+    cudaStream_t s = ppd::as_stream(stream);
+    Scalars* sc = reinterpret_cast<Scalars*>(workspace);
+    double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
+    const int nb = norm_blocks(n);
+    sqnorm_partial<<<nb, kThreads, 0, s>>>(grads, n, partial);
+    int rc = ppd::launch_status("sqnorm_partial");
+    if (rc) return rc;
+    norm_final<<<1, kThreads, 0, s>>>(partial, nb, (float)max_norm, sc, grad_norm_out, nullptr, nullptr);
+    rc = ppd::launch_status("norm_final");
+    if (rc) return rc;
+    int64_t blocks = (n / kVec + kThreads - 1) / kThreads;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 8 * ppd::kNumSMs) blocks = 8 * ppd::kNumSMs;
+    rmsprop_kernel<<<(int)blocks, kThreads, 0, s>>>(params, grads, square_avg, n, sc, (float)alpha, (float)(1.0 - alpha), (float)eps, (float)(-lr));
+    return ppd::launch_status("rmsprop_kernel");
 }

@@ -106,8 +106,46 @@ ppo_loss_kernel(const float* __restrict__ z, int ldz, int A, const int64_t* __re
     }
 }
 
+// A2C loss forward + backward (PKG/algo/a2c_acktr.py:49-52,71-72): advantages = returns - values;
+//   value_loss = mean(adv^2), action_loss = -mean(adv.detach() * logp), loss = vcoef * value_loss + action_loss - ecoef * mean(H).
+// partial[] holds { sum adv^2, sum adv * logp, sum H } per block (ppo_loss_final negates the middle one and scales).
+__global__ void __launch_bounds__(kThreads)
+a2c_loss_kernel(const float* __restrict__ z, int ldz, int A, const int64_t* __restrict__ actions, const float* __restrict__ returns,
+                int64_t B, float inv_rows, float vcoef, float ecoef, float* __restrict__ dz, float* __restrict__ partial) {
+    __shared__ float scratch[32];
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    float t_v = 0.f, t_a = 0.f, t_e = 0.f;
+    if (i < B) {
+        const float* zr = z + i * ldz;
+        float* dzr = dz + i * ldz;
+        const int64_t a = actions[i];
+        const RowStats st = row_softmax_stats(zr, A, a);
+        const float adv = returns[i] - zr[A];
+        t_v = adv * adv;
+        t_a = adv * st.logp;
+        t_e = st.ent;
+        dzr[A] = (vcoef * inv_rows) * (-2.0f * adv);                 // d mean(adv^2) / dv
+        const float g_lp = -adv * inv_rows;                           // d(-mean(adv.detach() * logp)) / dlogp_a
+        const float ce = ecoef * inv_rows;
+        for (int j = 0; j < A; ++j) {
+            const float lp = zr[j] - st.lse;
+            const float p = expf(lp);
+            const float onehot = (j == a) ? 1.f : 0.f;
+            dzr[j] = g_lp * (onehot - p) + ce * (p * (lp + st.ent));
+        }
+    }
+    t_v = ppd::block_sum(t_v, scratch);
+    t_a = ppd::block_sum(t_a, scratch);
+    t_e = ppd::block_sum(t_e, scratch);
+    if (threadIdx.x == 0) {
+        partial[3 * blockIdx.x + 0] = t_v;
+        partial[3 * blockIdx.x + 1] = t_a;
+        partial[3 * blockIdx.x + 2] = t_e;
+    }
+}
+
 __global__ void __launch_bounds__(256)
-ppo_loss_final(const float* __restrict__ partial, int nblocks, float inv_rows, float* __restrict__ loss_out) {
+ppo_loss_final(const float* __restrict__ partial, int nblocks, float inv_rows, double vscale, float* __restrict__ loss_out) {
     __shared__ double scratch[32];
     double v = 0, a = 0, e = 0;
     for (int i = threadIdx.x; i < nblocks; i += 256) {
@@ -119,7 +157,7 @@ ppo_loss_final(const float* __restrict__ partial, int nblocks, float inv_rows, f
     a = ppd::block_sum(a, scratch);
     e = ppd::block_sum(e, scratch);
     if (threadIdx.x == 0) {
-        loss_out[0] = (float)(0.5 * v * inv_rows);
+        loss_out[0] = (float)(vscale * v * inv_rows);
         loss_out[1] = (float)(-a * inv_rows);
         loss_out[2] = (float)(e * inv_rows);
     }
@@ -174,7 +212,26 @@ extern "C" int ppd_ppo_loss_fwd_bwd(const float* z, int ldz, int A, const int64_
                                             logp_out, entropy_out, (float*)workspace);
     int rc = ppd::launch_status("ppo_loss_kernel");
     if (rc) return rc;
-    ppo_loss_final<<<1, 256, 0, s>>>((const float*)workspace, nb, inv_rows, loss_out);
+    ppo_loss_final<<<1, 256, 0, s>>>((const float*)workspace, nb, inv_rows, 0.5, loss_out);
+    return ppd::launch_status("ppo_loss_final");
+}
+
+extern "C" int ppd_a2c_loss_fwd_bwd(const float* z, int ldz, int A, const int64_t* actions, const float* returns, int64_t B,
+                                    int64_t global_rows, float value_coef, float entropy_coef, float* dz, float* loss_out,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    PPD_REQUIRE(z && actions && returns && dz && loss_out && workspace, "null pointer");
+    PPD_REQUIRE(B > 0 && global_rows >= B && A > 0 && ldz >= A + 1, "bad sizes");
+    const int nb = nblocks_for(B);
+    if (workspace_bytes < (size_t)3 * nb * sizeof(float)) {
+        ppd::set_error("ppd_a2c_loss_fwd_bwd: workspace too small");
+        return PPD_EWORKSPACE;
+    }
+    const float inv_rows = (float)(1.0 / (double)global_rows);
+    cudaStream_t s = ppd::as_stream(stream);
+    a2c_loss_kernel<<<nb, kThreads, 0, s>>>(z, ldz, A, actions, returns, B, inv_rows, value_coef, entropy_coef, dz, (float*)workspace);
+    int rc = ppd::launch_status("a2c_loss_kernel");
+    if (rc) return rc;
+    ppo_loss_final<<<1, 256, 0, s>>>((const float*)workspace, nb, inv_rows, 1.0, loss_out);
     return ppd::launch_status("ppo_loss_final");
 }
 

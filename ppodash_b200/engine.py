@@ -606,10 +606,11 @@ class PolicyEngine:
 
     # ------------------------------------------------------------------ training minibatch
     def train_minibatch(self, sample, clip_param, value_coef, entropy_coef, use_clipped_value_loss=True,
-                        global_rows=None, xcat_prefilled=None):
-        """Forward, fused PPO loss forward+backward, full backward for one minibatch
-        (PKG/algo/ppo.py:57-81).  Leaves d(loss)/d(params) in the flat gradient buffer and the three
-        loss partial sums at its tail; nothing is synchronised with the host."""
+                        global_rows=None, xcat_prefilled=None, loss="ppo"):
+        """Forward, fused loss forward+backward, full backward for one minibatch.  loss="ppo": PKG/algo/ppo.py:57-81;
+        loss="a2c": PKG/algo/a2c_acktr.py:49-52,71-72 (old_v / old_logp / adv of `sample` are unused and may be None).
+        Leaves d(loss)/d(params) in the flat gradient buffer and the three loss partial sums at its tail; nothing is
+        synchronised with the host."""
         obs, vobs, h0, actions, old_v, ret, masks, old_logp, adv = sample
         out = self.forward(obs, vobs, h0, masks, keep=True, xcat_prefilled=xcat_prefilled)
         L = lib()
@@ -624,11 +625,16 @@ class PolicyEngine:
         ws = _lib.workspace(L.ppd_ppo_loss_workspace(B), dev, "loss")
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
         act = actions.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
-        check(L.ppd_ppo_loss_fwd_bwd(z.data_ptr(), A + 1, A, act.data_ptr(), f32(old_logp).data_ptr(), f32(adv).data_ptr(),
-                                     f32(old_v).data_ptr(), f32(ret).data_ptr(), B, int(global_rows or B),
-                                     float(clip_param), float(value_coef), float(entropy_coef),
-                                     int(bool(use_clipped_value_loss)), dz.data_ptr(), None, None, loss_out.data_ptr(),
-                                     ws.data_ptr(), ws.numel(), self.stream), "ppo_loss")
+        if loss == "a2c":
+            check(L.ppd_a2c_loss_fwd_bwd(z.data_ptr(), A + 1, A, act.data_ptr(), f32(ret).data_ptr(), B, int(global_rows or B),
+                                         float(value_coef), float(entropy_coef), dz.data_ptr(), loss_out.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), self.stream), "a2c_loss")
+        else:
+            check(L.ppd_ppo_loss_fwd_bwd(z.data_ptr(), A + 1, A, act.data_ptr(), f32(old_logp).data_ptr(), f32(adv).data_ptr(),
+                                         f32(old_v).data_ptr(), f32(ret).data_ptr(), B, int(global_rows or B),
+                                         float(clip_param), float(value_coef), float(entropy_coef),
+                                         int(bool(use_clipped_value_loss)), dz.data_ptr(), None, None, loss_out.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), self.stream), "ppo_loss")
         # single chunk: every dY buffer stays valid until the end, so all bias gradients are reduced together then
         self._deferred = [] if len(sv["chunks"]) == 1 else None
         # ---- heads backward (weight / bias gradients on the side stream)
@@ -709,6 +715,19 @@ class PolicyEngine:
         return out
 
     # ------------------------------------------------------------------ optimiser
+    def rmsprop_step(self, lr, alpha, eps, max_grad_norm, grad_norm_out=None):
+        """clip_grad_norm_ + RMSprop.step over the flat buffers (a2c_acktr.py:74-78)."""
+        self.bind()
+        L = lib()
+        if getattr(self, "rms_state", None) is None or self.rms_state.numel() != self.flat.numel() or self.rms_state.device != self.device:
+            self.rms_state = torch.zeros_like(self.flat)
+        n = self.n_params
+        ws = _lib.workspace(L.ppd_clip_adam_workspace(n), self.device, "adam")
+        check(L.ppd_clip_rmsprop_step(self.flat.data_ptr(), self.flat_grad.data_ptr(), self.rms_state.data_ptr(), n, float(lr), float(alpha),
+                                      float(eps), float(max_grad_norm) if max_grad_norm else 0.0,
+                                      grad_norm_out.data_ptr() if grad_norm_out is not None else None,
+                                      ws.data_ptr(), ws.numel(), _lib.stream_ptr(self.device)), "clip_rmsprop_step")
+
     def adam_step(self, lr, betas, eps, max_grad_norm, loss_acc=None, grad_norm_out=None):
         """clip_grad_norm_ + Adam.step over the flat buffers (ppo.py:82-84)."""
         self.bind()

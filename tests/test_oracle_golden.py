@@ -207,3 +207,24 @@ def test_obs_pipeline_oracle_is_bit_exact_with_reference_wrappers(golden):
     st = o_obs.rollout_observations(frames, dones, nstack, g["mean"], g["std"])
     assert np.array_equal(st[2, :1].numpy(), g["head_stack"])
     assert sha(st) == str(g["sha_stack"])
+
+
+# --------------------------------------------------------------------------- A2C
+def test_a2c_update_oracle_vs_reference(golden):
+    """oracle/a2c_update.py against two consecutive updates of the reference's A2C_ACKTR (tests/golden/make_golden_a2c.py)."""
+    from oracle import a2c_update as o_a2c
+    g = golden("update_a2c")
+    init = {k[5:]: torch.as_tensor(g[k]) for k in g.files if k.startswith("init.")}
+    roll = {k[5:]: torch.as_tensor(g[k]) for k in g.files if k.startswith("roll.")}
+    st = o_a2c.A2CState(init, float(g["lr"]), float(g["eps"]), float(g["alpha"]))
+    kw = dict(recurrent=True, value_loss_coef=float(g["vcoef"]), entropy_coef=float(g["ecoef"]), max_grad_norm=float(g["max_grad_norm"]))
+    out1 = o_a2c.a2c_update(st, roll, **kw)
+    np.testing.assert_allclose(np.array(out1), g["losses1"], rtol=1e-6, atol=1e-8)
+    for k, v in st.params.items():
+        # (the fixture was made with one thread, run.py:55; this process may use several: the convolutions' summation order differs,
+        #  and RMSprop's g / (sqrt(v) + eps) amplifies that on entries with a gradient near eps -- 2e-3 of lr = 1.4e-6 absolute)
+        np.testing.assert_allclose(v.detach().numpy(), g["mid." + k], rtol=1e-6, atol=1.4e-6, err_msg=k)
+    out2 = o_a2c.a2c_update(st, roll, **kw)
+    np.testing.assert_allclose(np.array(out2), g["losses2"], rtol=1e-5, atol=1e-7)
+    for k, v in st.params.items():
+        np.testing.assert_allclose(v.detach().numpy(), g["final." + k], rtol=1e-5, atol=3e-6, err_msg=k)
