@@ -41,16 +41,28 @@ class FusedClipAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         self._policy.engine().adam_step(g["lr"], g["betas"], g["eps"], self.max_grad_norm, loss_acc, grad_norm_out)
 
+    def _layout_signature(self):
+        eng = self._policy.engine()
+        return [(n, sg.off, sg.numel) for n, sg in eng.segs.items()]
+
     def state_dict(self):
+        """{format, layout, step, exp_avg, exp_avg_sq, param_groups}: the moments are flat buffers in the ENGINE's segment layout
+        (permuted conv weights, padded w_ih, 256-byte aligned segments), so the layout travels with them and is checked on load."""
         eng = self._policy.engine()
         eng.bind()
         st = eng.adam_state
-        return dict(step=st["step"], exp_avg=st["exp_avg"].clone(), exp_avg_sq=st["exp_avg_sq"].clone(),
+        return dict(format="ppodash_b200.FusedClipAdam/1", layout=self._layout_signature(), step=st["step"],
+                    exp_avg=st["exp_avg"].clone(), exp_avg_sq=st["exp_avg_sq"].clone(),
                     param_groups=[{k: v for k, v in g.items() if k != "params"} for g in self.param_groups])
 
     def load_state_dict(self, sd):
+        if "exp_avg" not in sd or "layout" not in sd:
+            raise ValueError("FusedClipAdam.load_state_dict expects the dict FusedClipAdam.state_dict() writes "
+                             "(flat moments + layout signature); torch.optim.Adam's per-parameter format is not accepted")
         eng = self._policy.engine()
         eng.bind()
+        if [tuple(x) for x in sd["layout"]] != [tuple(x) for x in self._layout_signature()]:
+            raise ValueError("FusedClipAdam.load_state_dict: the saved moments were laid out for another network shape")
         eng.adam_state["step"] = int(sd["step"])
         eng.adam_state["exp_avg"].copy_(sd["exp_avg"])
         eng.adam_state["exp_avg_sq"].copy_(sd["exp_avg_sq"])
