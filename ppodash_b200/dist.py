@@ -38,6 +38,20 @@ def all_reduce_sum(t, process_group=None):
     return t
 
 
+class _Done:
+    def wait(self):
+        return True
+
+
+def all_reduce_sum_async(t, process_group=None):
+    """In-place SUM all-reduce of a contiguous view, enqueued behind the work of the CURRENT stream; returns a handle whose
+    ``wait()`` makes the then-current stream wait for the result (torch.distributed ``async_op=True``).  No-op on a single rank."""
+    ws, _ = world(process_group)
+    if ws > 1:
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=process_group, async_op=True)
+    return _Done()
+
+
 def equivalent_global_env_blocks(local_perms, n_local, num_mini_batch):
     """The env blocks a SINGLE process must use to see the same minibatches as G ranks that each drew
     `local_perms[r]` (a permutation of its n_local envs) in recurrent_generator: global minibatch k is the

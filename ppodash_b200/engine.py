@@ -235,9 +235,15 @@ class PolicyEngine:
                 self.ctx.__exit__(*exc)
             return False
 
-    def _flush_colsums(self):
-        """All bias gradients of the minibatch in two launches (ppd_colsum_multi)."""
-        todo, self._deferred = self._deferred, None
+    def _flush_colsums(self, from_off=None):
+        """All bias gradients of the minibatch in two launches (ppd_colsum_multi).  from_off: flush only the sums whose output lies at
+        or beyond that offset of the flat gradient buffer and keep collecting the others (early gradient bucket, see train_minibatch)."""
+        if from_off is not None:
+            base = self.flat_grad.data_ptr() + 4 * from_off
+            todo = [c for c in (self._deferred or []) if c[4].data_ptr() >= base]
+            self._deferred = [c for c in self._deferred if c[4].data_ptr() < base]
+        else:
+            todo, self._deferred = self._deferred, None
         if not todo:
             return
         L = lib()
@@ -440,7 +446,7 @@ class PolicyEngine:
         self._gemm(a3t[r0:], self.flat_dim, 1, self.seg("fc.w"), self.flat_dim, 1, feat[r0:], ldf, n, H, self.flat_dim,
                    bias=self.seg("fc.b"), relu=1, b_param=True)
 
-    def _trunk_backward_rows(self, obs, r0, r1, cols, off, cols_valid, dfeat, ldd, acc):
+    def _trunk_backward_rows(self, obs, r0, r1, cols, off, cols_valid, dfeat, ldd, acc, after_fc=None):
         """rows [r0, r1): dfeat (already masked by feat > 0) -> FC / conv gradients, written to (acc=0, first chunk) or
         added to (acc=1) the flat gradient buffer.  Weight / bias gradients run on the side stream."""
         L = lib()
@@ -463,6 +469,8 @@ class PolicyEngine:
             with self._Side(self):
                 self._gemm(dfeat[r0:], ldd, 0, a3t[r0:], fd, 0, self.seg("fc.w", True), fd, H, fd, n, acc=acc)
                 self._colsum(dfeat[r0:], ldd, n, H, self.seg("fc.b", True), acc)
+                if after_fc is not None:
+                    after_fc()          # every gradient from fc.w to the end of the flat buffer is enqueued on the side stream
             self._gemm(dfeat[r0:], ldd, 1, self.seg("fc.w"), fd, 0, da3t[r0:], fd, n, fd, H, mask=a3t[r0:], ldm=fd, b_param=True)
             check(L.ppd_batched_transpose(da3t[r0:].data_ptr(), n, 32, s3 * s3, dy3[r0:].data_ptr(), self.stream), "transpose")
             g3, g2, g1 = ConvGeom(n, s2, s2, 64, 3, 3, 1), ConvGeom(n, s1, s1, 32, 4, 4, 2), ConvGeom(n, hw, hw, C, 8, 8, 4)
@@ -606,11 +614,15 @@ class PolicyEngine:
 
     # ------------------------------------------------------------------ training minibatch
     def train_minibatch(self, sample, clip_param, value_coef, entropy_coef, use_clipped_value_loss=True,
-                        global_rows=None, xcat_prefilled=None, loss="ppo"):
+                        global_rows=None, xcat_prefilled=None, loss="ppo", grad_ready=None):
         """Forward, fused loss forward+backward, full backward for one minibatch.  loss="ppo": PKG/algo/ppo.py:57-81;
         loss="a2c": PKG/algo/a2c_acktr.py:49-52,71-72 (old_v / old_logp / adv of `sample` are unused and may be None).
         Leaves d(loss)/d(params) in the flat gradient buffer and the three loss partial sums at its tail; nothing is
-        synchronised with the host."""
+        synchronised with the host.
+        grad_ready(lo, hi): optional callback, called with the CURRENT stream being the one on which flat_grad[lo:hi] becomes final.
+        Data-parallel training uses it to all-reduce the gradient in two buckets: [fc.w, end) -- FC, GRU and head gradients plus
+        the loss partials, 97 % of the bytes, final before the convolution backward starts -- overlaps the convolution backward;
+        [0, fc.w) follows at the end.  Without the callback (or when the minibatch is cut into chunks) nothing changes."""
         obs, vobs, h0, actions, old_v, ret, masks, old_logp, adv = sample
         out = self.forward(obs, vobs, h0, masks, keep=True, xcat_prefilled=xcat_prefilled)
         L = lib()
@@ -644,6 +656,16 @@ class PolicyEngine:
             self._colsum(dz, A + 1, B, A + 1, self.seg("heads.b", True))
         chunks, cols = sv["chunks"], sv["cols"]
         dfeat = self.buf("t_dfeat", B, H)
+        # early gradient bucket [fc.w, end): only when the minibatch is one chunk (every gradient is written exactly once)
+        early = grad_ready is not None and len(chunks) == 1 and self._deferred is not None and self.precision == "tf32x3"
+        fc_off = self.segs["fc.w"].off
+
+        def early_bucket():
+            # (called on the side stream, after the FC weight gradient) bias sums of the bucket, then hand the range over
+            self._flush_colsums(from_off=fc_off)
+            if self.recurrent:
+                self.seg("gru.b_hh", True)[:2 * H].copy_(self.seg("gru.b_ih", True)[:2 * H])
+            grad_ready(fc_off, self.flat_grad.numel())
         if self.recurrent:
             T, E, Ipad = sv["T"], sv["E"], self.Ipad
             dhs = self.buf("t_dhs", B, H)
@@ -659,6 +681,21 @@ class PolicyEngine:
                 ev = torch.cuda.Event()
                 ev.record(main)
                 gstream.wait_event(ev)
+            # ---- GRU parameter gradients over all T*E rows (side stream; dgi complete because main waited for it)
+            def gru_param_grads():
+                with self._Side(self):
+                    hm = self.buf("t_hm", B, H)
+                    check(L.ppd_gru_masked_prev(hs.data_ptr(), sv["h0"].data_ptr(), m.data_ptr(), T, E, H,
+                                                hm.data_ptr(), self.stream), "masked_prev")
+                    gw_hh = self.seg("gru.w_hh", True)
+                    self._gemm(dgi, 3 * H, 0, xcat, Ipad, 0, self.seg("gru.w_ih", True), Ipad, 3 * H, Ipad, B)
+                    self._colsum(dgi, 3 * H, B, 3 * H, self.seg("gru.b_ih", True))
+                    self._gemm(dgi, 3 * H, 0, hm, H, 0, gw_hh, H, 2 * H, H, B)                    # r, z rows of dW_hh
+                    self._gemm(dghn, H, 0, hm, H, 0, gw_hh[2 * H * H:], H, H, H, B)                # n rows
+                    gb_hh = self.seg("gru.b_hh", True)
+                    if self._deferred is None:
+                        gb_hh[:2 * H].copy_(self.seg("gru.b_ih", True)[:2 * H])                  # same sums for r, z
+                    self._colsum(dghn, H, B, H, gb_hh[2 * H:])
             # BPTT runs over the time chunks from the last to the first on the GRU stream; as soon as a chunk's dgi is
             # there, the main stream back-propagates that chunk through the FC / conv trunk while the GRU continues
             for ci in range(len(chunks) - 1, -1, -1):
@@ -683,35 +720,28 @@ class PolicyEngine:
                     main.wait_event(ev)
                 # d(feat) = dgi W_ih[:, :H], masked by feat > 0 (ReLU of the FC layer)
                 self._gemm(dgi[r0:], 3 * H, 1, w_ih, Ipad, 0, dfeat[r0:], H, n, H, 3 * H, mask=xcat[r0:], ldm=Ipad, b_param=True)
+                if early:
+                    gru_param_grads()          # before the convolution backward: the early gradient bucket is complete sooner
                 self._trunk_backward_rows(sv["obs"], r0, r1, cols, r0 if cols[3] else 0, cols[3], dfeat, H,
-                                          0 if ci == len(chunks) - 1 else 1)
-            # ---- GRU parameter gradients over all T*E rows (side stream; dgi complete because main waited for it)
-            with self._Side(self):
-                hm = self.buf("t_hm", B, H)
-                check(L.ppd_gru_masked_prev(hs.data_ptr(), sv["h0"].data_ptr(), m.data_ptr(), T, E, H,
-                                            hm.data_ptr(), self.stream), "masked_prev")
-                gw_hh = self.seg("gru.w_hh", True)
-                self._gemm(dgi, 3 * H, 0, xcat, Ipad, 0, self.seg("gru.w_ih", True), Ipad, 3 * H, Ipad, B)
-                self._colsum(dgi, 3 * H, B, 3 * H, self.seg("gru.b_ih", True))
-                self._gemm(dgi, 3 * H, 0, hm, H, 0, gw_hh, H, 2 * H, H, B)                    # r, z rows of dW_hh
-                self._gemm(dghn, H, 0, hm, H, 0, gw_hh[2 * H * H:], H, H, H, B)                # n rows
-                gb_hh = self.seg("gru.b_hh", True)
-                if self._deferred is None:
-                    gb_hh[:2 * H].copy_(self.seg("gru.b_ih", True)[:2 * H])                  # same sums for r, z
-                self._colsum(dghn, H, B, H, gb_hh[2 * H:])
+                                          0 if ci == len(chunks) - 1 else 1, after_fc=early_bucket if early else None)
+            if not early:
+                gru_param_grads()
         else:
             self._gemm(dz, A + 1, 1, self.seg("heads.w"), H, 0, dfeat, H, B, H, A + 1, mask=feats, ldm=H)
             for ci, (r0, r1) in enumerate(chunks):
-                self._trunk_backward_rows(sv["obs"], r0, r1, cols, r0 if cols[3] else 0, cols[3], dfeat, H, 0 if ci == 0 else 1)
+                self._trunk_backward_rows(sv["obs"], r0, r1, cols, r0 if cols[3] else 0, cols[3], dfeat, H, 0 if ci == 0 else 1,
+                                          after_fc=early_bucket if early else None)
         if self._deferred is not None:
             gb = None
-            if self.recurrent:      # b_hh's r,z sums equal b_ih's: drop that copy from the deferred list's dependencies
+            if self.recurrent and not early:      # b_hh's r,z sums equal b_ih's: drop that copy from the deferred list's dependencies
                 gb = (self.seg("gru.b_hh", True), self.seg("gru.b_ih", True))
             with self._Side(self):
                 self._flush_colsums()
                 if gb is not None:
                     gb[0][:2 * H].copy_(gb[1][:2 * H])
         self._join()
+        if grad_ready is not None:
+            grad_ready(0, fc_off if early else self.flat_grad.numel())          # the remaining bucket (or, without overlap, everything)
         return out
 
     # ------------------------------------------------------------------ optimiser

@@ -204,3 +204,36 @@ def test_state_dict_roundtrip_and_rebind():
     assert torch.equal(pol2.get_value(obs, vo, h, m), v0)
     pol.cpu(); pol.to(DEV)                       # moving the module drops the views; the engine re-binds
     assert torch.equal(pol.get_value(obs, vo, h, m), v0)
+
+
+def test_early_gradient_bucket_is_final_when_handed_over():
+    """Data-parallel overlap (engine.train_minibatch(grad_ready=...)): the bucket [fc.w, end) is handed over before the convolution
+    backward runs.  A snapshot taken on the hand-over stream must already equal the final gradient, the two buckets must tile the
+    buffer, and the gradients must be bit-identical to the run without the callback."""
+    torch.manual_seed(0)
+    pol = ppd.Policy((3, 84, 84), Discrete(8), base_kwargs={"recurrent": True}, vector_obs_len=15).to(DEV)
+    eng = pol.engine("tf32x3")
+    T, E = 16, 4
+    cfg = synthetic.RolloutConfig("t", T, E, 3, 15, 8, True, 1, 1, 1e-4, 0.001)
+    roll = synthetic.make_rollout(cfg, seed=3, reset_prob=0.05)
+    B = T * E
+    gen = torch.Generator().manual_seed(1)
+    dd = lambda t: t.to(DEV)
+    sample = (dd(roll["obs"][:T].reshape(B, 3, 84, 84)), dd(roll["vector_obs"][:T].reshape(B, 15)), dd(roll["recurrent_hidden_states"][0]),
+              dd(roll["actions"].reshape(B, 1)), dd(0.1 * torch.randn(B, 1, generator=gen)), dd(0.3 * torch.randn(B, 1, generator=gen)),
+              dd(roll["masks"][:T].reshape(B, 1)), dd(roll["action_log_probs"].reshape(B, 1)), dd(torch.randn(B, 1, generator=gen)))
+    eng.train_minibatch(sample, 0.1, 0.5, 0.001)
+    torch.cuda.synchronize()
+    want = eng.flat_grad.clone()
+    snaps = []
+
+    def grad_ready(lo, hi):
+        snaps.append((lo, hi, eng.flat_grad[lo:hi].clone()))          # on the stream the range became final on
+    eng.train_minibatch(sample, 0.1, 0.5, 0.001, grad_ready=grad_ready)
+    torch.cuda.synchronize()
+    assert torch.equal(eng.flat_grad, want)
+    assert len(snaps) == 2
+    (lo1, hi1, s1), (lo0, hi0, s0) = snaps
+    assert lo1 == eng.segs["fc.w"].off and hi1 == eng.flat_grad.numel() and lo0 == 0 and hi0 == lo1
+    assert torch.equal(s1, want[lo1:hi1]) and torch.equal(s0, want[lo0:hi0])
+    assert (hi1 - lo1) / eng.flat_grad.numel() > 0.95
