@@ -386,6 +386,8 @@ def run_b200(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the gradient all-reduce overlaps the convolution backward, whose persistent kernels leave it PPD_COMM_CTAS SMs (default 8)
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("PPD_COMM_CTAS", "8"))
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
     obs_mode = obs_mode_of(args, cfg)

@@ -297,7 +297,9 @@ int ppd_relu_mask(float* x, const float* act, int64_t n, void* stream);
 /* Tuning / A-B switches (defaults in brackets): 0 / [1] two co-resident CTAs for the narrow tiles of the non-persistent kernel;
  * 32 / 64 / 128 / 256 / [-1] force its tile width; 2 / [3] its TMEM-A mode; 4 / [5] non-persistent / persistent kernel for 3xTF32;
  * 6 / [7] implicit convolutions with one im2col box per row and k-block / with the input staged once per tile; 8 / [9] streamed /
- * shared-memory-resident weight tiles in the convolutions. */
+ * shared-memory-resident weight tiles in the convolutions; 1000 + n: at most n CTAs for the persistent kernel ([1000] = one per SM) --
+ * a data-parallel caller lowers it while an NCCL all-reduce is in flight so that both kernels are resident instead of the collective
+ * delaying a statically scheduled CTA. */
 void ppd_tc_gemm_set_option(int option);
 /* out[j] (+)= sum_i X[i*ld + j]  (bias gradients) */
 size_t ppd_colsum_workspace(int64_t I, int64_t J);

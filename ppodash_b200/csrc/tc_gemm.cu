@@ -582,6 +582,7 @@ extern "C" void ppd_tc_gemm_set_option(int v) {
     else if (v == 8 || v == 9) ppd::tca::g_b_resident = v - 8;
     else if (v == 32 || v == 64 || v == 128 || v == 256) g_force_bn = v;
     else if (v == -1) g_force_bn = 0;
+    else if (v >= 1000 && v <= 1000 + ppd::kNumSMs) ppd::tca::g_max_ctas = (v == 1000) ? ppd::kNumSMs : v - 1000;
 }
 
 extern "C" size_t ppd_tc_gemm_workspace(int64_t I, int64_t J, int64_t KK) {

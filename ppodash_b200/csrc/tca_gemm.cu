@@ -1124,6 +1124,7 @@ int make_map_2d(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, i
     return 0;
 }
 
+int g_max_ctas = kNumSMs;     // CTAs of the persistent kernel (one per SM); lowered while a collective needs SMs of its own
 int g_b_resident = 1;         // convolutions keep the weight tiles of all k-blocks in shared memory when they fit
 int g_conv_resident = 1;      // forward NHWC convolutions stage their input once per tile (ConvA mode 6); 0 = one im2col box per row and k-block (mode 1)
 // N-D fp32 tensor map (dims / strides innermost first; strides in bytes for dims 1..nd-1), OOB elements read as zero.
@@ -1149,7 +1150,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     PPD_REQUIRE(sb_stages >= 2, "shared memory: no room for the B ring");
     a.sb_stages = sb_stages;
     const size_t smem = a_region + (size_t)sb_stages * 2 * a.bn * BK * 4 + 1024;
-    const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+    const int grid = a.total_items < g_max_ctas ? a.total_items : g_max_ctas;
     cudaError_t e = launch_kernel(grid, smem, s, tmA, tmB, tmBlo, a);
     if (e != cudaSuccess) { set_error("tca conv: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
     return launch_status("tca_gemm_kernel(conv)");
@@ -1370,7 +1371,7 @@ int conv_wgrad(const float* x, const ppd_conv_geom* g, int nchw, const float* dy
     if (sb_stages > 8) sb_stages = 8;
     a.sb_stages = sb_stages;
     const size_t smem = (size_t)kSA * BM * BK * 4 + (size_t)sb_stages * 2 * a.bn * BK * 4 + 1024;
-    const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+    const int grid = a.total_items < g_max_ctas ? a.total_items : g_max_ctas;
     cudaError_t e = launch_kernel(grid, smem, s, tmA, tmB, tmB, a);
     if (e != cudaSuccess) { set_error("tca conv: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
     if (splits_out) *splits_out = splits;
@@ -1434,7 +1435,7 @@ int launch(const ppd_gemm_args* g, int transpose_out, const float* b_lo, void* w
     if (sb_stages > 8) sb_stages = 8;
     a.sb_stages = sb_stages;
     const size_t smem = (size_t)kSA * BM * BK * 4 + (size_t)sb_stages * 2 * p.bn * BK * 4 + 1024;
-    const int grid = a.total_items < kNumSMs ? a.total_items : kNumSMs;
+    const int grid = a.total_items < g_max_ctas ? a.total_items : g_max_ctas;
     {
         cudaError_t e = launch_kernel(grid, smem, s, tmA, tmB, tmBlo, a);
         if (e != cudaSuccess) { set_error("tca_gemm: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }

@@ -98,7 +98,7 @@ struct Args {
     ConvA conv;
 };
 
-extern int g_conv_resident, g_b_resident;
+extern int g_conv_resident, g_b_resident, g_max_ctas;
 
 struct Plan { int bn, num_m, num_n, splits; int64_t kk_per_split; size_t ws; };
 

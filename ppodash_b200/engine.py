@@ -98,6 +98,9 @@ class PolicyEngine:
         self._side = None
         self._gru_stream = None
         self._deferred = None
+        # SMs left to an in-flight gradient all-reduce during the convolution backward (data parallel only); pair it with
+        # NCCL_MAX_CTAS of the same value.  0 = persistent kernels keep all SMs.
+        self.comm_ctas = int(os.environ.get("PPD_COMM_CTAS", "8"))
 
     # ------------------------------------------------------------------ parameters
     PRECISIONS = ("fp32", "tf32x3", "tf32")
@@ -666,6 +669,10 @@ class PolicyEngine:
             if self.recurrent:
                 self.seg("gru.b_hh", True)[:2 * H].copy_(self.seg("gru.b_ih", True)[:2 * H])
             grad_ready(fc_off, self.flat_grad.numel())
+            # leave SMs to the collective while the convolution backward runs: a persistent kernel that fills all 148 SMs would
+            # make the NCCL kernel wait for a kernel boundary and then delay one of the next kernel's statically scheduled CTAs
+            if self.comm_ctas:
+                L.ppd_tc_gemm_set_option(1000 + 148 - self.comm_ctas)
         if self.recurrent:
             T, E, Ipad = sv["T"], sv["E"], self.Ipad
             dhs = self.buf("t_dhs", B, H)
@@ -741,6 +748,8 @@ class PolicyEngine:
                     gb[0][:2 * H].copy_(gb[1][:2 * H])
         self._join()
         if grad_ready is not None:
+            if early and self.comm_ctas:
+                L.ppd_tc_gemm_set_option(1000)
             grad_ready(0, fc_off if early else self.flat_grad.numel())          # the remaining bucket (or, without overlap, everything)
         return out
 
