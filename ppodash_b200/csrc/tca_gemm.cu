@@ -1307,7 +1307,7 @@ static void wgrad_plan(const ppd_conv_geom* g, int Cout, int nchw, ConvA& cv, in
     cv.total_seg = g->B * OH * cv.spr;
     cv.total_kb = (cv.total_seg + cv.nseg - 1) / cv.nseg;
     num_m = (cv.nchunks + 1) / 2;
-    splits = kNumSMs / num_m;
+    splits = g_max_ctas / num_m;            // one wave of the CTAs the kernel may use
     if (splits > cv.total_kb / 8) splits = cv.total_kb / 8;
     if (splits < 1) splits = 1;
     // tcgen05 accumulates with truncation, so the error of an accumulator grows with the length of its chain: a 2048-sample
@@ -1387,15 +1387,15 @@ Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_avail, bool limit) {
     const int64_t tiles = (int64_t)p.num_n * p.num_m;
     const int64_t nkb = (KK + BK - 1) / BK;
     int64_t splits = 1;
-    if (tiles < kNumSMs) {
-        splits = kNumSMs / tiles;                   // fill the SMs once; every split keeps >= 4 k-blocks
+    if (tiles < g_max_ctas) {
+        splits = g_max_ctas / tiles;                // fill the SMs once; every split keeps >= 4 k-blocks
         if (splits > nkb / 4) splits = nkb / 4;
         if (splits < 1) splits = 1;
     }
     // tcgen05 accumulates with truncation: with ONE accumulator a chain of KK/8 x 3 accumulate steps lost ~1.2e-5 (relative) at
     // KK ~ 1500.  The main / correction accumulator pair sees a third of the steps per accumulator (4e-6 at KK = 1568, inside the
     // 1e-5 gate), so chains are only cut beyond 64 k-blocks (2048), where the output is small enough for the partials to be cheap.
-    if (KK > 2048 && tiles <= 2 * kNumSMs && splits < (nkb + 63) / 64) splits = (nkb + 63) / 64;
+    if (KK > 2048 && tiles <= 2 * g_max_ctas && splits < (nkb + 63) / 64) splits = (nkb + 63) / 64;
     if (limit) {
         while (splits > 1 && (size_t)splits * I * J * sizeof(float) > ws_avail) --splits;
     }
