@@ -361,11 +361,18 @@ def tca_roofline(cfg, pk, top_ms, top_calls, rows_mb):
         import glob
         files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_tca_traffic.json")))
         tr = json.load(open(files[-1]))
-        roof["traffic"] = tr["avg_dram_bytes_per_launch"] * top_calls
-        head = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
-        roof["traffic_note"] = (f"dram__bytes_read+write.sum averaged over {tr['launches']} consecutive launches (ncu --set full, "
-                                f"{os.path.basename(files[-1])}, kernel source as of commit {tr.get('commit', 'unknown')}; HEAD {head or 'n/a'}) x "
-                                f"{top_calls} launches per step")
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from ncu_summary import kernel_source_sha256
+        same = tr.get("kernel_source_sha256") == kernel_source_sha256()
+        if same:
+            roof["traffic"] = tr["avg_dram_bytes_per_launch"] * top_calls
+            roof["traffic_note"] = (f"dram__bytes_read+write.sum averaged over {tr['launches']} consecutive launches of one bench step (ncu, "
+                                    f"{os.path.basename(files[-1])}; taken from the kernel sources this run was built from: sha256 matches) x "
+                                    f"{top_calls} launches per step")
+        else:
+            # a capture of other kernel sources says nothing about this build: report no traffic rather than a stale one
+            roof["traffic_note"] = (f"STALE: {os.path.basename(files[-1])} was captured from other tca_gemm sources than this tree holds "
+                                    f"(kernel_source_sha256 differs); re-run tools/profile_gpu.sh and tools/ncu_summary.py traffic")
     except Exception:
         pass
     return roof, tf

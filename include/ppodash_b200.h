@@ -349,11 +349,13 @@ int ppd_gru_backward(const float* dhs, const float* masks, const float* w_hh, co
                      void* stream);
 int ppd_gru_masked_prev(const float* hs, const float* h0, const float* masks, int T, int E, int H,
                         float* hm, void* stream);
-/* Kernel selection for the two calls above: 0 (default) = thread-block-cluster / DSMEM kernels when
- * E <= 8 and H % 16 == 0 (one 16-CTA cluster per env, W_hh slices resident in shared memory, one
- * mbarrier handshake per step; at H = 512 the W_hh slice lives in registers), else the grid-cooperative
- * kernels; 1 = always grid-cooperative; 2 = cluster kernels with the W_hh slice in shared memory even at
- * H = 512 (the generic-H variant, kept selectable for testing). */
+/* Kernel selection for the two calls above: 0 (default) = thread-block-cluster / DSMEM kernels when H % 16 == 0 (one 16-CTA
+ * cluster per env, one mbarrier handshake per step; at H = 512 the W_hh slice lives in registers and any E runs as waves of
+ * clusters, with the BACKWARD pass of E >= 9 envs on persistent clusters that interleave up to four envs each; generic H: W_hh
+ * slices in shared memory, E <= 8), else the grid-cooperative kernels; 1 = always grid-cooperative; 2 = cluster kernels with the
+ * W_hh slice in shared memory even at H = 512 (the generic-H variant, kept selectable for testing); 3 = the interleaved-env
+ * backward kernel for every E; 4 = one cluster per env for every E; 100 + n = the interleaved kernel assumes n resident clusters
+ * (0 = ask the occupancy API; tuning / tests). */
 void ppd_gru_set_mode(int mode);
 
 #ifdef __cplusplus

@@ -95,6 +95,13 @@ class PPO():
         # data parallel: None -> use the default process group if one is initialised with >1 ranks
         self.process_group = process_group
         self.last_grad_norm = None
+        self.prefetch_gather = True       # gather minibatch i+1 on a side stream while minibatch i trains (update())
+        self._side = None
+
+    def _gather_stream(self, dev):
+        if self._side is None or self._side.device != torch.device(dev):
+            self._side = torch.cuda.Stream(device=dev)
+        return self._side
 
     def _world(self):
         return ppd_dist.world(self.process_group)[0]
@@ -127,13 +134,61 @@ class PPO():
         gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.optimizer.max_grad_norm = self.max_grad_norm
 
-        for e in range(self.ppo_epoch):
-            if pol.is_recurrent:
-                data_generator = rollouts.recurrent_generator(advantages, self.num_mini_batch)
-            else:
-                data_generator = rollouts.feed_forward_generator(advantages, self.num_mini_batch)
-            for sample in data_generator:
-                rows = sample[0].shape[0]
+        def all_samples():
+            for e in range(self.ppo_epoch):
+                if pol.is_recurrent:
+                    data_generator = rollouts.recurrent_generator(advantages, self.num_mini_batch)
+                else:
+                    data_generator = rollouts.feed_forward_generator(advantages, self.num_mini_batch)
+                for sample in data_generator:
+                    yield sample
+
+        # The minibatch gathers depend only on the rollout and the advantage statistics, not on the parameters: minibatch i+1 is
+        # gathered on a side stream while minibatch i trains -- queued behind the point where its GRU recurrence starts, which
+        # keeps only 16 SMs per env busy (64 of 148), so the HBM-bound gather runs in the idle ones.  The permutations are drawn
+        # in the same order as before (one randperm per epoch, PKG/storage.py:138,169).
+        main = torch.cuda.current_stream(dev)
+        # ... which only pays while the recurrence leaves a good part of the GPU idle (one 16-SM cluster per env of the minibatch):
+        # with many envs per minibatch (or no recurrence) there is nothing to fill, and a second in-flight copy of a multi-GB
+        # minibatch only costs allocator traffic (measured at 128 envs x 512 steps per minibatch: 2.9 -> 4.0 s per update).
+        envs_per_mb = rollouts.rewards.size(1) // self.num_mini_batch
+        use_side = self.prefetch_gather and pol.is_recurrent and 16 * envs_per_mb <= 148 - 32
+        side = self._gather_stream(dev) if use_side else None
+        samples = all_samples()
+
+        def fetch(after=None, first=False):
+            if side is None:
+                s = next(samples, None)
+                return None if s is None else (s, None)
+            with torch.cuda.stream(side):
+                if first:
+                    side.wait_stream(main)            # returns, advantage statistics, last update's writes
+                if after is not None:
+                    side.wait_event(after)
+                s = next(samples, None)
+                if s is None:
+                    return None
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return s, ev
+
+        cur = fetch(first=True)
+        while cur is not None:
+            sample, ev = cur
+            if ev is not None:
+                main.wait_event(ev)
+                for t in sample:
+                    if t is not None:
+                        t.record_stream(main)         # allocated on the side stream, consumed on this one
+            nxt = []
+            if side is not None:
+                def at_gru(_n=nxt):
+                    e0 = torch.cuda.Event()
+                    e0.record(main)
+                    _n.append(fetch(after=e0))
+                eng.on_gru_forward = at_gru
+            rows = sample[0].shape[0]
+            try:
                 if world > 1:
                     # two buckets, all-reduced asynchronously from the stream on which each becomes final: [fc.w, end) (FC, GRU,
                     # heads, loss partials: 97 % of the bytes) overlaps the convolution backward, [0, fc.w) follows at the end
@@ -148,7 +203,12 @@ class PPO():
                 else:
                     eng.train_minibatch(sample, self.clip_param, self.value_loss_coef, self.entropy_coef,
                                         self.use_clipped_value_loss, global_rows=rows)
-                self.optimizer.step(loss_acc=loss_acc, grad_norm_out=gnorm)
+            finally:
+                eng.on_gru_forward = None
+            if not nxt:
+                nxt.append(fetch())               # no recurrence in this network (or a chunked minibatch): gather behind the whole minibatch
+            self.optimizer.step(loss_acc=loss_acc, grad_norm_out=gnorm)
+            cur = nxt[0]
 
         num_updates = self.ppo_epoch * self.num_mini_batch
         vals = (loss_acc / num_updates).tolist()          # the only device->host sync of update()

@@ -28,6 +28,8 @@ int gru_backward_cluster(const float* dhs, const float* masks, const float* w_hh
                          const float* sr, const float* sz, const float* sn, const float* sghn, int T, int E, int H,
                          float* dgi, float* dghn, float* dh0, cudaStream_t s);
 extern int g_reg_kernels;
+extern int g_multi_min_e;
+extern int g_multi_clusters;
 static int g_gru_mode = 0;   // 0 = auto (cluster path when it applies), 1 = always the grid-cooperative kernels
 }  // namespace ppd
 
@@ -342,8 +344,10 @@ extern "C" int ppd_gru_backward(const float* dhs, const float* masks, const floa
 }
 
 extern "C" void ppd_gru_set_mode(int mode) {
+    if (mode >= 100) { ppd::g_multi_clusters = mode - 100; return; }
     ppd::g_gru_mode = (mode == 1) ? 1 : 0;
     ppd::g_reg_kernels = (mode == 2) ? 0 : 1;
+    ppd::g_multi_min_e = (mode == 3) ? 1 : (mode == 4) ? (1 << 30) : 9;
 }
 
 extern "C" int ppd_gru_masked_prev(const float* hs, const float* h0, const float* masks, int T, int E, int H,

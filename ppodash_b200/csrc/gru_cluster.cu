@@ -16,10 +16,13 @@
 // Envs are independent sequences, so E envs run as E clusters side by side (E*16 SMs busy).
 // Global loads of the next step's operands are issued one step ahead (software pipelining).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "ppd_common.cuh"
 
 namespace cg = cooperative_groups;
+
+namespace ppd { extern int g_multi_clusters; }
 
 namespace {
 
@@ -547,6 +550,258 @@ __global__ void __launch_bounds__(kH, 1) gru_bwd_cluster512_kernel(const BwdArgs
     cluster.sync();
 }
 
+// =====================================================================================================
+// Backward over many envs (E > 8, the 128-env minibatches of the 8 x 1024 configuration): PERSISTENT clusters, INTERLEAVED envs.
+// One cluster per env leaves the recurrence latency-bound -- of the ~1700 clocks of a backward step only ~400 are FMAs, the rest
+// is the gate chain of one warp, two block barriers and the DSMEM exchange -- and E envs cost ceil(E / 7 resident clusters)
+// sequential waves of that.  Envs are independent sequences and W_hh is the same for all of them, so here every resident cluster
+// keeps its register copy of W_hh for the whole launch and walks NE env slots in lock step as a two-stage software pipeline:
+//   G(i)  ONE designated warp per slot (warps 12..15: the highest warp id of each scheduler, which the arbiter favours; lane =
+//         hidden unit): carry sum of the 16 received partials, gate backward, the step's results to HBM, the next operands;
+//   M(i)  every warp: the 24 x 4 register-block mat-vec and the reduce-scatter push of the one-env kernel.
+// G runs one slot-step AHEAD of M, so the exchange latency and the gate chain hide behind the other slots' mat-vecs; hand-offs
+// inside the CTA are mbarriers (full / empty per slot), across CTAs st.async + complete_tx as in the one-env kernel.
+// Measured at E = 128, T = 512: 6.2 ms against 8.3 ms for 19 waves of one-env clusters.  The same treatment of the FORWARD
+// recurrence did not pay and is not kept: its mat-vec needs a 12-shuffle butterfly per lane (3 gate rows per hidden unit) and
+// an extra staged hand-off for the coalesced push; three variants (gate phase replicated over the half-warps, on designated
+// warps, as a 3-stage pipeline) ran at 1700-3000 clocks per slot-step, no better than the 1600 of the one-env kernel -- every
+// mbarrier wait costs a warp ~250 clocks even when its phase is already complete, and replicated gate / address arithmetic
+// makes the kernel issue-bound (~350 instructions per warp and slot-step against the 57 of the mat-vec itself; clock64 stamps).
+// (A 17th warp for the gate phase would cap every thread at 96 registers: five warps on one scheduler's 16 K registers.)
+// Buffers are double-buffered by step parity; a CTA can only receive step t-1 data for a buffer after every CTA has consumed
+// step t+1 from it (the same argument as for the one-env kernels).  Rounds (groups of NE envs) are separated by cluster.sync().
+// =====================================================================================================
+constexpr int kMaxNE = 4;
+
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NE>
+__global__ void __launch_bounds__(kH, 1) gru_bwd_multi_kernel(const BwdArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ __align__(16) float dgh[NE][kR];              // d(hidden-side pre-activations) of own units
+    __shared__ float recv[NE][2][CS * kHU];                  // partial dh_{t-1} of own units from every CTA, by step parity
+    __shared__ __align__(8) uint64_t rbar[NE][2], full[NE], empty[NE];
+    const int E = a.E, T = a.T;
+    const int rank = (int)cluster.block_rank();
+    const int NC = gridDim.x / CS, cid = blockIdx.x / CS;
+    const int j0 = rank * kHU;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t step_bytes = CS * kHU * 4;
+    if (tid == 0) {
+        for (int k = 0; k < NE; ++k) {
+            mbar_init(&rbar[k][0], 1); mbar_init(&rbar[k][1], 1);
+            mbar_init(&full[k], 32); mbar_init(&empty[k], kH / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int cg4 = tid >> 2, rq = tid & 3;
+    float2 wc[kR / 4][2];                         // W_hh[own row 24rq + i][4cg4 + (0,1) | (2,3)]
+#pragma unroll
+    for (int i = 0; i < kR / 4; ++i) {
+        const int r = (kR / 4) * rq + i;
+        const int g = r / kHU, uu = r - g * kHU;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.w_hh + (size_t)(g * kH + j0 + uu) * kH + 4 * cg4));
+        wc[i][0] = make_float2(v.x, v.y); wc[i][1] = make_float2(v.z, v.w);
+    }
+    int myslot = -1;
+#pragma unroll
+    for (int k = 0; k < NE; ++k) if (warp == (12 + k)) myslot = k;
+    const int ju = j0 + lane;
+    // thread tid ends up with the partial sum of unit tid: its owner CTA and this CTA's slot in the owner's receive buffers
+    const uint32_t dst_rank = (uint32_t)(tid / kHU);
+    const uint32_t slot = (uint32_t)(rank * kHU + (tid % kHU));
+    uint32_t ph_r = 0, ph_full = 0, ph_empty = 1u;           // rbar bit b and empty of the designated slot; full bit k (all warps)
+    __syncthreads();
+
+    const int n_mine = cid < E ? (E - cid + NC - 1) / NC : 0;
+    const int n_max = (E + NC - 1) / NC;
+    // operands of the designated slot's next gate phase
+    float o_dh = 0.f, o_r = 0.f, o_z = 0.f, o_n = 0.f, o_ghn = 0.f, o_hp = 0.f, o_m = 0.f, dhz = 0.f, m_prev = 0.f;
+    for (int base = 0; base < n_max; base += NE) {
+        const int nact = min(NE, n_mine - base);
+        auto load_ops = [&](int t, int env) {
+            const size_t row = (size_t)t * E + env;
+            o_dh = __ldg(a.dhs + row * kH + ju);
+            o_r = __ldg(a.sr + row * kH + ju); o_z = __ldg(a.sz + row * kH + ju);
+            o_n = __ldg(a.sn + row * kH + ju); o_ghn = __ldg(a.sghn + row * kH + ju);
+            o_m = __ldg(a.masks + row);
+            o_hp = (t == 0) ? __ldg(a.h0 + (size_t)env * kH + ju) : __ldg(a.hs + (row - E) * kH + ju);
+        };
+        for (int k = 0; k < nact; ++k) {
+            if (myslot == k) { load_ops(T - 1, cid + NC * (base + k)); dhz = 0.f; m_prev = 0.f; }
+            if (tid == 0) {
+                mbar_arm(&rbar[k][(T - 1) & 1], step_bytes);
+                if (T > 1) mbar_arm(&rbar[k][(T - 2) & 1], step_bytes);
+            }
+        }
+        __syncthreads();
+        cluster.sync();
+        // carry into step tpush-1 of slot k: the partial sums pushed at step tpush (buffer tpush & 1), summed over the 16 CTAs
+        auto take_carry = [&](const int k, const int tpush) -> float {
+            const int b = tpush & 1;
+            mbar_wait(&rbar[k][b], (ph_r >> b) & 1u);
+            ph_r ^= 1u << b;
+            if (lane == 0 && tpush >= 2) mbar_arm(&rbar[k][b], step_bytes);     // phase complete: arm it for the pushes of step tpush-2
+            const float* rb = &recv[k][b][lane];
+            float v[CS];
+#pragma unroll
+            for (int src = 0; src < CS; ++src) v[src] = rb[src * kHU];
+#pragma unroll
+            for (int w2 = CS / 2; w2 > 0; w2 >>= 1)
+#pragma unroll
+                for (int i = 0; i < w2; ++i) v[i] += v[i + w2];
+            return (v[0] + dhz) * m_prev;
+        };
+        auto gate = [&](const int k, const int t) {              // designated warp of slot k: carry, gate backward, results, next operands
+            const int env = cid + NC * (base + k);
+            const float carry = (t == T - 1) ? 0.f : take_carry(k, t + 1);
+            const float dh = o_dh + carry;
+            const float rg = o_r, z = o_z, n = o_n, ghn = o_ghn;
+            const float m_t = o_m;
+            const float hm = o_hp * m_t;
+            const float dz = dh * (hm - n);
+            const float dn = dh * (1.f - z);
+            const float dpn = dn * (1.f - n * n);
+            const float dpz = dz * z * (1.f - z);
+            const float dpr = (dpn * ghn) * rg * (1.f - rg);
+            const float dgn = dpn * rg;
+            dhz = dh * z; m_prev = m_t;
+            mbar_wait(&empty[k], ph_empty & 1u);                 // the mat-vecs are done with the previous step's values
+            ph_empty ^= 1u;
+            dgh[k][lane] = dpr; dgh[k][kHU + lane] = dpz; dgh[k][2 * kHU + lane] = dgn;
+            mbar_arrive_local(&full[k]);
+            const size_t row = (size_t)t * E + env;
+            float* g = a.dgi + row * 3 * kH;
+            g[ju] = dpr; g[kH + ju] = dpz; g[2 * kH + ju] = dpn;
+            a.dghn[row * kH + ju] = dgn;
+            if (t > 0) load_ops(t - 1, env);
+        };
+        auto matvec = [&](const int k, const int t) {            // partial dh_{t-1}[unit tid] over this CTA's 96 rows, pushed to the unit's owner
+            const int b = t & 1;
+            mbar_wait(&full[k], (ph_full >> k) & 1u);
+            ph_full ^= 1u << k;
+            const float4* d4 = reinterpret_cast<const float4*>(&dgh[k][(kR / 4) * rq]);
+            float2 c01 = make_float2(0.f, 0.f), c23 = c01;
+#pragma unroll
+            for (int i = 0; i < kR / 16; ++i) {
+                const float4 dv = d4[i];
+                const float2 dx = make_float2(dv.x, dv.x), dy = make_float2(dv.y, dv.y), dz = make_float2(dv.z, dv.z), dw = make_float2(dv.w, dv.w);
+                ffma2(c01, dx, wc[4 * i][0]); ffma2(c23, dx, wc[4 * i][1]);
+                ffma2(c01, dy, wc[4 * i + 1][0]); ffma2(c23, dy, wc[4 * i + 1][1]);
+                ffma2(c01, dz, wc[4 * i + 2][0]); ffma2(c23, dz, wc[4 * i + 2][1]);
+                ffma2(c01, dw, wc[4 * i + 3][0]); ffma2(c23, dw, wc[4 * i + 3][1]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_local(&empty[k]);         // dgh[k] has been consumed
+            const float c0 = c01.x, c1 = c01.y, c2 = c23.x, c3 = c23.y;
+            const bool up2 = (rq & 2) != 0;
+            const float k0 = up2 ? c2 : c0, k1 = up2 ? c3 : c1, g0 = up2 ? c0 : c2, g1 = up2 ? c1 : c3;
+            const float r0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 2), r1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 2);
+            const bool up1 = (rq & 1) != 0;
+            const float sum = (up1 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, up1 ? r0 : r1, 1);
+            st_async_f32(map_to_rank(smem_u32(&recv[k][b][slot]), dst_rank), sum, map_to_rank(smem_u32(&rbar[k][b]), dst_rank));
+        };
+        // Software pipeline over the slot-steps i = (T - 1 - t) * nact + k: the gate phase of i + 1 is issued BEFORE the mat-vec of i
+        // (its carry comes from the mat-vec of i + 1 - nact, issued earlier whenever nact > 1)
+        if (nact > 0) {
+            const int n_it = T * nact;
+            int km = 0, tm = T - 1, kg = 0, tg = T - 1;
+            if (nact > 1) {
+                if (warp == 12) gate(0, T - 1);
+                if (++kg == nact) { kg = 0; --tg; }
+            }
+            for (int i = 0; i < n_it; ++i) {
+                if (nact == 1) {
+                    if (warp == 12) gate(0, tm);
+                    matvec(0, tm);
+                    --tm;
+                } else {
+                    if (tg >= 0 && warp == (12 + kg)) gate(kg, tg);
+                    matvec(km, tm);
+                    if (++km == nact) { km = 0; --tm; }
+                    if (++kg == nact) { kg = 0; --tg; }
+                }
+            }
+            // dh0: the carry out of step 0
+            if (myslot >= 0 && myslot < nact) {
+                const float carry = take_carry(myslot, 0);
+                if (a.dh0) a.dh0[(size_t)(cid + NC * (base + myslot)) * kH + ju] = carry;
+            }
+        }
+        cluster.sync();
+    }
+}
+
+// Persistent launch: as many clusters as the device holds (at most one per env), NE envs interleaved per cluster and round.
+template <typename K>
+int launch_multi(K kernel, const void* args_struct, int nclusters, cudaStream_t s, const char* what) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS * nclusters);
+    cfg.blockDim = dim3(kH);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    void* params[] = {const_cast<void*>(args_struct)};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kernel, params);
+    if (e != cudaSuccess) {
+        ppd::set_error("%s: %s", what, cudaGetErrorString(e));
+        cudaGetLastError();
+        return (int)e;
+    }
+    return ppd::launch_status(what);
+}
+
+// resident 16-CTA clusters of the multi-env kernels on this device (0: the cluster launch is not possible)
+template <typename K>
+int multi_clusters(K kernel) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS * 16);
+    cfg.blockDim = dim3(kH);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// envs per cluster and round: the fewest rounds, then the smallest NE that still needs that many
+inline int pick_ne(int E, int nclusters) {
+    const int per = (E + nclusters - 1) / nclusters;
+    const int rounds = (per + kMaxNE - 1) / kMaxNE;
+    return (per + rounds - 1) / rounds;
+}
+
+int multi_backward(const BwdArgs& a, cudaStream_t s) {
+    static int ncl = -1;
+    if (ncl < 0) {
+        ncl = multi_clusters(gru_bwd_multi_kernel<4>);
+        int n;
+        n = multi_clusters(gru_bwd_multi_kernel<3>); if (n < ncl) ncl = n;
+        n = multi_clusters(gru_bwd_multi_kernel<2>); if (n < ncl) ncl = n;
+        n = multi_clusters(gru_bwd_multi_kernel<1>); if (n < ncl) ncl = n;
+    }
+    if (ncl < 1) return -1;
+    const int want = ppd::g_multi_clusters > 0 ? ppd::g_multi_clusters : ncl;
+    const int nc = a.E < want ? a.E : want;
+    switch (pick_ne(a.E, nc)) {
+        case 1: return launch_multi(gru_bwd_multi_kernel<1>, &a, nc, s, "gru_bwd_multi_kernel");
+        case 2: return launch_multi(gru_bwd_multi_kernel<2>, &a, nc, s, "gru_bwd_multi_kernel");
+        case 3: return launch_multi(gru_bwd_multi_kernel<3>, &a, nc, s, "gru_bwd_multi_kernel");
+        default: return launch_multi(gru_bwd_multi_kernel<4>, &a, nc, s, "gru_bwd_multi_kernel");
+    }
+}
+
 size_t fwd_smem(int H) { const int HU = H / CS; return (size_t)(3 * HU * H + 2 * H + 3 * HU + HU) * sizeof(float); }
 size_t bwd_smem(int H) { const int HU = H / CS; return (size_t)(3 * HU * H + 3 * HU + 2 * CS * HU + H) * sizeof(float); }
 
@@ -583,6 +838,8 @@ int launch_cluster(K kernel, const void* args_struct, int threads, int E, size_t
 namespace ppd {
 
 int g_reg_kernels = 1;   // 0 (ppd_gru_set_mode(2)): use the generic shared-memory cluster kernels even at H = 512
+int g_multi_clusters = 0; // resident clusters the persistent kernels assume (0: ask the occupancy API); ppd_gru_set_mode(100 + n)
+int g_multi_min_e = 9;   // H = 512: E >= this runs the persistent interleaved-env BACKWARD kernel (ppd_gru_set_mode(3): every E; (4): never)
 
 // Return 0 on success, -1 if the cluster path does not apply (caller falls back to gru.cu), >0 on CUDA error.
 int gru_forward_cluster(const float* gi, const float* h0, const float* masks, const float* w_hh, const float* b_hh,
@@ -603,8 +860,10 @@ int gru_backward_cluster(const float* dhs, const float* masks, const float* w_hh
                          float* dgi, float* dghn, float* dh0, cudaStream_t s) {
     if ((E > 8 && !(H == kH && g_reg_kernels)) || E > 4095 || H % CS != 0 || H / CS > kThreads || bwd_smem(H) > 227 * 1024) return -1;
     BwdArgs a{dhs, masks, w_hh, h0, hs, sr, sz, sn, sghn, dgi, dghn, dh0, T, E, H};
+    if (H == kH && g_reg_kernels && E >= g_multi_min_e) { const int rc = multi_backward(a, s); if (rc >= 0) return rc; }
     if (H == kH && g_reg_kernels) return launch_cluster(gru_bwd_cluster512_kernel, &a, kH, E, 0, s, "gru_bwd_cluster512_kernel");
     return launch_cluster(gru_bwd_cluster_kernel, &a, kThreads, E, bwd_smem(H), s, "gru_bwd_cluster_kernel");
 }
 
 }  // namespace ppd
+

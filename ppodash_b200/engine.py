@@ -93,6 +93,9 @@ class PolicyEngine:
         # anyway and only pay for smaller GEMMs and repeated W_hh loads.  The chunking itself is what bounds the im2col
         # scratch for large minibatches (E=128: 65 536 rows).
         self.overlap_gru = False
+        # Called on the current stream right before the training forward pass launches the GRU recurrence (16 SMs per env: 64 of
+        # the 148 at 4 envs per minibatch).  algo.PPO uses it to gather the NEXT minibatch on a side stream into those idle SMs.
+        self.on_gru_forward = None
         self.time_chunks = 4
         self.cols_budget = 6 << 30        # bytes of im2col matrices kept from forward for backward
         self._side = None
@@ -589,6 +592,8 @@ class PolicyEngine:
                                             b_hh.data_ptr(), n // E, E, H, hs[r0:].data_ptr(),
                                             hl.data_ptr() if last else None, *svp, self.stream), "gru_forward")
                 if gstream is None:
+                    if keep and self.on_gru_forward is not None:
+                        self.on_gru_forward()          # the recurrence leaves 84 SMs idle: the caller queues independent work behind this point
                     run_gru()
                 else:
                     ev = torch.cuda.Event()

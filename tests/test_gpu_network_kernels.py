@@ -137,12 +137,13 @@ def test_batched_transpose():
     assert torch.equal(y.cpu(), x.transpose(1, 2).contiguous())
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("T,E,H,I", [(5, 3, 32, 35), (16, 4, 512, 527), (1, 32, 512, 527), (4, 40, 64, 64), (64, 4, 512, 527),
-                                     (1, 2, 512, 527), (33, 8, 512, 512), (6, 40, 512, 527)])
+                                     (1, 2, 512, 527), (33, 8, 512, 512), (6, 40, 512, 527), (7, 21, 512, 527), (2, 11, 512, 527), (3, 37, 512, 527)])
 def test_gru_forward_backward_vs_torch(T, E, H, I, mode):
     """mode 0: cluster/DSMEM kernels where they apply (W_hh in registers at H=512: any E, run as waves of clusters; generic H: E <= 8);
-    mode 1: grid-cooperative kernels; mode 2: cluster kernels with W_hh in shared memory."""
+    mode 1: grid-cooperative kernels; mode 2: cluster kernels with W_hh in shared memory; mode 3: the persistent interleaved-env
+    backward kernel (default from E = 9) for every E; mode 4: one cluster per env for every E."""
     _lib.lib().ppd_gru_set_mode(mode)
     try:
         _gru_case(T, E, H, I)

@@ -18,6 +18,10 @@ DEV = "cuda:0"
 def main():
     L = _lib.lib()
     st = _lib.stream_ptr()
+    if os.environ.get("PPD_GRU_MODE"):          # 3: interleaved-env kernels for every E, 4: one cluster per env for every E
+        L.ppd_gru_set_mode(int(os.environ["PPD_GRU_MODE"]))
+    if os.environ.get("PPD_GRU_CLUSTERS"):
+        L.ppd_gru_set_mode(100 + int(os.environ["PPD_GRU_CLUSTERS"]))
     T, E, H = int(os.environ.get("PPD_T", 512)), int(os.environ.get("PPD_E", 4)), 512
     g = torch.Generator().manual_seed(0)
     d = lambda *s, scale=1.0: (scale * torch.randn(*s, generator=g)).to(DEV)

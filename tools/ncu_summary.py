@@ -68,6 +68,17 @@ def full(src, dst):
     print("wrote", dst)
 
 
+def kernel_source_sha256():
+    """sha256 over the sources of the persistent tcgen05 kernel (run this script in the tree the capture was taken from)."""
+    import hashlib
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ppodash_b200", "csrc")
+    h = hashlib.sha256()
+    for name in ("tca_gemm.cu", "tca_gemm.cuh", "tma_utils.cuh"):
+        h.update(open(os.path.join(root, name), "rb").read())
+    return h.hexdigest()
+
+
 def traffic(src, dst, cmd):
     """DRAM bytes and device time of consecutive launches of one kernel family (3 metrics per launch)."""
     import json
@@ -85,7 +96,9 @@ def traffic(src, dst, cmd):
     n = len(per)
     rd, wr, us = (sum(d[k] for d in per.values()) for k in ("read", "write", "us"))
     rec = {"kernel": "tca_gemm_kernel", "launches": n, "dram_bytes_read": rd, "dram_bytes_written": wr,
-           "avg_dram_bytes_per_launch": (rd + wr) / n, "total_us": us, "command": cmd}
+           "avg_dram_bytes_per_launch": (rd + wr) / n, "total_us": us, "command": cmd,
+           # the capture is only meaningful for the kernel sources it was taken from: bench.py compares this with the tree it runs in
+           "kernel_source_sha256": kernel_source_sha256()}
     json.dump(rec, open(dst + ".json", "w"), indent=1)
     with open(dst + ".md", "w") as f:
         f.write(f"# DRAM traffic of `tca_gemm_kernel` over {n} consecutive launches of the bench step\n\n`{cmd}`\n\n")
