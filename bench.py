@@ -321,8 +321,14 @@ def run_c5(ppd, torch, dist, args, world, rank, dev):
     ms = torch.tensor([a.elapsed_time(b)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # attribution on ONE stream (as for the main workload): a weight-gradient kernel timed on the side stream would include the time it
+    # spent queued behind the input-gradient kernel it alternates with
+    eng = pol.engine()
+    ov, eng.overlap_wgrad = eng.overlap_wgrad, False
+    pg, agent.prefetch_gather = agent.prefetch_gather, False
     with _lib.profiled() as prof:
         step()
+    eng.overlap_wgrad, agent.prefetch_gather = ov, pg
     pk = prof.summary()
     ms_step = ms.item() / nsteps
     del st, pol, agent
@@ -503,9 +509,10 @@ def run_b200(args, cfg):
     # time is its own and not the time it spent queued behind a concurrent persistent kernel)
     eng = pol.engine()
     ov, eng.overlap_wgrad = eng.overlap_wgrad, False
+    pg, agent.prefetch_gather = agent.prefetch_gather, False          # (the next minibatch's gather normally runs on a side stream, too)
     with _lib.profiled() as prof:
         step(False)
-    eng.overlap_wgrad = ov
+    eng.overlap_wgrad, agent.prefetch_gather = ov, pg
     per_kernel = prof.summary()
     n_params = eng.n_params
 

@@ -13,6 +13,8 @@ Data-parallel: every rank holds the envs of its shard in its own 
 advantage moments (3 doubles) are all-reduced once per update and the flat gradient buffer (with
 the loss partial sums in its tail) once per minibatch; all ranks then apply the identical step.
 """
+import os
+
 import torch
 
 from .. import _lib
@@ -95,7 +97,8 @@ class PPO():
         # data parallel: None -> use the default process group if one is initialised with >1 ranks
         self.process_group = process_group
         self.last_grad_norm = None
-        self.prefetch_gather = True       # gather minibatch i+1 on a side stream while minibatch i trains (update())
+        # gather minibatch i+1 on a side stream while minibatch i trains (update()); PPD_PREFETCH_GATHER=0 turns it off (A/B timing)
+        self.prefetch_gather = os.environ.get("PPD_PREFETCH_GATHER", "1") != "0"
         self._side = None
 
     def _gather_stream(self, dev):
