@@ -451,15 +451,18 @@ def run_b200(args, cfg):
         barrier()
         a = torch.cuda.Event(enable_timing=True)
         b = torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps)]
         a.record()
-        for _ in range(nsteps):
+        for i in range(nsteps):
             out = step(with_upload)
+            marks[i].record()                      # (every step already ends with a device->host read: no extra synchronisation)
         b.record()
         barrier()
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), out
+        each = [round((a if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 3) for i in range(nsteps)]
+        return ms.item(), out, each
 
     upload()
     st.finish_upload()
@@ -499,9 +502,9 @@ def run_b200(args, cfg):
     if rank == 0:
         sampler.start()
     _lib.reset_launch_count()
-    ms_total, losses = timed(args.steps, False)
+    ms_total, losses, ms_each = timed(args.steps, False)
     launches = _lib.launch_count()
-    ms_e2e = timed(args.steps, True)[0]
+    ms_e2e, _, ms_each_e2e = timed(args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- attribute the step to kernels (one extra, untimed-for-the-metric step with per-call CUDA events)
@@ -575,7 +578,7 @@ def run_b200(args, cfg):
                     note=f"peak = copy bandwidth {pk['how']}")
 
     line = dict(metric="ppo_update_env_steps_per_sec", value=value, unit="env-steps/s", n_gpus=world, steps=args.steps,
-                warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                warmup=args.warmup, ms_per_step=ms_step, ms_each_step=ms_each, ms_each_step_e2e=ms_each_e2e, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype={"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core split, fp32-level accuracy)",
                        "tf32": "tf32"}[args.precision], data="synthetic",
                 config=config_dict(cfg, args, world, obs_mode),

@@ -100,6 +100,7 @@ class PPO():
         # gather minibatch i+1 on a side stream while minibatch i trains (update()); PPD_PREFETCH_GATHER=0 turns it off (A/B timing)
         self.prefetch_gather = os.environ.get("PPD_PREFETCH_GATHER", "1") != "0"
         self._side = None
+        self._gbufs = None
 
     def _gather_stream(self, dev):
         if self._side is None or self._side.device != torch.device(dev):
@@ -157,6 +158,14 @@ class PPO():
         envs_per_mb = rollouts.rewards.size(1) // self.num_mini_batch
         use_side = self.prefetch_gather and pol.is_recurrent and 16 * envs_per_mb <= 148 - 32
         side = self._gather_stream(dev) if use_side else None
+        if side is not None:
+            # two caller-owned observation buffers, used in turn: the gather of minibatch i+2 is queued behind an event of minibatch
+            # i+1's forward pass, i.e. behind every reader of minibatch i
+            rows = rollouts.rewards.size(0) * envs_per_mb
+            shape = (rows,) + tuple(getattr(rollouts, "policy_obs_shape", None) or rollouts.obs.shape[2:])
+            if self._gbufs is None or self._gbufs[0]["obs"].shape != shape or self._gbufs[0]["obs"].device != torch.device(dev):
+                self._gbufs = [{"obs": torch.empty(shape, dtype=torch.float32, device=dev)} for _ in range(2)]
+            rollouts.set_gather_buffers(self._gbufs)
         samples = all_samples()
 
         def fetch(after=None, first=False):
@@ -175,6 +184,17 @@ class PPO():
                 ev.record(side)
             return s, ev
 
+        try:
+            self._run_minibatches(fetch, main, side, eng, world, loss_acc, gnorm)
+        finally:
+            if side is not None:
+                rollouts.set_gather_buffers(None)
+        num_updates = self.ppo_epoch * self.num_mini_batch
+        vals = (loss_acc / num_updates).tolist()          # the only device->host sync of update()
+        self.last_grad_norm = gnorm
+        return vals[0], vals[1], vals[2]
+
+    def _run_minibatches(self, fetch, main, side, eng, world, loss_acc, gnorm):
         cur = fetch(first=True)
         while cur is not None:
             sample, ev = cur
@@ -209,11 +229,12 @@ class PPO():
             finally:
                 eng.on_gru_forward = None
             if not nxt:
-                nxt.append(fetch())               # no recurrence in this network (or a chunked minibatch): gather behind the whole minibatch
+                # no recurrence in this network, or a chunked minibatch: gather behind the whole minibatch (the event keeps the side
+                # stream behind the readers of the buffer it is about to overwrite)
+                e1 = None
+                if side is not None:
+                    e1 = torch.cuda.Event()
+                    e1.record(main)
+                nxt.append(fetch(after=e1))
             self.optimizer.step(loss_acc=loss_acc, grad_norm_out=gnorm)
             cur = nxt[0]
-
-        num_updates = self.ppo_epoch * self.num_mini_batch
-        vals = (loss_acc / num_updates).tolist()          # the only device->host sync of update()
-        self.last_grad_norm = gnorm
-        return vals[0], vals[1], vals[2]

@@ -14,13 +14,14 @@
 //
 // One CTA per SM, persistent over (m tile, n tile, k split) work items; 16 warps:
 //   warp 0      TMA producer of A (ring of kSA x 16 KB: deep enough to cover the HBM latency at full bandwidth)
-//   warp 1      MMA issuer; owns the TMEM allocation (512 columns: 2 tiles x [main | correction] accumulators, 4 A stages x 64)
+//   warp 1      MMA issuer; owns the TMEM allocation (512 columns: 2 tiles x [main | correction] accumulators, 2 A slots x 128 = two k-blocks each)
 //   warp 2      TMA producer of B (ring of [hi | lo] tiles), independent of the A ring
 //   warps 4-11  transform: smem A tile -> registers -> hi/lo -> TMEM A stage (and the split of B in shared
 //               memory when the caller has no pre-split copy of it)
 //   warps 12-15 epilogue: tcgen05.ld of the finished accumulator while the next tile's MMAs fill the other
 // Every hand-off is an mbarrier; tcgen05.commit releases B stages, TMEM A stages and accumulators.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "ppd_common.cuh"
 #include "tca_gemm.cuh"
@@ -220,6 +221,13 @@ struct Ring {
 };
 
 // Pipeline timeline of CTA 0 (debug builds only: -DPPD_TCA_TRACE): trace[(it * 16 + slot)] = clock64()
+#ifdef PPD_TCA_TRACE2
+// low-perturbation timeline: clock64 stamps go to SHARED memory (CS2R + STS), CTA 0 dumps them after its last tile
+__device__ unsigned g_trace2[24 * 8 + 8];     // + entry / exit / first issue / first epilogue stamps
+#define TR2(it_, slot_) do { if (blockIdx.x == 0 && lane == 0 && (it_) >= 32u && (it_) < 56u) tr2[((it_) - 32u) * 8u + (slot_)] = (unsigned)clock64(); } while (0)
+#else
+#define TR2(it_, slot_) do { } while (0)
+#endif
 #ifdef PPD_TCA_TRACE
 __device__ long long* g_trace = nullptr;
 #define TCA_TRACE(it_, slot_) do { if (g_trace && blockIdx.x == 0 && (it_) < 256 && lane == 0) g_trace[(it_) * 16 + (slot_)] = clock64(); } while (0)
@@ -308,6 +316,11 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ __align__(8) uint64_t ta_full[kTA], ta_empty[kTA], acc_full[2], acc_empty[2];
     __shared__ __align__(8) uint64_t bs_full[kMaxSB];   // weight gradients: B stage split into [hi | lo] by the epilogue warps
     __shared__ uint32_t tmem_base_slot;
+#ifdef PPD_TCA_TRACE2
+    __shared__ unsigned tr2[24 * 8 + 8];
+    for (int i = threadIdx.x; i < 24 * 8 + 8; i += blockDim.x) tr2[i] = 0;
+    if (threadIdx.x == 0) tr2[24 * 8] = (unsigned)clock64();
+#endif
     __shared__ int tap_line[kMaxTaps];                  // modes 6 / 7: line offset of k-block kb inside the tile's stage
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -355,6 +368,10 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    // programmatic dependent launch: let the next kernel of the stream start its own prologue as SMs free up, and wait here for the
+    // previous kernel (and its memory) before the first global access of any role
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0 && mode == 0) {
         // ================= TMA producer, A tiles of a plain GEMM: one box per stage
@@ -651,43 +668,72 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint64_t bdesc0 = a.b_mn ? make_desc(smem_u32(smemB), 4096, 512, kLayoutSw128Base32)
                                        : make_desc(smem_u32(smemB), 0, 1024, kLayoutSw128);
         const uint32_t kstep = a.b_mn ? (1024u >> 4) : (32u >> 4);          // descriptor start-address step per 8 k
-        uint32_t it = 0, tile_it = 0, epoch = 0;
+        uint32_t it = 0, tile_it = 0, epoch = 0, pit = 0;
         int loaded_cls = -1;
         Ring rb;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
+#ifdef PPD_TCA_TRACE2
+            if (blockIdx.x == 0 && lane == 0 && tile_it == 7) tr2[24 * 8 + 6] = (unsigned)clock64();
+#endif
             const Item t = decode<MODE>(a, w);
             const bool reload = !a.b_resident || t.cls != loaded_cls;
             // resident B: its stages are released only when this CTA's NEXT tile needs other weights
             const int wn = w + gridDim.x;
             const bool release = !a.b_resident || (wn < a.total_items && decode<MODE>(a, wn).cls != t.cls);
             const uint32_t acc = tile_it & 1u;
+#ifdef PPD_TCA_TRACE2
+            if (blockIdx.x == 0 && lane == 0 && tile_it == 7) tr2[24 * 8 + 7] = (unsigned)clock64();
+#endif
             mbar_wait(&acc_empty[acc], ((tile_it >> 1) & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d = tmem_base + kAccCol0 + acc * kAccStride;
-            for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB)) {
-                const uint32_t ts = it % kTA, s = a.b_resident ? (uint32_t)kb : rb.s;
-                mbar_wait(&ta_full[ts], (it / kTA) & 1u);
-                if (a.b_presplit && reload) mbar_wait(&full_b[s], a.b_resident ? (epoch & 1u) : rb.ph);
-                if (esb) mbar_wait(&bs_full[s], rb.ph);
+            // k-blocks are handed over in PAIRS (one tensor-memory slot of 128 columns = two k-blocks, filled by ONE transform group):
+            // one ta_full wait, one fence, one election and one ta_empty commit per 16 MMAs.  Every mbarrier wait costs this warp
+            // 150-250 clocks even when its phase is long complete, and the issuer's loop is one of the two serial chains a k-block
+            // passes through.
+            const int npairs = (t.nkb + 1) >> 1;
+            for (int pp = 0; pp < npairs; ++pp, ++pit) {
+                const int nh = min(2, t.nkb - 2 * pp);
+                const uint32_t slot = pit % kTP;
+#ifdef PPD_TCA_TRACE2
+                if (blockIdx.x == 0 && lane == 0 && pit == 0) tr2[24 * 8 + 2] = (unsigned)clock64();
+#endif
+                TR2(it, 5);
+                mbar_wait(&ta_full[slot], (pit / kTP) & 1u);
+                uint32_t sh[2];
+                for (int h = 0; h < nh; ++h) {
+                    const int kb = 2 * pp + h;
+                    const uint32_t s = a.b_resident ? (uint32_t)kb : rb.s;
+                    sh[h] = s;
+                    if (a.b_presplit && reload) mbar_wait(&full_b[s], a.b_resident ? (epoch & 1u) : rb.ph);
+                    if (esb) mbar_wait(&bs_full[s], rb.ph);
+                    rb.next(kSB);
+                }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                TR2(it, 6);
                 if (elect_one()) {
                     TCA_TRACE1(it, 8);
-                    const uint64_t db = bdesc0 + (uint64_t)((s * 2u * b_bytes) >> 4);
-                    const uint32_t ta = tmem_base + kTaCol0 + ts * 64u;
+                    for (int h = 0; h < nh; ++h) {
+                        const int kb = 2 * pp + h;
+                        const uint64_t db = bdesc0 + (uint64_t)((sh[h] * 2u * b_bytes) >> 4);
+                        const uint32_t ta = tmem_base + kTaCol0 + slot * 128u + (uint32_t)h * 64u;
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
+                        for (int k = 0; k < BK / 8; ++k) {
 #ifndef PPD_ABL_NOMMA
-                        umma_tf32_ts(d, ta + k * 8u, db + (uint64_t)(k * kstep), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32_ts(d, ta + k * 8u, db + (uint64_t)(k * kstep), idesc2, (kb > 0 || k > 0) ? 1u : 0u);
 #ifndef PPD_ABL_ONEMMA
-                        umma_tf32_ts(d + (uint32_t)bn, ta + 32u + k * 8u, db + (uint64_t)(k * kstep), idesc1, 1u);
+                            umma_tf32_ts(d + (uint32_t)bn, ta + 32u + k * 8u, db + (uint64_t)(k * kstep), idesc1, 1u);
 #endif
 #endif
+                        }
+                        if (release) umma_commit(&empty_b[sh[h]]);
                     }
-                    umma_commit(&ta_empty[ts]);
-                    if (release) umma_commit(&empty_b[s]);
+                    umma_commit(&ta_empty[slot]);
                     TCA_TRACE1(it, 9);
                 }
                 __syncwarp();
+                TR2(it, 7);
+                it += (uint32_t)nh;
             }
             if (elect_one()) umma_commit(&acc_full[acc]);
             __syncwarp();
@@ -703,15 +749,21 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int r = q * 32 + lane;
         const int gt = (threadIdx.x - 128) & 127;     // thread index within the group
         const uint32_t smemA_u = smem_u32(smemA), smemB_u = smem_u32(smemB);
-        uint32_t it = 0, tile_it = 0;
-        int turn = 0;                                  // it % kGroups
+        uint32_t it = 0, tile_it = 0, pit = 0;
+        int turn = 0;                                  // pit % kGroups
         Ring rb;
         // per-thread constants of the convolution modes (row r of the tile = pixel ox of tile row g): no division in the loops
         const int g_r = mode ? r / max(a.conv.segw, 1) : 0, ox_r = mode ? r - g_r * a.conv.segw : 0;
         const uint32_t row4 = (uint32_t)a.conv.Win * 4u;
         const uint32_t off4 = mode == 4 ? (uint32_t)(g_r * (32 / max(a.conv.KW, 1)) * a.conv.Win + ox_r * a.conv.s) * 4u : 0u;
         for (int w = blockIdx.x; w < a.total_items; w += gridDim.x, ++tile_it) {
+#ifdef PPD_TCA_TRACE2
+            if (blockIdx.x == 0 && lane == 0 && q == 0 && grp == 0 && tile_it == 7) tr2[24 * 8 + 4] = (unsigned)clock64();
+#endif
             const Item t = decode<MODE>(a, w);
+#ifdef PPD_TCA_TRACE2
+            if (blockIdx.x == 0 && lane == 0 && q == 0 && grp == 0 && tile_it == 7) tr2[24 * 8 + 5] = (unsigned)clock64();
+#endif
             const bool ok4 = g_r < t.nvalid;
             // mode 6 (tile-resident raw input): this thread's pixel is line `line0` of the stage for tap (0, 0); wait for the stage once
             uint32_t line0 = 0, stage6 = 0;
@@ -735,11 +787,25 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 stage6 = smemA_u + (tile_it & 1u) * cv.tile_stage_bytes;
                 mbar_wait(&full_a[tile_it & 1u], (tile_it >> 1) & 1u);
             }
-            for (int kb = 0; kb < t.nkb; ++kb, ++it, rb.next(kSB), turn = (turn + 1 == kGroups) ? 0 : turn + 1) {
-                if (turn != grp) continue;
+            // k-blocks are taken in PAIRS: one tensor-memory slot (128 columns), one ta_empty wait, one wait::st / fence / arrive and one
+            // trip around this loop per TWO k-blocks -- the fixed latencies of a hand-off, not the split arithmetic, are what a transform
+            // group's time per k-block is made of
+            const int npairs = (t.nkb + 1) >> 1;
+            for (int pp = 0; pp < npairs; ++pp, ++pit, turn = (turn + 1 == kGroups) ? 0 : turn + 1) {
+                const int nh = min(2, t.nkb - 2 * pp);
+                if (turn != grp) {
+                    it += (uint32_t)nh;
+                    for (int h = 0; h < nh; ++h) rb.next(kSB);
+                    continue;
+                }
+                const uint32_t slot = pit % kTP;
+                for (int h = 0; h < nh; ++h, ++it, rb.next(kSB)) {
+                const int kb = 2 * pp + h;
                 const uint32_t s = it % kSA;
                 if (q == 0) TCA_TRACE(it, 2);
+                if (q == 0) TR2(it, 0);
                 if (!resident) mbar_wait(&full_a[s], (it / kSA) & 1u);
+                if (q == 0) TR2(it, 1);
                 if (q == 0) TCA_TRACE(it, 3);
                 const uint32_t sa = smemA_u + s * a_bytes;
                 float x[32];
@@ -834,11 +900,14 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 __syncwarp();
                 if (lane == 0 && !resident) mbar_arrive(&empty_a[s]);          // the tile is in registers: slot back to the producer
                 if (q == 0) TCA_TRACE(it, 4);
-                const uint32_t ts = it % kTA;
-                mbar_wait(&ta_empty[ts], ((it / kTA) & 1u) ^ 1u);
+                if (q == 0) TR2(it, 2);
+                if (h == 0) {
+                    mbar_wait(&ta_empty[slot], ((pit / kTP) & 1u) ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                if (q == 0) TR2(it, 3);
                 if (q == 0) TCA_TRACE(it, 5);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kTaCol0 + ts * 64u;
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kTaCol0 + slot * 128u + (uint32_t)h * 64u;
 #if defined(PPD_ABL_NOSTTM)
                 if (hi[0] == 0x12345678u) tmem_st16(ta, hi);
 #elif defined(PPD_ST32)
@@ -871,11 +940,13 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 }
+                }       // k-blocks of the pair
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ta_full[ts]);
-                if (q == 0) TCA_TRACE(it, 7);
+                if (lane == 0) mbar_arrive(&ta_full[slot]);
+                if (q == 0) TR2(it - 1, 4);
+                if (q == 0) TCA_TRACE(it - 1, 7);
             }
             if (resident) {                            // every read of this warp from the tile's stage is done
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic reads before the async-proxy refill
@@ -913,6 +984,9 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             }
             mbar_wait(&acc_full[acc], (tile_it >> 1) & 1u);
+#ifdef PPD_TCA_TRACE2
+            if (blockIdx.x == 0 && lane == 0 && q == 0 && tile_it == 0) tr2[24 * 8 + 3] = (unsigned)clock64();
+#endif
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t i = t.i0 + q * 32 + lane;
             bool row_ok = i < a.I;
@@ -937,8 +1011,12 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 {
                     float u[32];
                     const uint32_t tad = tmem_base + ((uint32_t)(q * 32) << 16) + kAccCol0 + acc * kAccStride + (uint32_t)c0;
+#ifdef PPD_ABL_NOLDTM
+                    for (int c = 0; c < 32; ++c) { u[c] = 0.f; v[c] = __uint_as_float(tad + c); }     // timing experiment: no TMEM reads
+#else
                     tmem_ld32(tad + (uint32_t)bn, u);
                     tmem_ld32(tad, v);
+#endif
 #pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] += u[c];
                 }
@@ -1000,7 +1078,28 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const float* mrow = a.mask ? a.mask + mrow_off + c0 : nullptr;
                     const bool vec = (jb + 31 < a.J) && ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) &&
                                      (!mrow || (((a.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)));
-                    if (vec) {
+                    const bool vec8 = vec && !a.accumulate && ((reinterpret_cast<uintptr_t>(crow) & 31) == 0) &&
+                                      (!mrow || ((reinterpret_cast<uintptr_t>(mrow) & 31) == 0));
+                    if (vec8) {
+                        // A thread owns a row, so every store instruction of a warp touches 32 different cache lines: the LSU handles
+                        // one line per clock, and those clocks are taken from the transform warps' shared-memory reads and tcgen05.st
+                        // (clock64 stamps: a ~1000-clock bubble in the transform AND the issuer once per tile, gone with the stores
+                        // removed).  256-bit accesses (sm_100) halve the instruction count: 4 x 32 lines per row block instead of 8 x 32.
+#pragma unroll
+                        for (int c = 0; c < 32; c += 8) {
+                            if (mrow) {
+                                float m[8];
+                                asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                             : "=f"(m[0]), "=f"(m[1]), "=f"(m[2]), "=f"(m[3]), "=f"(m[4]), "=f"(m[5]), "=f"(m[6]), "=f"(m[7])
+                                             : "l"(mrow + c));
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[c + e] = m[e] > 0.f ? v[c + e] : 0.f;
+                            }
+                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(crow + c), "f"(v[c]), "f"(v[c + 1]),
+                                         "f"(v[c + 2]), "f"(v[c + 3]), "f"(v[c + 4]), "f"(v[c + 5]), "f"(v[c + 6]), "f"(v[c + 7])
+                                         : "memory");
+                        }
+                    } else if (vec) {
 #pragma unroll
                         for (int c = 0; c < 32; c += 4) {
                             float4 x = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
@@ -1029,11 +1128,22 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+#ifdef PPD_TCA_TRACE2
+    if (blockIdx.x == 0) if (threadIdx.x == 0) tr2[24 * 8 + 1] = (unsigned)clock64();
+    __syncthreads();
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < 24 * 8 + 8; i += blockDim.x) g_trace2[i] = tr2[i];
+#endif
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
+// PPD_PDL=0 launches without the programmatic-serialisation attribute (A/B timing)
+static int pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PPD_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
 // One instantiation per operand layout (ConvA::mode; 5 = weight gradient over raw rows).
 template <int MODE>
 cudaError_t launch_mode(int grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
@@ -1044,8 +1154,18 @@ cudaError_t launch_mode(int grid, size_t smem, cudaStream_t s, const CUtensorMap
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    tca_gemm_kernel<MODE><<<grid, kThreads, smem, s>>>(tmA, tmB, tmBlo, a);
-    return cudaSuccess;
+    // Programmatic dependent launch: this kernel's CTAs may start (barrier init, TMEM allocation, tensor-map prefetch, work decode)
+    // while the previous kernel of the stream drains; griddepcontrol.wait in the kernel orders every global access behind it.
+    // 126.9 -> 124.8 ms per PPO update (1088 launches of this kernel), losses bit-identical.  The same treatment of the ~11 000 small
+    // launches of an update (reductions, transposes, SIMT GEMMs, loss, gathers) was measured too and made it 0.6 ms SLOWER: their
+    // early-scheduled CTAs only occupy SMs that the side streams' kernels could have used.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tca_gemm_kernel<MODE>, tmA, tmB, tmBlo, a);
 }
 cudaError_t launch_kernel(int grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
                           const Args& a) {
@@ -1079,6 +1199,11 @@ EncodeTiledFn encode_fn() {
 
 }  // namespace
 
+#ifdef PPD_TCA_TRACE2
+extern "C" int ppd_tca_trace2_read(unsigned* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_trace2, sizeof(unsigned) * (24 * 8 + 8));
+}
+#endif
 #ifdef PPD_TCA_TRACE
 extern "C" int ppd_tca_set_trace(void* dev_ptr) {
     return (int)cudaMemcpyToSymbol(g_trace, &dev_ptr, sizeof(void*));

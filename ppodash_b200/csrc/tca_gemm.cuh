@@ -14,7 +14,8 @@ constexpr int kMaxTaps = 64;       // k-blocks of a tile-resident convolution (m
 constexpr int kMaxSB = 18;         // shared-memory B stages ([hi | lo] each): a ring of as many as fit (at most 8), or all k-blocks resident
 constexpr size_t kSmemBudget = 225 * 1024;
 constexpr int kMaxChainKb = 176;   // weight gradients: k-blocks accumulated into one TMEM accumulator before the partial tile is flushed
-constexpr int kTA = 4;             // tensor-memory A stages (64 columns each: 32 hi + 32 lo)
+constexpr int kTA = 4;             // tensor-memory A stages (64 columns each: 32 hi + 32 lo) ...
+constexpr int kTP = kTA / 2;       // ... handed over in pairs: slots of two stages (two k-blocks), filled by one transform group
 #ifndef PPD_GROUPS
 #define PPD_GROUPS 2
 #endif

@@ -289,7 +289,7 @@ class RolloutStorage(object):
         """Fill one minibatch; returns the 9-tuple in the reference's order (storage.py:159-160)."""
         T, N = self.rewards.size(0), self.rewards.size(1)
         dev = self.obs.device
-        o = out or {}
+        o = out or self._next_gather_buffers(rows) or {}
         if self.obs_u8:
             obs_b = o.get("obs") if "obs" in o else torch.empty((rows,) + self.policy_obs_shape, dtype=torch.float32, device=dev)
         else:
@@ -345,6 +345,23 @@ class RolloutStorage(object):
                                             stream_ptr(dev))
         check(rc, "minibatch gather")
         return obs_b, vobs_b, hxs_b, act_b, val_b, ret_b, msk_b, lp_b, adv_b
+
+    def set_gather_buffers(self, buffers):
+        """Caller-owned output buffers for the generators, used in rotation (None: allocate per minibatch, the default).  `buffers`:
+        list of dicts {"obs": float32 [rows, *policy obs shape]}.  algo.PPO gathers minibatch i+1 on a side stream while minibatch i
+        trains and hands two sets over, so that no 100-MB block crosses streams through the caching allocator."""
+        self._gather_bufs = list(buffers) if buffers else None
+        self._gather_buf_i = 0
+
+    def _next_gather_buffers(self, rows):
+        bufs = getattr(self, "_gather_bufs", None)
+        if not bufs:
+            return None
+        b = bufs[self._gather_buf_i % len(bufs)]
+        if b["obs"].shape[0] != rows:
+            return None
+        self._gather_buf_i += 1
+        return b
 
     @staticmethod
     def _perm_to_device(perm, device):
