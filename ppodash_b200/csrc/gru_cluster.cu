@@ -324,8 +324,20 @@ __device__ __forceinline__ void ffma2(float2& c, const float2 a, const float2 b)
     c = *reinterpret_cast<float2*>(&cc);
 }
 
+#ifdef PPD_GRU_TRACE
+// clock stamps into shared memory (CS2R + STS; a traced step is ~14 % longer), dumped at exit: [kernel][step - 256][slot], CTA 0,
+// thread 0 (gate warp) / first thread of the last warp.  tools/probes/gru_trace.py
+__device__ unsigned g_gru_trace[2][32][8];
+#define GRU_TR(tt, slot) do { if (blockIdx.x == 0 && (tt) >= 256 && (tt) < 288) trs[((tt) - 256) * 8 + (slot)] = (unsigned)clock64(); } while (0)
+#else
+#define GRU_TR(tt, slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(const FwdArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
+#ifdef PPD_GRU_TRACE
+    __shared__ unsigned trs[32 * 8];
+#endif
     __shared__ __align__(16) float hb[2][kNC * kCPad];    // masked previous state, padded chunks, double-buffered
     __shared__ float gh[kR];
     __shared__ float stage[kHU];
@@ -374,7 +386,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(cons
 
     for (int t = 0; t < a.T; ++t) {
         const float* hcur = hb[t & 1];
+        if (tid == 0) GRU_TR(t, 0);
         if (t > 0) mbar_wait(&hbar[t & 1], (uint32_t)((t - 1) >> 1) & 1u);
+        if (tid == 0) GRU_TR(t, 1);
+        if (tid == kFwdThreads - 32) GRU_TR(t, 6);
         // ---- 4 x 32 block of the mat-vec: every state value read from shared memory feeds four rows
         {
             const float4* h4 = reinterpret_cast<const float4*>(hcur + cc * kCPad);
@@ -402,7 +417,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(cons
                 if ((cc & 3) == 0) gh[4 * rg + ((cc >> 3) & 1) * 2 + ((cc >> 2) & 1)] = acc;
             }
         }
+        if (tid == 0) GRU_TR(t, 2);
+        if (tid == kFwdThreads - 32) GRU_TR(t, 7);
         __syncthreads();
+        if (tid == 0) GRU_TR(t, 3);
         const size_t row = (size_t)t * E + env;
         if (gate_thread) {
             const float ghr = gh[tid] + bh_r, ghz = gh[kHU + tid] + bh_z, ghn = gh[2 * kHU + tid] + bh_n;
@@ -428,7 +446,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(cons
             }
         }
         if (t + 1 == a.T) break;
+        if (tid == 0) GRU_TR(t, 4);
         __syncthreads();
+        if (tid == 0) GRU_TR(t, 5);
         if (tid == 0 && t >= 1 && t + 2 < a.T) mbar_arm(&hbar[t & 1], step_bytes);
         {
             const uint32_t local_base = smem_u32(&hb[(t + 1) & 1][0]);
@@ -441,10 +461,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) gru_fwd_cluster512_kernel(cons
         }
     }
     cluster.sync();
+#ifdef PPD_GRU_TRACE
+    if (blockIdx.x == 0) for (int i = tid; i < 32 * 8; i += kFwdThreads) (&g_gru_trace[0][0][0])[i] = trs[i];
+#endif
 }
 
 __global__ void __launch_bounds__(kH, 1) gru_bwd_cluster512_kernel(const BwdArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
+#ifdef PPD_GRU_TRACE
+    __shared__ unsigned trs[32 * 8];
+#endif
     __shared__ __align__(16) float dgh[kR];
     __shared__ float recv[2][CS * kHU];
     __shared__ __align__(8) uint64_t rbar[2];
@@ -492,6 +518,7 @@ __global__ void __launch_bounds__(kH, 1) gru_bwd_cluster512_kernel(const BwdArgs
     for (int t = a.T - 1; t >= 0; --t) {
         const size_t row = (size_t)t * E + env;
         float dhz = 0.f, m_t = 0.f;
+        if (tid == 0) GRU_TR(a.T - 1 - t, 0);
         if (gate_thread) {
             const float dh = p_dh + carry;
             const float rg = p_r, z = p_z, n = p_n, ghn = p_ghn;
@@ -510,7 +537,9 @@ __global__ void __launch_bounds__(kH, 1) gru_bwd_cluster512_kernel(const BwdArgs
             dhz = dh * z;
             if (t > 0) prefetch(t - 1);
         }
+        if (tid == 0) GRU_TR(a.T - 1 - t, 1);
         __syncthreads();
+        if (tid == 0) GRU_TR(a.T - 1 - t, 2);
         // ---- partial dh_{t-1}[k] over this CTA's 96 rows
         float s;
         {
@@ -535,8 +564,11 @@ __global__ void __launch_bounds__(kH, 1) gru_bwd_cluster512_kernel(const BwdArgs
             s = (up1 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, up1 ? r0 : r1, 1);
         }
         // ---- reduce-scatter: push to the owner of unit k
+        if (tid == 0) GRU_TR(a.T - 1 - t, 3);
         st_async_f32(map_to_rank(smem_u32(&recv[t & 1][slot]), dst_rank), s, map_to_rank(smem_u32(&rbar[t & 1]), dst_rank));
+        if (tid == 0) GRU_TR(a.T - 1 - t, 4);
         mbar_wait(&rbar[t & 1], (uint32_t)((a.T - 1 - t) >> 1) & 1u);
+        if (tid == 0) GRU_TR(a.T - 1 - t, 5);
         if (gate_thread) {
             float acc = 0.f;
 #pragma unroll
@@ -544,10 +576,15 @@ __global__ void __launch_bounds__(kH, 1) gru_bwd_cluster512_kernel(const BwdArgs
             carry = (acc + dhz) * m_t;
             if (t == 0 && a.dh0) a.dh0[(size_t)env * kH + ju] = carry;
         }
+        if (tid == 0) GRU_TR(a.T - 1 - t, 6);
         __syncthreads();           // dgh and recv[t&1] are free again
+        if (tid == 0) GRU_TR(a.T - 1 - t, 7);
         if (tid == 0 && t >= 2) mbar_arm(&rbar[t & 1], step_bytes);
     }
     cluster.sync();
+#ifdef PPD_GRU_TRACE
+    if (blockIdx.x == 0) for (int i = tid; i < 32 * 8; i += kH) (&g_gru_trace[1][0][0])[i] = trs[i];
+#endif
 }
 
 // =====================================================================================================
@@ -867,3 +904,10 @@ int gru_backward_cluster(const float* dhs, const float* masks, const float* w_hh
 
 }  // namespace ppd
 
+
+#ifdef PPD_GRU_TRACE
+// Trace builds only (tools/probes/gru_trace.py)
+extern "C" int ppd_gru_trace_read(unsigned* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_gru_trace, sizeof(unsigned) * 2 * 32 * 8);
+}
+#endif
