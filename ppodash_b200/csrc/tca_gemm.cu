@@ -304,7 +304,7 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
 template <int MODE>       // ConvA::mode, as a compile-time constant (5 = mode 3 with raw rows): one lean kernel per operand layout
 __global__ void __launch_bounds__(kThreads, 1)
 tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmBlo, const Args a) {
+                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC, const Args a) {
     constexpr int mode = MODE == 5 ? 3 : MODE;
     constexpr bool raw = MODE == 5;
     // Weight gradients (modes 3 / 5) of the N = 32 layers: the activation B tile is split into [hi | lo] by the four EPILOGUE warps,
@@ -348,6 +348,7 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         if (a.b_presplit) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+        if (a.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     }
     if ((mode == 6 || mode == 7) && (int)threadIdx.x >= 64 && (int)threadIdx.x - 64 < a.conv.nkb) {
         // k-block kb = (channel plane, filter column, filter row), planes fastest.  Forward: tap (ky, kx) is lw*ky + kx lines
@@ -988,6 +989,11 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (blockIdx.x == 0 && lane == 0 && q == 0 && tile_it == 0) tr2[24 * 8 + 3] = (unsigned)clock64();
 #endif
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (a.tma_store) {
+                // the staging tile is free again once the previous tile's bulk store has READ it (issued by warp 12's lane 0)
+                if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             const int64_t i = t.i0 + q * 32 + lane;
             bool row_ok = i < a.I;
             int64_t crow_off = i * a.ldc + t.j0, mrow_off = i * a.ldm + t.j0;
@@ -1062,7 +1068,53 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
                 }
-                if (a.transpose_out) {
+                if (a.tma_store) {
+                    if (a.mask && row_ok) {                 // dgrad: ReLU mask of the activation this gradient flows into (same rows as dx)
+                        const float* mrow = a.mask + mrow_off + c0;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 8) {
+                            float m[8];
+                            asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=f"(m[0]), "=f"(m[1]), "=f"(m[2]), "=f"(m[3]), "=f"(m[4]), "=f"(m[5]), "=f"(m[6]), "=f"(m[7])
+                                         : "l"(mrow + c));
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[c + e] = m[e] > 0.f ? v[c + e] : 0.f;
+                        }
+                    }
+                    // Row r of the tile -> 128-byte row r of the staging tile of this 32-column block, 16-byte chunk c at position
+                    // c ^ (r & 7) (the 128B swizzle of the output tensor map: conflict-free for the 8 lanes of a store phase).  The
+                    // global write is ONE bulk tensor store per block: no LSU line-per-lane traffic at all.
+                    const int r = q * 32 + lane;
+                    const uint32_t srow = smem_u32(smem) + a.stage_off + (uint32_t)(c0 >> 5) * (BM * 128u) + (uint32_t)r * 128u;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        sts128(srow + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4),
+                               make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3])));
+                    if (c0 + 32 >= bn) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic writes -> async-proxy read
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (q == 0 && lane == 0) {
+                            for (int cb = 0; cb < bn; cb += 32) {
+                                const uint32_t src = smem_u32(smem) + a.stage_off + (uint32_t)(cb >> 5) * (BM * 128u);
+                                if (mode == 0)
+                                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC), "r"(src),
+                                                 "r"((int)t.j0 + cb), "r"((int)t.i0)
+                                                 : "memory");
+                                else if (mode == 2 || mode == 7) {
+                                    // dx seen as {C, j (stride s pixels), segment (stride s rows), px, py}: the tile's pixels of one parity class
+                                    const int py = t.cls / a.conv.s, px = t.cls - py * a.conv.s;
+                                    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tmC),
+                                                 "r"(src), "r"(cb), "r"(0), "r"(t.seg0), "r"(px), "r"(py)
+                                                 : "memory");
+                                } else
+                                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&tmC), "r"(src),
+                                                 "r"(cb), "r"(0), "r"(t.seg0)
+                                                 : "memory");
+                            }
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                } else if (a.transpose_out) {
                     // C is [J, I] row-major: for a fixed column the 32 lanes write 32 consecutive floats
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
@@ -1126,6 +1178,8 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     }
+    // the last bulk store must have completed before the CTA's shared memory goes away (issued by the first epilogue warp's lane 0)
+    if (a.tma_store && warp == 4 + kXformWarps && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
 #ifdef PPD_TCA_TRACE2
@@ -1138,6 +1192,12 @@ tca_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+// PPD_TMA_STORE=0: row-per-thread global stores in every epilogue (A/B timing)
+static int tma_store_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PPD_TMA_STORE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
 // PPD_PDL=0 launches without the programmatic-serialisation attribute (A/B timing)
 static int pdl_enabled() {
     static int v = -1;
@@ -1147,7 +1207,7 @@ static int pdl_enabled() {
 // One instantiation per operand layout (ConvA::mode; 5 = weight gradient over raw rows).
 template <int MODE>
 cudaError_t launch_mode(int grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
-                        const Args& a) {
+                        const CUtensorMap& tmC, const Args& a) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tca_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
@@ -1165,19 +1225,20 @@ cudaError_t launch_mode(int grid, size_t smem, cudaStream_t s, const CUtensorMap
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, tca_gemm_kernel<MODE>, tmA, tmB, tmBlo, a);
+    return cudaLaunchKernelEx(&cfg, tca_gemm_kernel<MODE>, tmA, tmB, tmBlo, tmC, a);
 }
 cudaError_t launch_kernel(int grid, size_t smem, cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
-                          const Args& a) {
+                          const Args& a, const CUtensorMap* tmC_opt = nullptr) {
+    const CUtensorMap& tmC = tmC_opt ? *tmC_opt : tmA;          // (unused unless a.tma_store)
     switch (a.conv.mode == 3 && a.conv.raw ? 5 : a.conv.mode) {
-        case 0: return launch_mode<0>(grid, smem, s, tmA, tmB, tmBlo, a);
-        case 1: return launch_mode<1>(grid, smem, s, tmA, tmB, tmBlo, a);
-        case 2: return launch_mode<2>(grid, smem, s, tmA, tmB, tmBlo, a);
-        case 3: return launch_mode<3>(grid, smem, s, tmA, tmB, tmBlo, a);
-        case 4: return launch_mode<4>(grid, smem, s, tmA, tmB, tmBlo, a);
-        case 5: return launch_mode<5>(grid, smem, s, tmA, tmB, tmBlo, a);
-        case 6: return launch_mode<6>(grid, smem, s, tmA, tmB, tmBlo, a);
-        case 7: return launch_mode<7>(grid, smem, s, tmA, tmB, tmBlo, a);
+        case 0: return launch_mode<0>(grid, smem, s, tmA, tmB, tmBlo, tmC, a);
+        case 1: return launch_mode<1>(grid, smem, s, tmA, tmB, tmBlo, tmC, a);
+        case 2: return launch_mode<2>(grid, smem, s, tmA, tmB, tmBlo, tmC, a);
+        case 3: return launch_mode<3>(grid, smem, s, tmA, tmB, tmBlo, tmC, a);
+        case 4: return launch_mode<4>(grid, smem, s, tmA, tmB, tmBlo, tmC, a);
+        case 5: return launch_mode<5>(grid, smem, s, tmA, tmB, tmBlo, tmC, a);
+        case 6: return launch_mode<6>(grid, smem, s, tmA, tmB, tmBlo, tmC, a);
+        case 7: return launch_mode<7>(grid, smem, s, tmA, tmB, tmBlo, tmC, a);
     }
     return cudaErrorInvalidValue;
 }
@@ -1273,10 +1334,43 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (a.b_resident) sb_stages = a.conv.nkb;
     if (sb_stages > 8 && !a.b_resident) sb_stages = 8;
     PPD_REQUIRE(sb_stages >= 2, "shared memory: no room for the B ring");
+    // Forward convolutions write their tiles with TMA: the epilogue stages the finished tile (128 rows x 32 columns per block) in shared
+    // memory and ONE bulk tensor store per block moves it -- the output tensor seen as {Cout, OW pixels, output rows}, box = the
+    // tile's whole output rows, so the rows past the tile's last valid one are never touched and the tensor bound clips the last tile.
+    CUtensorMap tmC;
+    const size_t stage_bytes = (size_t)(a.bn / 32) * BM * 128;
+    a.tma_store = 0;
+    const bool dgrad_mode = a.conv.mode == 2 || a.conv.mode == 7;
+    if (tma_store_enabled() && (a.conv.mode == 1 || a.conv.mode == 4 || a.conv.mode == 6 || dgrad_mode) && a.ldc == a.J && a.J % 32 == 0) {
+        const size_t b_stage = (size_t)2 * a.bn * BK * 4;
+        if (!a.b_resident)
+            while (sb_stages > 4 && a_region + sb_stages * b_stage + stage_bytes + 1024 > kSmemBudget) --sb_stages;
+        if (a_region + sb_stages * b_stage + stage_bytes + 1024 <= kSmemBudget) {
+            const ConvA& cv = a.conv;
+            int rc;
+            if (dgrad_mode) {
+                // dx [B, Hin, Win, C] with Hin = s Hq, Win = s Wq: pixel (segment sg = b Hq + i, j) of parity class (py, px) is row
+                // s sg + py, pixel s j + px -- {C, j, sg, px, py} with strides {1, s C, s Win C, C, Win C}
+                const cuuint64_t C = (cuuint64_t)a.J, st = (cuuint64_t)cv.s;
+                cuuint64_t dims[5] = {C, (cuuint64_t)cv.segw, (cuuint64_t)cv.nseg_class, st, st};
+                cuuint64_t str[4] = {st * C * 4, st * (cuuint64_t)cv.Win * C * 4, C * 4, (cuuint64_t)cv.Win * C * 4};
+                cuuint32_t box[5] = {32, (cuuint32_t)cv.segw, (cuuint32_t)cv.nseg, 1, 1};
+                rc = make_map_nd(&tmC, a.C, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            } else {
+                cuuint64_t dims[3] = {(cuuint64_t)a.J, (cuuint64_t)cv.segw, (cuuint64_t)(a.I / cv.segw)};
+                cuuint64_t str[2] = {(cuuint64_t)a.J * 4, (cuuint64_t)cv.segw * a.J * 4};
+                cuuint32_t box[3] = {32, (cuuint32_t)cv.segw, (cuuint32_t)cv.nseg};
+                rc = make_map_nd(&tmC, a.C, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+            }
+            if (rc) return rc;
+            a.tma_store = 1;
+            a.stage_off = (uint32_t)(a_region + sb_stages * b_stage);
+        }
+    }
     a.sb_stages = sb_stages;
-    const size_t smem = a_region + (size_t)sb_stages * 2 * a.bn * BK * 4 + 1024;
+    const size_t smem = a_region + (size_t)sb_stages * 2 * a.bn * BK * 4 + (a.tma_store ? stage_bytes : 0) + 1024;
     const int grid = a.total_items < g_max_ctas ? a.total_items : g_max_ctas;
-    cudaError_t e = launch_kernel(grid, smem, s, tmA, tmB, tmBlo, a);
+    cudaError_t e = launch_kernel(grid, smem, s, tmA, tmB, tmBlo, a, a.tma_store ? &tmC : nullptr);
     if (e != cudaSuccess) { set_error("tca conv: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
     return launch_status("tca_gemm_kernel(conv)");
 }
@@ -1558,11 +1652,24 @@ int launch(const ppd_gemm_args* g, int transpose_out, const float* b_lo, void* w
     a.total_items = p.num_m * p.num_n * p.splits;
     int sb_stages = (int)((kSmemBudget - 1024 - (size_t)kSA * BM * BK * 4) / ((size_t)2 * p.bn * BK * 4));
     if (sb_stages > 8) sb_stages = 8;
+    // dense, unmasked, un-split outputs (FC and GRU-projection forward) leave through TMA like the forward convolutions
+    CUtensorMap tmC;
+    const size_t a_region = (size_t)kSA * BM * BK * 4, b_stage = (size_t)2 * p.bn * BK * 4, stage_bytes = (size_t)(p.bn / 32) * BM * 128;
+    a.tma_store = 0;
+    if (tma_store_enabled() && !transpose_out && p.splits == 1 && !g->accumulate && !g->mask && g->ldc == g->J && g->J % 32 == 0 &&
+        !((uintptr_t)g->C & 15)) {
+        while (sb_stages > 4 && a_region + sb_stages * b_stage + stage_bytes + 1024 > kSmemBudget) --sb_stages;
+        if (a_region + sb_stages * b_stage + stage_bytes + 1024 <= kSmemBudget) {
+            if ((rc = make_map_2d(&tmC, g->C, g->I, g->J, g->ldc, 32, BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+            a.tma_store = 1;
+            a.stage_off = (uint32_t)(a_region + sb_stages * b_stage);
+        }
+    }
     a.sb_stages = sb_stages;
-    const size_t smem = (size_t)kSA * BM * BK * 4 + (size_t)sb_stages * 2 * p.bn * BK * 4 + 1024;
+    const size_t smem = a_region + (size_t)sb_stages * b_stage + (a.tma_store ? stage_bytes : 0) + 1024;
     const int grid = a.total_items < g_max_ctas ? a.total_items : g_max_ctas;
     {
-        cudaError_t e = launch_kernel(grid, smem, s, tmA, tmB, tmBlo, a);
+        cudaError_t e = launch_kernel(grid, smem, s, tmA, tmB, tmBlo, a, a.tma_store ? &tmC : nullptr);
         if (e != cudaSuccess) { set_error("tca_gemm: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
     }
     if (plan_out) *plan_out = p;

@@ -96,6 +96,9 @@ struct Args {
     const float* a_ptr;      // A tensor base (1-D bulk copies of the raw-row wgrad)
     uint32_t a_region_bytes; // bytes of the A region of shared memory (0 = kSA stages of 16 KB)
     int b_resident;          // convolutions: the B (weight) tiles of ALL k-blocks stay in shared memory; reloaded only when the tile class changes
+    int tma_store;           // epilogue: stage the finished tile in shared memory (128B-swizzled rows) and write it with ONE TMA store per
+                             // 32-column block instead of row-per-thread global stores (forward convolutions, plain GEMMs without split-K)
+    uint32_t stage_off;      // byte offset of that staging tile in dynamic shared memory (1024-aligned)
     ConvA conv;
 };
 
