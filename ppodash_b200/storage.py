@@ -273,7 +273,9 @@ class RolloutStorage(object):
         nv = next_value.detach().to(device=dev, dtype=torch.float32).reshape(N).contiguous()
         if dev.type != "cuda":
             raise _lib.PpdError("compute_returns needs the storage on a CUDA device (no CPU fallback)")
-        ws = _lib.workspace(lib().ppd_compute_returns_workspace(T, N), dev, "returns", zero=True)
+        # the look-back workspace re-arms itself between calls (epoch counters), which only works for calls that are ordered: one
+        # workspace per stream, so that returns computed concurrently on two streams of a device never share it
+        ws = _lib.workspace(lib().ppd_compute_returns_workspace(T, N), dev, "returns@%x" % stream_ptr(dev), zero=True)
         check(lib().ppd_compute_returns(
             ptr(self.rewards, torch.float32), ptr(self.value_preds, torch.float32),
             ptr(self.masks, torch.float32), ptr(self.bad_masks, torch.float32),
