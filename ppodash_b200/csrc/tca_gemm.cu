@@ -18,8 +18,12 @@
 //   warp 2      TMA producer of B (ring of [hi | lo] tiles), independent of the A ring
 //   warps 4-11  transform: smem A tile -> registers -> hi/lo -> TMEM A stage (and the split of B in shared
 //               memory when the caller has no pre-split copy of it)
-//   warps 12-15 epilogue: tcgen05.ld of the finished accumulator while the next tile's MMAs fill the other
-// Every hand-off is an mbarrier; tcgen05.commit releases B stages, TMEM A stages and accumulators.
+//   warps 12-15 epilogue: tcgen05.ld of the finished accumulator while the next tile's MMAs fill the other; the tile leaves through a
+//               shared-memory staging tile and TMA bulk tensor stores where the output is dense (a thread owns a ROW of the tile, and
+//               row-per-thread global stores cost the LSU one cache line per lane: measured as a ~1000-clock bubble per tile in
+//               the transform warps and the issuer), else through 256-bit row stores
+// Every hand-off is an mbarrier; tcgen05.commit releases B stages, TMEM A stages and accumulators.  k-blocks are handed from the
+// transform groups to the issuer in pairs (one 128-column TMEM slot per group).  Launches are programmatic dependent launches.
 #include <cuda.h>
 #include <stdlib.h>
 

@@ -69,13 +69,17 @@ def full(src, dst):
 
 
 def kernel_source_sha256():
-    """sha256 over the sources of the persistent tcgen05 kernel (run this script in the tree the capture was taken from)."""
+    """sha256 over the sources of the persistent tcgen05 kernel, comments and whitespace ignored (run this script in the tree the
+    capture was taken from)."""
     import hashlib
     import os
     root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ppodash_b200", "csrc")
+    import re
     h = hashlib.sha256()
     for name in ("tca_gemm.cu", "tca_gemm.cuh", "tma_utils.cuh"):
-        h.update(open(os.path.join(root, name), "rb").read())
+        src = open(os.path.join(root, name), encoding="utf-8").read()
+        src = re.sub(r"//[^\n]*", "", src)              # comments and layout do not change the kernel: hash the code only
+        h.update(" ".join(src.split()).encode())
     return h.hexdigest()
 
 
