@@ -249,3 +249,32 @@ def test_early_gradient_bucket_is_final_when_handed_over():
                 a, b = final[sg.off:sg.off + sg.numel], want[sg.off:sg.off + sg.numel]
                 assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()), name
         assert (hi1 - lo1) / eng.flat_grad.numel() > 0.95
+
+
+def test_update_with_prefetched_gathers_is_bit_identical():
+    """PPO.update gathers minibatch i+1 on a side stream (into two buffers it owns) while minibatch i trains; that must not change a
+    single bit of the update: same losses and same parameters as with the gathers on the main stream."""
+    T, N = 32, 8
+    cfg = synthetic.RolloutConfig("t", T, N, 3, 15, 8, True, 2, 4, 1e-4, 0.001)
+    roll = synthetic.make_rollout(cfg, seed=5, reset_prob=0.05)
+    results = []
+    for prefetch in (True, False, True):
+        torch.manual_seed(0)
+        pol = ppd.Policy((3, 84, 84), Discrete(8), base_kwargs={"recurrent": True}, vector_obs_len=15).to(DEV)
+        pol.engine("tf32x3")
+        st = ppd.RolloutStorage(T, N, (3, 84, 84), [15], Discrete(8), 512)
+        for k in ppd.RolloutStorage._FIELDS:
+            getattr(st, k).copy_(roll[k])
+        st.to(DEV)
+        st.compute_returns(roll["next_value"].to(DEV), True, cfg.gamma, cfg.gae_lambda, False)
+        agent = ppd.algo.PPO(pol, cfg.clip_param, cfg.ppo_epoch, cfg.num_mini_batch, cfg.value_loss_coef, cfg.entropy_coef,
+                             lr=cfg.lr, eps=cfg.eps, max_grad_norm=cfg.max_grad_norm)
+        agent.prefetch_gather = prefetch
+        torch.manual_seed(11)
+        out = [agent.update(st) for _ in range(2)]          # the second update re-uses the buffers of the first
+        results.append((out, {k: v.clone() for k, v in pol.state_dict().items()}))
+        assert getattr(st, "_gather_bufs", None) is None      # handed back after every update
+    (o1, p1), (o0, p0), (o2, p2) = results
+    assert o1 == o0 == o2
+    for k in p0:
+        assert torch.equal(p1[k], p0[k]) and torch.equal(p2[k], p0[k]), k
