@@ -347,6 +347,36 @@ __global__ void __launch_bounds__(kThreads) colsum_multi_final_kernel(const Mult
     }
 }
 
+// Very short contractions (the 9-wide policy / value heads' input gradient: dhs[B, 512] = dz[B, 9] . W[9, 512]): a tiled GEMM spends its
+// time filling 128 x 128 tiles for nine multiply-adds per output (13.5 us for the 2048-row minibatch).  Here a thread owns four
+// adjacent outputs: KK broadcast loads of its A row, KK coalesced 16-byte loads of B (L1-resident), 4 KK FMAs, one 16-byte store.
+// A [I, KK] contraction-contiguous, B [KK, J] row-major; same epilogue as the tiled kernel (bias, ReLU mask, relu, accumulate).
+constexpr int kSkinnyK = 16;
+__global__ void __launch_bounds__(kThreads) sgemm_skinny_k_kernel(const Args a) {
+    const int64_t J4 = a.J >> 2, total = a.I * J4;
+    const int KK = (int)a.KK;
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kThreads) {
+        const int64_t i = e / J4, j = (e - i * J4) << 2;
+        const float* arow = a.A + i * a.lda;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int k = 0; k < KK; ++k) {
+            const float av = __ldg(arow + k);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(a.B + (int64_t)k * a.ldb + j));
+            acc.x = fmaf(av, b.x, acc.x); acc.y = fmaf(av, b.y, acc.y); acc.z = fmaf(av, b.z, acc.z); acc.w = fmaf(av, b.w, acc.w);
+        }
+        if (a.bias) { acc.x += __ldg(a.bias + j); acc.y += __ldg(a.bias + j + 1); acc.z += __ldg(a.bias + j + 2); acc.w += __ldg(a.bias + j + 3); }
+        if (a.mask) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(a.mask + i * a.ldm + j));
+            acc.x = m.x > 0.f ? acc.x : 0.f; acc.y = m.y > 0.f ? acc.y : 0.f; acc.z = m.z > 0.f ? acc.z : 0.f; acc.w = m.w > 0.f ? acc.w : 0.f;
+        }
+        if (a.relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        float4* c = reinterpret_cast<float4*>(a.C + i * a.ldc + j);
+        if (a.accumulate) { const float4 o = *c; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+        *c = acc;
+    }
+}
+
 struct Plan { int bi, bj; int64_t gx, gy; int splits; int64_t kk_per_split; size_t ws; };
 
 Plan make_plan(int64_t I, int64_t J, int64_t KK, size_t ws_bytes_avail, bool have_ws_limit) {
@@ -412,6 +442,13 @@ extern "C" int ppd_sgemm(const ppd_gemm_args* g, void* workspace, size_t workspa
     cudaStream_t s = ppd::as_stream(stream);
     dim3 grid((unsigned)p.gx, (unsigned)p.gy, (unsigned)p.splits);
     const bool ak = g->a_kmajor != 0, bk = g->b_kmajor != 0;
+    if (ak && !bk && g->KK <= kSkinnyK && g->J % 4 == 0 && g->ldb % 4 == 0 && g->ldc % 4 == 0 &&
+        !(((uintptr_t)g->B | (uintptr_t)g->C) & 15) && (!g->mask || (g->ldm % 4 == 0 && !((uintptr_t)g->mask & 15)))) {
+        int64_t nb = (g->I * (g->J / 4) + kThreads - 1) / kThreads;
+        if (nb > 16 * ppd::kNumSMs) nb = 16 * ppd::kNumSMs;
+        sgemm_skinny_k_kernel<<<(unsigned)nb, kThreads, 0, s>>>(a);
+        return ppd::launch_status("sgemm_skinny_k_kernel");
+    }
     if (p.bi == 128)      launch_tile<128, 128, 8, 8>(a, grid, s, ak, bk);
     else if (p.bj == 32)  launch_tile<64, 32, 4, 2>(a, grid, s, ak, bk);
     else                  launch_tile<64, 64, 4, 4>(a, grid, s, ak, bk);

@@ -47,7 +47,8 @@ def test_sgemm_forward_nt(M, N, K):
     assert torch.all(C[:, N:] == -5.0)          # never writes outside J
 
 
-@pytest.mark.parametrize("M,N,K", [(5, 3, 7), (300, 64, 512), (2048, 512, 1568), (130, 1536, 527), (1000, 9, 512)])
+@pytest.mark.parametrize("M,N,K", [(5, 3, 7), (300, 64, 512), (2048, 512, 1568), (130, 1536, 527), (1000, 9, 512), (2048, 9, 512), (777, 16, 36),
+                                   (64, 17, 512)])
 def test_sgemm_dgrad_nn_with_relu_mask(M, N, K):
     g = torch.Generator().manual_seed(M * 3 + N + K)
     dY = torch.randn(M, N, generator=g)
