@@ -1227,7 +1227,9 @@ cudaError_t launch_mode(int grid, size_t smem, cudaStream_t s, const CUtensorMap
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    // ... but not while SMs are being left to an in-flight collective (g_max_ctas below the SM count): an early-scheduled dependent's
+    // CTAs would sit on exactly those SMs, spinning in griddepcontrol.wait, and the NCCL kernel would wait for them
+    attr[0].val.programmaticStreamSerializationAllowed = (pdl_enabled() && g_max_ctas >= kNumSMs) ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, tca_gemm_kernel<MODE>, tmA, tmB, tmBlo, tmC, a);
 }
