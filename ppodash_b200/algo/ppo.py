@@ -185,8 +185,10 @@ class PPO():
             return s, ev
 
         try:
+            eng._fast_bind = True                 # the module tree was checked above; it does not change while update() runs
             self._run_minibatches(fetch, main, side, eng, world, loss_acc, gnorm)
         finally:
+            eng._fast_bind = False
             if side is not None:
                 rollouts.set_gather_buffers(None)
         num_updates = self.ppo_epoch * self.num_mini_batch

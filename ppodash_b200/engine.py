@@ -93,6 +93,9 @@ class PolicyEngine:
         # anyway and only pay for smaller GEMMs and repeated W_hh loads.  The chunking itself is what bounds the im2col
         # scratch for large minibatches (E=128: 65 536 rows).
         self.overlap_gru = False
+        self._sp = None                   # cached cudaStream_t of the current stream while train_minibatch runs (see `stream`)
+        self._bound_params = None         # Parameter objects of the last successful bind check
+        self._fast_bind = False           # set by algo.PPO for the duration of one update (see _is_bound)
         # Called on the current stream right before the training forward pass launches the GRU recurrence (16 SMs per env: 64 of
         # the 148 at 4 envs per minibatch).  algo.PPO uses it to gather the NEXT minibatch on a side stream into those idle SMs.
         self.on_gru_forward = None
@@ -152,9 +155,15 @@ class PolicyEngine:
             return False
         lo = self.flat.data_ptr()
         hi = lo + self.flat.numel() * 4
-        for p in self.policy.parameters():
+        # Inside train_minibatch / the optimiser step (64 x 2 calls per update) only the Parameter objects seen by the last full check
+        # are looked at: walking the module tree costs ~30 us of host time per call.  Every entry from outside (PPO.update, act,
+        # state_dict ...) still walks it, so a module that was moved or re-assigned between updates is noticed.
+        params = self._bound_params if (self._sp is not None or self._fast_bind) and self._bound_params is not None else list(self.policy.parameters())
+        for p in params:
             if p.device != self.flat.device or not (lo <= p.data_ptr() < hi):
+                self._bound_params = None
                 return False
+        self._bound_params = params
         return True
 
     def bind(self):
@@ -209,8 +218,29 @@ class PolicyEngine:
     # ------------------------------------------------------------------ streams
     @property
     def stream(self):
-        """cudaStream_t of torch's current stream on this device (kernels are enqueued where torch ops go)."""
-        return _lib.stream_ptr(self.device)
+        """cudaStream_t of torch's current stream on this device (kernels are enqueued where torch ops go).  Inside train_minibatch the
+        pointer is cached (`_sp`, kept in step with the engine's own stream switches): torch.cuda.current_stream() costs ~8 us of host
+        time, there are ~60 launches per minibatch, and with 12 500 launches in a 120-ms update the Python side is what the device waits for."""
+        sp = self._sp
+        return sp if sp is not None else _lib.stream_ptr(self.device)
+
+    def _on_stream(self, stream):
+        """torch.cuda.stream(stream) that keeps the cached pointer in step."""
+        eng = self
+
+        class _Ctx:
+            def __enter__(self_c):
+                self_c.ctx = torch.cuda.stream(stream)
+                self_c.ctx.__enter__()
+                self_c.prev = eng._sp
+                if eng._sp is not None:
+                    eng._sp = stream.cuda_stream
+                return self_c
+
+            def __exit__(self_c, *exc):
+                eng._sp = self_c.prev
+                return self_c.ctx.__exit__(*exc)
+        return _Ctx()
 
     def _ws(self, nbytes, tag):
         # one scratch buffer per (kind, stream): GEMMs running concurrently on two streams must not share split-K partials
@@ -232,7 +262,7 @@ class PolicyEngine:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(eng.device))
             eng._side.wait_event(ev)
-            self.ctx = torch.cuda.stream(eng._side)
+            self.ctx = eng._on_stream(eng._side)
             self.ctx.__enter__()
             return self
 
@@ -599,7 +629,7 @@ class PolicyEngine:
                     ev = torch.cuda.Event()
                     ev.record(main)
                     gstream.wait_event(ev)
-                    with torch.cuda.stream(gstream):
+                    with self._on_stream(gstream):
                         run_gru()
             if gstream is not None:
                 ev = torch.cuda.Event()
@@ -631,6 +661,15 @@ class PolicyEngine:
         Data-parallel training uses it to all-reduce the gradient in two buckets: [fc.w, end) -- FC, GRU and head gradients plus
         the loss partials, 97 % of the bytes, final before the convolution backward starts -- overlaps the convolution backward;
         [0, fc.w) follows at the end.  Without the callback (or when the minibatch is cut into chunks) nothing changes."""
+        self._sp = _lib.stream_ptr(self.device)
+        try:
+            return self._train_minibatch(sample, clip_param, value_coef, entropy_coef, use_clipped_value_loss, global_rows, xcat_prefilled,
+                                         loss, grad_ready)
+        finally:
+            self._sp = None
+
+    def _train_minibatch(self, sample, clip_param, value_coef, entropy_coef, use_clipped_value_loss, global_rows, xcat_prefilled, loss,
+                         grad_ready):
         obs, vobs, h0, actions, old_v, ret, masks, old_logp, adv = sample
         out = self.forward(obs, vobs, h0, masks, keep=True, xcat_prefilled=xcat_prefilled)
         L = lib()
@@ -725,7 +764,7 @@ class PolicyEngine:
                 if gstream is None:
                     run_gru()
                 else:
-                    with torch.cuda.stream(gstream):
+                    with self._on_stream(gstream):
                         run_gru()
                         ev = torch.cuda.Event()
                         ev.record(gstream)
