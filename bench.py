@@ -498,6 +498,15 @@ def run_b200(args, cfg):
 
     for _ in range(args.warmup):
         step(False)
+    # 12 500 Python-issued launches per update keep the host within ~20 % of the device time, so any host pause inside a step shows
+    # (single steps of 130-200 ms were seen on some boxes of the pool).  One candidate is a full-heap garbage collection -- torch alone
+    # leaves a few million tracked objects -- so what exists after the warm-up, which is long-lived, is moved out of the collector's
+    # sight, as a training script would do.  A precaution: on a quiet box it changes nothing (24 steps each way: 121.2-121.4 ms,
+    # slowest step 123.5 / 123.8).  PPD_GC_FREEZE=0: don't.
+    if os.environ.get("PPD_GC_FREEZE", "1") != "0":
+        import gc
+        gc.collect()
+        gc.freeze()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
