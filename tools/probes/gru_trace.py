@@ -1,4 +1,4 @@
-"""Per-phase clock timeline of the one-env register GRU kernels (CTA 0; library built with -DPPD_GRU_TRACE: stamps go to shared memory).
+"""Per-phase clock timeline of the one-env register GRU kernels (CTA 0; instrumented build: make -C ppodash_b200/csrc probes; stamps go to shared memory).
 PPD_LIB=$PWD/ppodash_b200/libppd_grutrace.so python tools/probes/gru_trace.py"""
 import ctypes, os, sys
 import numpy as np

@@ -1,4 +1,4 @@
-"""Low-perturbation timeline of the persistent tcgen05 kernel (library built with -DPPD_TCA_TRACE2: clock64 stamps go to shared
+"""Low-perturbation timeline of the persistent tcgen05 kernel (instrumented build: make -C ppodash_b200/csrc probes; clock64 stamps go to shared
 memory): k-blocks 32..55 of CTA 0.   PPD_LIB=.../libppd_trace2.so python tools/probes/tca_trace2.py <conv1.fwd|conv2.fwd|conv2.dgrad|conv1.wgrad|conv2.wgrad|fc.fwd>"""
 import ctypes, os, sys
 import numpy as np
