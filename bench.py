@@ -513,6 +513,7 @@ def run_b200(args, cfg):
     _lib.reset_launch_count()
     ms_total, losses, ms_each = timed(args.steps, False)
     launches = _lib.launch_count()
+    host_launches = int(_lib.lib().ppd_launch_count())          # issued from Python one by one (the rest were replayed from CUDA graphs)
     ms_e2e, _, ms_each_e2e = timed(args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -601,6 +602,13 @@ def run_b200(args, cfg):
         line["gru"] = dict(fwd_latency_us_per_timestep=1e3 * f["ms"] / (f["calls"] * T), bwd_latency_us_per_timestep=1e3 * b["ms"] / (b["calls"] * T),
                            ms_per_step=f["ms"] + b["ms"], envs_per_minibatch=E,
                            note="T sequential steps per launch: latency-bound at this E; 16-CTA cluster per env, W_hh in registers")
+    mg = getattr(agent, "_graphs", None)
+    line["minibatch_graphs"] = dict(
+        enabled=bool(agent.use_cuda_graph and mg is not None and mg.disabled is None),
+        launches_issued_from_python_per_step=host_launches / args.steps, launches_replayed_per_step=(launches - host_launches) / args.steps,
+        captures=mg.captures if mg else 0, capture_failed=mg.disabled if mg else None,
+        note="PPD_GRAPH=1: forward + loss + backward of a minibatch are two replayed CUDA graphs (ppodash_b200/minibatch_graph.py); the "
+             "gathers, clip + Adam and the returns scan are launched from Python; gpu_launches counts both kinds")
     if parity is not None:
         line["parity_check"] = parity
     if c5 is not None:

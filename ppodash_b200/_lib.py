@@ -201,6 +201,9 @@ def workspace(nbytes, device, tag="default", zero=False):
     return buf
 
 
+_profiling = 0
+
+
 class _Profile:
     """CUDA-event timing of every C-ABI call made while active (used by bench.py to attribute the
     step time to kernels).  Events are recorded on the stream the kernels are launched on."""
@@ -210,6 +213,8 @@ class _Profile:
         self._saved = {}
 
     def __enter__(self):
+        global _profiling
+        _profiling += 1
         handle = lib()
         for name in _PROTOTYPES:
             fn = getattr(handle, name)
@@ -230,6 +235,8 @@ class _Profile:
         return self
 
     def __exit__(self, *exc):
+        global _profiling
+        _profiling -= 1
         handle = lib()
         for name, fn in self._saved.items():
             setattr(handle, name, fn)
@@ -249,9 +256,31 @@ def profiled():
     return _Profile()
 
 
+_replayed = 0          # kernel launches made by CUDA-graph replays (minibatch_graph.py): the library's counter does not see those
+
+
+def note_replayed_launches(n):
+    global _replayed
+    _replayed += int(n)
+
+
 def launch_count():
-    return int(lib().ppd_launch_count())
+    """Kernels launched so far: the library's own count of its launches plus those replayed from captured graphs."""
+    return int(lib().ppd_launch_count()) + _replayed
 
 
 def reset_launch_count():
+    global _replayed
+    _replayed = 0
     lib().ppd_reset_launch_count()
+
+
+def live_workspaces():
+    """The workspace buffers alive right now (a captured graph references them so that a later, larger request, which replaces
+    the cache entry, does not free memory the graph still points at)."""
+    return list(_workspaces.values())
+
+
+def profiling():
+    """True while a _lib.profiled() block is active (per-call CUDA events: graph replays would hide the calls from it)."""
+    return _profiling > 0

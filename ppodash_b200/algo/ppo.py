@@ -20,7 +20,11 @@ import torch
 from .. import _lib
 from .. import dist as ppd_dist
 from .._lib import check, lib
+from ..minibatch_graph import MinibatchGraphs
 from ..storage import FusedAdvantages
+
+GRAPH_DEFAULT = "1"
+GRAPH_MAX_ROWS = 8192
 
 
 class FusedClipAdam(torch.optim.Optimizer):
@@ -99,8 +103,11 @@ class PPO():
         self.last_grad_norm = None
         # gather minibatch i+1 on a side stream while minibatch i trains (update()); PPD_PREFETCH_GATHER=0 turns it off (A/B timing)
         self.prefetch_gather = os.environ.get("PPD_PREFETCH_GATHER", "1") != "0"
+        # one minibatch = two replayed CUDA graphs instead of ~190 launches from Python (minibatch_graph.py); single process only
+        self.use_cuda_graph = os.environ.get("PPD_GRAPH", GRAPH_DEFAULT) != "0"
         self._side = None
         self._gbufs = None
+        self._graphs = None
 
     def _gather_stream(self, dev):
         if self._side is None or self._side.device != torch.device(dev):
@@ -158,13 +165,26 @@ class PPO():
         envs_per_mb = rollouts.rewards.size(1) // self.num_mini_batch
         use_side = self.prefetch_gather and pol.is_recurrent and 16 * envs_per_mb <= 148 - 32
         side = self._gather_stream(dev) if use_side else None
-        if side is not None:
-            # two caller-owned observation buffers, used in turn: the gather of minibatch i+2 is queued behind an event of minibatch
-            # i+1's forward pass, i.e. behind every reader of minibatch i
-            rows = rollouts.rewards.size(0) * envs_per_mb
-            shape = (rows,) + tuple(getattr(rollouts, "policy_obs_shape", None) or rollouts.obs.shape[2:])
-            if self._gbufs is None or self._gbufs[0]["obs"].shape != shape or self._gbufs[0]["obs"].device != torch.device(dev):
-                self._gbufs = [{"obs": torch.empty(shape, dtype=torch.float32, device=dev)} for _ in range(2)]
+        # CUDA graphs: single process, default precision mode, and not while bench.py attributes time to C-ABI calls
+        # (and for minibatches small enough that launch overhead matters: at 65 536 rows the kernels run for milliseconds)
+        graphs = None
+        T_, N_ = rollouts.rewards.size(0), rollouts.rewards.size(1)
+        mb_rows = T_ * envs_per_mb if pol.is_recurrent else (T_ * N_) // self.num_mini_batch
+        if self.use_cuda_graph and world == 1 and eng.precision == "tf32x3" and mb_rows <= GRAPH_MAX_ROWS and not _lib.profiling():
+            if self._graphs is None or self._graphs.eng is not eng:
+                self._graphs = MinibatchGraphs(eng)
+            graphs = self._graphs
+        if side is not None or graphs is not None:
+            # caller-owned minibatch buffers ("slots"), used in turn.  Two when the gathers are prefetched: the gather of minibatch
+            # i+2 is queued behind an event of minibatch i+1's forward pass, i.e. behind every reader of minibatch i.  Without graphs
+            # only the observations live in them (no 100-MB block crosses streams through the allocator); a captured graph bakes
+            # the addresses of all nine tensors in, so then every field does.
+            T = rollouts.rewards.size(0)
+            if pol.is_recurrent:
+                rows, hrows = T * envs_per_mb, envs_per_mb
+            else:
+                rows = hrows = (T * rollouts.rewards.size(1)) // self.num_mini_batch
+            self._make_slots(rollouts, rows, hrows, 2 if side is not None else 1, graphs is not None, dev)
             rollouts.set_gather_buffers(self._gbufs)
         samples = all_samples()
 
@@ -186,17 +206,40 @@ class PPO():
 
         try:
             eng._fast_bind = True                 # the module tree was checked above; it does not change while update() runs
-            self._run_minibatches(fetch, main, side, eng, world, loss_acc, gnorm)
+            self._run_minibatches(fetch, main, side, eng, world, loss_acc, gnorm, graphs)
         finally:
             eng._fast_bind = False
-            if side is not None:
-                rollouts.set_gather_buffers(None)
+            rollouts.set_gather_buffers(None)
         num_updates = self.ppo_epoch * self.num_mini_batch
         vals = (loss_acc / num_updates).tolist()          # the only device->host sync of update()
         self.last_grad_norm = gnorm
         return vals[0], vals[1], vals[2]
 
-    def _run_minibatches(self, fetch, main, side, eng, world, loss_acc, gnorm):
+    def _make_slots(self, rollouts, rows, hrows, n, full, dev):
+        dev = torch.device(dev)
+        shape = (rows,) + tuple(getattr(rollouts, "policy_obs_shape", None) or rollouts.obs.shape[2:])
+        cur = self._gbufs
+        if cur is not None and len(cur) == n and cur[0]["obs"].shape == shape and cur[0]["obs"].device == dev \
+                and ("actions" in cur[0]) == full and (not full or cur[0]["hxs"].shape[0] == hrows):
+            return
+        if self._graphs is not None:
+            self._graphs.clear()                  # their graphs point into the buffers about to be dropped
+        self._gbufs = []
+        for _ in range(n):
+            b = {"obs": torch.empty(shape, dtype=torch.float32, device=dev)}
+            if full:
+                like = lambda t, r=rows: torch.empty((r,) + tuple(t.shape[2:]), dtype=t.dtype, device=dev)
+                b.update(vector_obs=like(rollouts.vector_obs), hxs=like(rollouts.recurrent_hidden_states, hrows),
+                         actions=like(rollouts.actions), value_preds=like(rollouts.value_preds), returns=like(rollouts.returns),
+                         masks=like(rollouts.masks), logp=like(rollouts.action_log_probs),
+                         adv=torch.empty(rows, 1, dtype=torch.float32, device=dev))
+            self._gbufs.append(b)
+
+    def _in_slot(self, sample):
+        p = sample[0].data_ptr()
+        return any(b["obs"].data_ptr() == p and "actions" in b for b in (self._gbufs or []))
+
+    def _run_minibatches(self, fetch, main, side, eng, world, loss_acc, gnorm, graphs=None):
         cur = fetch(first=True)
         while cur is not None:
             sample, ev = cur
@@ -206,13 +249,20 @@ class PPO():
                     if t is not None:
                         t.record_stream(main)         # allocated on the side stream, consumed on this one
             nxt = []
+            at_gru = None
             if side is not None:
                 def at_gru(_n=nxt):
                     e0 = torch.cuda.Event()
                     e0.record(main)
                     _n.append(fetch(after=e0))
-                eng.on_gru_forward = at_gru
             rows = sample[0].shape[0]
+            if graphs is not None and self._in_slot(sample):
+                graphs.run(sample, (float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef),
+                                    bool(self.use_clipped_value_loss), rows), at_gru)
+                self._after_minibatch(nxt, fetch, main, side, loss_acc, gnorm)
+                cur = nxt[0]
+                continue
+            eng.on_gru_forward = at_gru
             try:
                 if world > 1:
                     # two buckets, all-reduced asynchronously from the stream on which each becomes final: [fc.w, end) (FC, GRU,
@@ -230,13 +280,16 @@ class PPO():
                                         self.use_clipped_value_loss, global_rows=rows)
             finally:
                 eng.on_gru_forward = None
-            if not nxt:
-                # no recurrence in this network, or a chunked minibatch: gather behind the whole minibatch (the event keeps the side
-                # stream behind the readers of the buffer it is about to overwrite)
-                e1 = None
-                if side is not None:
-                    e1 = torch.cuda.Event()
-                    e1.record(main)
-                nxt.append(fetch(after=e1))
-            self.optimizer.step(loss_acc=loss_acc, grad_norm_out=gnorm)
+            self._after_minibatch(nxt, fetch, main, side, loss_acc, gnorm)
             cur = nxt[0]
+
+    def _after_minibatch(self, nxt, fetch, main, side, loss_acc, gnorm):
+        if not nxt:
+            # no recurrence in this network, or a chunked minibatch: gather behind the whole minibatch (the event keeps the side
+            # stream behind the readers of the buffer it is about to overwrite)
+            e1 = None
+            if side is not None:
+                e1 = torch.cuda.Event()
+                e1.record(main)
+            nxt.append(fetch(after=e1))
+        self.optimizer.step(loss_acc=loss_acc, grad_norm_out=gnorm)

@@ -299,11 +299,11 @@ class RolloutStorage(object):
         vobs_b = o.get("vector_obs") if "vector_obs" in o else self._out(rows, self.vector_obs)
         hrows = rows if mode == "ff" else E
         hxs_b = o.get("hxs") if "hxs" in o else self._out(hrows, self.recurrent_hidden_states)
-        act_b = self._out(rows, self.actions)
-        val_b = self._out(rows, self.value_preds)
-        ret_b = self._out(rows, self.returns)
-        msk_b = self._out(rows, self.masks)
-        lp_b = self._out(rows, self.action_log_probs)
+        act_b = o.get("actions") if "actions" in o else self._out(rows, self.actions)
+        val_b = o.get("value_preds") if "value_preds" in o else self._out(rows, self.value_preds)
+        ret_b = o.get("returns") if "returns" in o else self._out(rows, self.returns)
+        msk_b = o.get("masks") if "masks" in o else self._out(rows, self.masks)
+        lp_b = o.get("logp") if "logp" in o else self._out(rows, self.action_log_probs)
         d = GatherDesc()
         if self.obs_u8:
             # observations: uint8 frames -> normalised, stacked float32 rows (ppd_gather_obs_u8_*); the small fields follow below
@@ -331,13 +331,13 @@ class RolloutStorage(object):
         adv_b = None
         keep = None
         if isinstance(advantages, FusedAdvantages):
-            adv_b = torch.empty(rows, 1, dtype=torch.float32, device=dev)
+            adv_b = o.get("adv") if "adv" in o else torch.empty(rows, 1, dtype=torch.float32, device=dev)
             d.adv_stats, d.adv_out = ptr(advantages.stats, torch.float32), ptr(adv_b)
         elif advantages is not None:
             keep = advantages.detach()
             if keep.dtype != torch.float32 or not keep.is_contiguous():
                 keep = keep.float().contiguous()
-            adv_b = torch.empty(rows, 1, dtype=torch.float32, device=dev)
+            adv_b = o.get("adv") if "adv" in o else torch.empty(rows, 1, dtype=torch.float32, device=dev)
             d.adv, d.adv_out = ptr(keep), ptr(adv_b)
         if mode == "ff":
             rc = lib().ppd_gather_feed_forward(ctypes.byref(d), ptr(perm_dev, torch.int64), start, rows, T, N,
@@ -350,7 +350,8 @@ class RolloutStorage(object):
 
     def set_gather_buffers(self, buffers):
         """Caller-owned output buffers for the generators, used in rotation (None: allocate per minibatch, the default).  `buffers`:
-        list of dicts {"obs": float32 [rows, *policy obs shape]}.  algo.PPO gathers minibatch i+1 on a side stream while minibatch i
+        list of dicts {"obs": float32 [rows, *policy obs shape]} and, optionally, any of "vector_obs", "hxs", "actions", "value_preds",
+        "returns", "masks", "logp", "adv" (shapes as the generators yield them; fields left out are allocated per minibatch).  algo.PPO gathers minibatch i+1 on a side stream while minibatch i
         trains and hands two sets over, so that no 100-MB block crosses streams through the caching allocator."""
         self._gather_bufs = list(buffers) if buffers else None
         self._gather_buf_i = 0

@@ -278,3 +278,58 @@ def test_update_with_prefetched_gathers_is_bit_identical():
     assert o1 == o0 == o2
     for k in p0:
         assert torch.equal(p1[k], p0[k]) and torch.equal(p2[k], p0[k]), k
+
+
+@pytest.mark.parametrize("recurrent,prefetch", [(True, True), (True, False), (False, False)])
+def test_update_through_cuda_graphs_is_bit_identical(recurrent, prefetch):
+    """PPO.update with every minibatch replayed from captured CUDA graphs (minibatch_graph.py: graph A up to the GRU recurrence, the
+    next minibatch's gather queued behind it, graph B for the rest; one graph without a recurrence) launches the kernels of the eager
+    path with the same arguments: losses and parameters must not differ by a bit.  The third update changes clip_param (a by-value
+    kernel argument baked into the graphs): the minibatch is captured again, not replayed with the old value."""
+    T, N = 32, 8
+    C, V = (3, 15) if recurrent else (1, 0)
+    cfg = synthetic.RolloutConfig("t", T, N, C, V, 8, recurrent, 2, 4, 1e-4, 0.001)
+    roll = synthetic.make_rollout(cfg, seed=5, reset_prob=0.05)
+    results = []
+    for graph in (False, True):
+        torch.manual_seed(0)
+        pol = ppd.Policy((C, 84, 84), Discrete(8), base_kwargs={"recurrent": recurrent}, vector_obs_len=V).to(DEV)
+        pol.engine("tf32x3")
+        st = ppd.RolloutStorage(T, N, (C, 84, 84), [V], Discrete(8), 512)
+        for k in ppd.RolloutStorage._FIELDS:
+            getattr(st, k).copy_(roll[k])
+        st.to(DEV)
+        st.compute_returns(roll["next_value"].to(DEV), True, cfg.gamma, cfg.gae_lambda, False)
+        agent = ppd.algo.PPO(pol, cfg.clip_param, cfg.ppo_epoch, cfg.num_mini_batch, cfg.value_loss_coef, cfg.entropy_coef,
+                             lr=cfg.lr, eps=cfg.eps, max_grad_norm=cfg.max_grad_norm)
+        agent.prefetch_gather = prefetch
+        agent.use_cuda_graph = graph
+        torch.manual_seed(11)
+        out = [agent.update(st) for _ in range(2)]
+        agent.clip_param = 0.05
+        out.append(agent.update(st))
+        if graph:
+            g = agent._graphs
+            slots = 2 if (recurrent and prefetch) else 1
+            assert g.disabled is None, g.disabled
+            assert g.captures == 2 * slots, g.captures              # each slot once per clip_param value
+            # 8 minibatches per update; the first two of a new minibatch shape run eagerly, all others are replays
+            assert g.replays == 3 * 8 - 2, g.replays
+            assert all(len(e.graphs) == (2 if recurrent else 1) for e in g.entries.values())
+        else:
+            assert agent._graphs is None
+        # graphs off and on again: the minibatch buffers are rebuilt, the old graphs dropped and new ones captured
+        agent.use_cuda_graph = False
+        out.append(agent.update(st))
+        agent.use_cuda_graph = graph
+        out.append(agent.update(st))
+        if graph:
+            assert g.disabled is None, g.disabled
+            # (only the prefetching path keeps observation-only buffers while graphs are off; the others allocate per minibatch
+            # then and find their buffers -- and graphs -- unchanged afterwards)
+            assert (g.captures, len(g.entries)) == ((3 * slots, slots) if prefetch else (2 * slots, 2 * slots))
+        results.append((out, {k: v.clone() for k, v in pol.state_dict().items()}))
+    (o0, p0), (o1, p1) = results
+    assert o0 == o1
+    for k in p0:
+        assert torch.equal(p1[k], p0[k]), k
