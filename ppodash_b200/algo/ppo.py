@@ -105,6 +105,10 @@ class PPO():
         self.prefetch_gather = os.environ.get("PPD_PREFETCH_GATHER", "1") != "0"
         # one minibatch = two replayed CUDA graphs instead of ~190 launches from Python (minibatch_graph.py); single process only
         self.use_cuda_graph = os.environ.get("PPD_GRAPH", GRAPH_DEFAULT) != "0"
+        # all nine tensors of a minibatch live in buffers this object owns (graphs need that; without graphs it still saves eight
+        # allocations per minibatch on the gather stream and the allocator's cross-stream bookkeeping for them: -0.5 ms per update);
+        # PPD_STATIC_MINIBATCH=0: only the observations do, the small fields are allocated per minibatch (A/B timing)
+        self.static_minibatch = os.environ.get("PPD_STATIC_MINIBATCH", "1") != "0"
         self._side = None
         self._gbufs = None
         self._graphs = None
@@ -174,17 +178,17 @@ class PPO():
             if self._graphs is None or self._graphs.eng is not eng:
                 self._graphs = MinibatchGraphs(eng)
             graphs = self._graphs
-        if side is not None or graphs is not None:
+        own_slots = side is not None or graphs is not None
+        if own_slots:
             # caller-owned minibatch buffers ("slots"), used in turn.  Two when the gathers are prefetched: the gather of minibatch
-            # i+2 is queued behind an event of minibatch i+1's forward pass, i.e. behind every reader of minibatch i.  Without graphs
-            # only the observations live in them (no 100-MB block crosses streams through the allocator); a captured graph bakes
-            # the addresses of all nine tensors in, so then every field does.
+            # i+2 is queued behind an event of minibatch i+1's forward pass, i.e. behind every reader of minibatch i.  All nine
+            # tensors live in them: a captured graph bakes their addresses in, and no block crosses streams through the allocator.
             T = rollouts.rewards.size(0)
             if pol.is_recurrent:
                 rows, hrows = T * envs_per_mb, envs_per_mb
             else:
                 rows = hrows = (T * rollouts.rewards.size(1)) // self.num_mini_batch
-            self._make_slots(rollouts, rows, hrows, 2 if side is not None else 1, graphs is not None, dev)
+            self._make_slots(rollouts, rows, hrows, 2 if side is not None else 1, graphs is not None or self.static_minibatch, dev)
             rollouts.set_gather_buffers(self._gbufs)
         samples = all_samples()
 
@@ -209,7 +213,8 @@ class PPO():
             self._run_minibatches(fetch, main, side, eng, world, loss_acc, gnorm, graphs)
         finally:
             eng._fast_bind = False
-            rollouts.set_gather_buffers(None)
+            if own_slots:
+                rollouts.set_gather_buffers(None)
         num_updates = self.ppo_epoch * self.num_mini_batch
         vals = (loss_acc / num_updates).tolist()          # the only device->host sync of update()
         self.last_grad_norm = gnorm

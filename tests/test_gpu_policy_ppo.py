@@ -319,9 +319,9 @@ def test_update_through_cuda_graphs_is_bit_identical(recurrent, prefetch):
         else:
             assert agent._graphs is None
         # graphs off and on again: the minibatch buffers are rebuilt, the old graphs dropped and new ones captured
-        agent.use_cuda_graph = False
+        agent.use_cuda_graph, agent.static_minibatch = False, False
         out.append(agent.update(st))
-        agent.use_cuda_graph = graph
+        agent.use_cuda_graph, agent.static_minibatch = graph, True
         out.append(agent.update(st))
         if graph:
             assert g.disabled is None, g.disabled

@@ -1,5 +1,7 @@
 """A/B of PPO.update with and without CUDA graphs of the minibatch (ppodash_b200/minibatch_graph.py) in ONE process on one GPU:
-the bench workload (C2, uint8 storage), the same agent, `agent.use_cuda_graph` switched between blocks of steps.
+the bench workload (C2, uint8 storage), the same agent, `agent.use_cuda_graph` / `agent.static_minibatch` switched between
+blocks of steps (three modes: eager with the small minibatch fields allocated per minibatch, eager with all nine minibatch tensors in
+buffers PPO owns, graphs).
     python tools/graph_ab.py [--workload c2] [--steps 4] [--rounds 3]
 Prints one JSON line per block (device time per update from CUDA events, kernel launches per update and how many of them were
 issued from Python) and a summary."""
@@ -45,7 +47,10 @@ def main():
         torch.manual_seed(99)
         return agent.update(st)
 
-    def block(graph, n):
+    MODES = {"eager, small fields allocated per minibatch": (False, False), "eager": (False, True), "graphs": (True, True)}
+
+    def block(mode, n):
+        graph, agent.static_minibatch = MODES[mode]
         agent.use_cuda_graph = graph
         step()                                          # settle (captures on the first graph block)
         torch.cuda.synchronize()
@@ -59,21 +64,22 @@ def main():
         wall = time.perf_counter() - t0
         torch.cuda.synchronize()
         each = [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(n)]
-        return dict(graph=graph, ms=round(sum(each) / n, 3), each=each, wall_ms=round(1e3 * wall / n, 3), losses=list(out),
-                    launches=_lib.launch_count() // n, from_python=int(_lib.lib().ppd_launch_count()) // n)
+        g = agent._graphs
+        return dict(mode=mode, ms=round(sum(each) / n, 3), each=each, wall_ms=round(1e3 * wall / n, 3), losses=list(out),
+                    launches=_lib.launch_count() // n, from_python=int(_lib.lib().ppd_launch_count()) // n,
+                    capture_failed=g.disabled if g else None)
 
     for _ in range(2):
         step()
     res = []
     for r in range(a.rounds):
-        for graph in (False, True):
-            b = block(graph, a.steps)
+        for mode in MODES:
+            b = block(mode, a.steps)
             res.append(b)
             print(json.dumps(b), flush=True)
     g = agent._graphs
-
-    summary = dict(eager_ms=min(b["ms"] for b in res if not b["graph"]), graph_ms=min(b["ms"] for b in res if b["graph"]),
-                   captures=g.captures if g else 0, capture_failed=g.disabled if g else None)
+    summary = {m: [b["ms"] for b in res if b["mode"] == m] for m in MODES}
+    summary.update(captures=g.captures if g else 0, capture_failed=g.disabled if g else None)
     print(json.dumps(summary), flush=True)
 
 
