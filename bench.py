@@ -607,8 +607,9 @@ def run_b200(args, cfg):
         enabled=bool(agent.use_cuda_graph and mg is not None and mg.disabled is None),
         launches_issued_from_python_per_step=host_launches / args.steps, launches_replayed_per_step=(launches - host_launches) / args.steps,
         captures=mg.captures if mg else 0, capture_failed=mg.disabled if mg else None,
-        note="PPD_GRAPH=1: forward + loss + backward of a minibatch are two replayed CUDA graphs (ppodash_b200/minibatch_graph.py); the "
-             "gathers, clip + Adam and the returns scan are launched from Python; gpu_launches counts both kinds")
+        note="PPD_GRAPH=1 (off by default: measured 0.2-0.7 ms per update slower, DESIGN.md section 7): forward + loss + backward of a "
+             "minibatch are replayed CUDA graphs (ppodash_b200/minibatch_graph.py); the gathers, clip + Adam and the returns scan are "
+             "launched from Python; gpu_launches counts both kinds")
     if parity is not None:
         line["parity_check"] = parity
     if c5 is not None:

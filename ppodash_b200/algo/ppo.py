@@ -23,7 +23,7 @@ from .._lib import check, lib
 from ..minibatch_graph import MinibatchGraphs
 from ..storage import FusedAdvantages
 
-GRAPH_DEFAULT = "1"
+GRAPH_DEFAULT = "0"
 GRAPH_MAX_ROWS = 8192
 
 
@@ -103,8 +103,10 @@ class PPO():
         self.last_grad_norm = None
         # gather minibatch i+1 on a side stream while minibatch i trains (update()); PPD_PREFETCH_GATHER=0 turns it off (A/B timing)
         self.prefetch_gather = os.environ.get("PPD_PREFETCH_GATHER", "1") != "0"
-        # one minibatch = two replayed CUDA graphs instead of ~190 launches from Python (minibatch_graph.py); single process only
-        self.use_cuda_graph = os.environ.get("PPD_GRAPH", GRAPH_DEFAULT) != "0"
+        # one minibatch = replayed CUDA graphs instead of 36 launches from Python (minibatch_graph.py); single process only; opt-in
+        # (PPD_GRAPH=1): measured 0.2-0.7 ms per update slower on the device than the Python-issued launches
+        # (True / 1: two graphs, split where the recurrence starts; 2: one graph with an external event there, see MinibatchGraphs.single)
+        self.use_cuda_graph = {"0": False, "1": True}.get(os.environ.get("PPD_GRAPH", GRAPH_DEFAULT), 2)
         # all nine tensors of a minibatch live in buffers this object owns (graphs need that; without graphs it still saves eight
         # allocations per minibatch on the gather stream and the allocator's cross-stream bookkeeping for them: -0.5 ms per update);
         # PPD_STATIC_MINIBATCH=0: only the observations do, the small fields are allocated per minibatch (A/B timing)
@@ -178,6 +180,7 @@ class PPO():
             if self._graphs is None or self._graphs.eng is not eng:
                 self._graphs = MinibatchGraphs(eng)
             graphs = self._graphs
+            graphs.single = self.use_cuda_graph == 2
         own_slots = side is not None or graphs is not None
         if own_slots:
             # caller-owned minibatch buffers ("slots"), used in turn.  Two when the gathers are prefetched: the gather of minibatch
@@ -200,7 +203,8 @@ class PPO():
                 if first:
                     side.wait_stream(main)            # returns, advantage statistics, last update's writes
                 if after is not None:
-                    side.wait_event(after)
+                    for e in (after if isinstance(after, tuple) else (after,)):
+                        side.wait_event(e)
                 s = next(samples, None)
                 if s is None:
                     return None
@@ -256,10 +260,12 @@ class PPO():
             nxt = []
             at_gru = None
             if side is not None:
-                def at_gru(_n=nxt):
-                    e0 = torch.cuda.Event()
-                    e0.record(main)
-                    _n.append(fetch(after=e0))
+                def at_gru(events=None, _n=nxt):
+                    # events: what the gather has to wait for, when the caller has them already (MinibatchGraphs, one-graph mode)
+                    if events is None:
+                        events = torch.cuda.Event()
+                        events.record(main)
+                    _n.append(fetch(after=events))
             rows = sample[0].shape[0]
             if graphs is not None and self._in_slot(sample):
                 graphs.run(sample, (float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef),

@@ -20,6 +20,10 @@ gathers (their permutation offsets change) and, in data-parallel runs, everythin
 
 Replays launch exactly the kernels the eager path launches, with the same arguments: results are bit-identical
 (tests/test_gpu_policy_ppo.py::test_update_through_cuda_graphs_is_bit_identical).
+
+Measured on B200 at the PPO-Dash shape (tools/graph_ab.py, profiles/r2_minibatch_graphs.md): 196 instead of 2 500 launches issued
+from Python per update, and 0.2-0.7 ms per update MORE device time than the Python-issued launches (which keep ahead of the device
+anyway), with two graphs per minibatch or one.  Hence opt-in: PPD_GRAPH=1 (two graphs) / 2 (one), or agent.use_cuda_graph.
 """
 import warnings
 
@@ -31,7 +35,7 @@ WARM_MINIBATCHES = 2      # eager minibatches of a new shape before the first ca
 
 
 class _Entry:
-    __slots__ = ("graphs", "held", "launches", "out")
+    __slots__ = ("graphs", "held", "launches", "out", "ext")
 
 
 class MinibatchGraphs:
@@ -43,6 +47,9 @@ class MinibatchGraphs:
         self.cap = None          # the stream every capture runs on (per-stream kernel workspaces are keyed by it: one set for all graphs)
         self.replays = 0
         self.captures = 0
+        # single=True: ONE graph per minibatch; the point where the recurrence starts is an external event-record node
+        # (cudaEventRecordExternal) that the gather stream waits on from outside the graph.  Halves the graph launches.
+        self.single = False
         self.disabled = None     # reason, once a capture has failed: everything runs eagerly from then on
 
     def clear(self):
@@ -52,7 +59,8 @@ class MinibatchGraphs:
 
     def _keys(self, sample, hyper):
         eng = self.eng
-        shape_key = (eng.signature(), eng.overlap_wgrad, tuple(None if t is None else (tuple(t.shape), t.dtype) for t in sample))
+        shape_key = (eng.signature(), eng.overlap_wgrad, bool(self.single),
+                     tuple(None if t is None else (tuple(t.shape), t.dtype) for t in sample))
         return shape_key, (shape_key, hyper, tuple(None if t is None else t.data_ptr() for t in sample))
 
     def run(self, sample, hyper, between=None):
@@ -80,11 +88,20 @@ class MinibatchGraphs:
                 return
             self.entries[key] = ent
         self.replays += 1
-        ent.graphs[0].replay()
-        if between is not None:
-            between()
-        for g in ent.graphs[1:]:
-            g.replay()
+        if ent.ext is not None and between is not None:
+            # One graph.  Correctness of what `between` queues must not rest on how a wait issued after the launch sees the record
+            # node inside it, so it also gets an ordinary event recorded BEFORE the launch (= behind the previous minibatch, the last
+            # reader of the buffer the next gather overwrites); the external event only holds the gather back to the recurrence.
+            before = torch.cuda.Event()
+            before.record(torch.cuda.current_stream(eng.device))
+            ent.graphs[0].replay()
+            between((before, ent.ext))
+        else:
+            ent.graphs[0].replay()
+            if between is not None:
+                between()
+            for g in ent.graphs[1:]:
+                g.replay()
         _lib.note_replayed_launches(ent.launches)
 
     def _eager(self, sample, hyper, between, bufs):
@@ -127,7 +144,14 @@ class MinibatchGraphs:
             g, open_graph[0] = open_graph[0], None
             g.capture_end()
 
+        ext = [None]
+
         def split():
+            if self.single:
+                if ext[0] is None:
+                    ext[0] = torch.cuda.Event(external=True)
+                    ext[0].record(cap)                      # an event-record node of the graph
+                return
             # graph A ends where the recurrence starts (no side-stream work is open here: the forward pass runs on one stream)
             end()
             graphs.append(torch.cuda.CUDAGraph())
@@ -151,6 +175,7 @@ class MinibatchGraphs:
         main.wait_stream(cap)
         ent = _Entry()
         ent.graphs = graphs
+        ent.ext = ext[0]
         ent.out = out                                   # tensors allocated inside the capture (graph pool) stay referenced
         ent.held = _lib.live_workspaces()
         ent.launches = _lib.launch_count() - n0

@@ -291,7 +291,8 @@ def test_update_through_cuda_graphs_is_bit_identical(recurrent, prefetch):
     cfg = synthetic.RolloutConfig("t", T, N, C, V, 8, recurrent, 2, 4, 1e-4, 0.001)
     roll = synthetic.make_rollout(cfg, seed=5, reset_prob=0.05)
     results = []
-    for graph in (False, True):
+    # 2 = one graph per minibatch, the gather's trigger as an external event-record node (MinibatchGraphs.single)
+    for graph in ((False, True, 2) if recurrent else (False, True)):
         torch.manual_seed(0)
         pol = ppd.Policy((C, 84, 84), Discrete(8), base_kwargs={"recurrent": recurrent}, vector_obs_len=V).to(DEV)
         pol.engine("tf32x3")
@@ -315,7 +316,8 @@ def test_update_through_cuda_graphs_is_bit_identical(recurrent, prefetch):
             assert g.captures == 2 * slots, g.captures              # each slot once per clip_param value
             # 8 minibatches per update; the first two of a new minibatch shape run eagerly, all others are replays
             assert g.replays == 3 * 8 - 2, g.replays
-            assert all(len(e.graphs) == (2 if recurrent else 1) for e in g.entries.values())
+            assert all(len(e.graphs) == (2 if recurrent and graph is True else 1) for e in g.entries.values())
+            assert all((e.ext is not None) == (graph == 2) for e in g.entries.values())
         else:
             assert agent._graphs is None
         # graphs off and on again: the minibatch buffers are rebuilt, the old graphs dropped and new ones captured
@@ -329,7 +331,8 @@ def test_update_through_cuda_graphs_is_bit_identical(recurrent, prefetch):
             # then and find their buffers -- and graphs -- unchanged afterwards)
             assert (g.captures, len(g.entries)) == ((3 * slots, slots) if prefetch else (2 * slots, 2 * slots))
         results.append((out, {k: v.clone() for k, v in pol.state_dict().items()}))
-    (o0, p0), (o1, p1) = results
-    assert o0 == o1
-    for k in p0:
-        assert torch.equal(p1[k], p0[k]), k
+    o0, p0 = results[0]
+    for o1, p1 in results[1:]:
+        assert o0 == o1
+        for k in p0:
+            assert torch.equal(p1[k], p0[k]), k

@@ -47,7 +47,8 @@ def main():
         torch.manual_seed(99)
         return agent.update(st)
 
-    MODES = {"eager, small fields allocated per minibatch": (False, False), "eager": (False, True), "graphs": (True, True)}
+    MODES = {"eager, small fields allocated per minibatch": (False, False), "eager": (False, True), "graphs": (True, True),
+             "one graph": (2, True)}
 
     def block(mode, n):
         graph, agent.static_minibatch = MODES[mode]
