@@ -174,9 +174,12 @@ class PPO():
         # CUDA graphs: single process, default precision mode, and not while bench.py attributes time to C-ABI calls
         # (and for minibatches small enough that launch overhead matters: at 65 536 rows the kernels run for milliseconds)
         graphs = None
-        T_, N_ = rollouts.rewards.size(0), rollouts.rewards.size(1)
-        mb_rows = T_ * envs_per_mb if pol.is_recurrent else (T_ * N_) // self.num_mini_batch
-        if self.use_cuda_graph and world == 1 and eng.precision == "tf32x3" and mb_rows <= GRAPH_MAX_ROWS and not _lib.profiling():
+        T, N = rollouts.rewards.size(0), rollouts.rewards.size(1)
+        if pol.is_recurrent:
+            rows, hrows = T * envs_per_mb, envs_per_mb            # rows of a minibatch, rows of its hidden-state tensor
+        else:
+            rows = hrows = (T * N) // self.num_mini_batch
+        if self.use_cuda_graph and world == 1 and eng.precision == "tf32x3" and rows <= GRAPH_MAX_ROWS and not _lib.profiling():
             if self._graphs is None or self._graphs.eng is not eng:
                 self._graphs = MinibatchGraphs(eng)
             graphs = self._graphs
@@ -186,11 +189,6 @@ class PPO():
             # caller-owned minibatch buffers ("slots"), used in turn.  Two when the gathers are prefetched: the gather of minibatch
             # i+2 is queued behind an event of minibatch i+1's forward pass, i.e. behind every reader of minibatch i.  All nine
             # tensors live in them: a captured graph bakes their addresses in, and no block crosses streams through the allocator.
-            T = rollouts.rewards.size(0)
-            if pol.is_recurrent:
-                rows, hrows = T * envs_per_mb, envs_per_mb
-            else:
-                rows = hrows = (T * rollouts.rewards.size(1)) // self.num_mini_batch
             self._make_slots(rollouts, rows, hrows, 2 if side is not None else 1, graphs is not None or self.static_minibatch, dev)
             rollouts.set_gather_buffers(self._gbufs)
         samples = all_samples()
