@@ -3,7 +3,8 @@ launches and as many ctypes calls on three streams) as TWO replayed CUDA graphs.
 
 Why two: algo.PPO gathers minibatch i+1 on a side stream behind the point where minibatch i's GRU recurrence starts (the recurrence
 keeps 16 SMs per env busy and leaves the rest to the HBM-bound gather).  Graph A ends at that point, the caller queues the gather
-behind it (`between()`), graph B starts with the recurrence.  A network without a recurrence is one graph.
+behind it (`between()`), graph B starts with the recurrence.  A network without a recurrence is one graph.  `single = True`
+(PPD_GRAPH=2) keeps the whole minibatch in one graph and marks that point with an external event-record node instead.
 
 What a graph bakes in, and who keeps it valid:
   * the 9 tensors of the minibatch -- algo.PPO owns two sets of them ("slots") and the generators gather into them in turn
